@@ -1,0 +1,165 @@
+"""Python host of the bundle-adjustment path: a thin wrapper over the C ABI (include/argus_b200.h).
+
+``solve_motstr`` is the one-shot drop-in for ``sba_motstr_levmar_x`` + ``img_projsKDRTS_x/_jac_x``
+(sba-1.6p/sba_levmar.c:449-1428); ``BundleAdjuster`` keeps the problem resident in HBM (bench, parity hooks,
+multi-GPU).  Multi-GPU is one process per GPU: points (with all their observations) are block-partitioned over
+the ranks by ``shard_points`` and the only exchange is the all-reduce hook the C solver calls
+(``torch.distributed.all_reduce`` on NCCL).
+"""
+import ctypes
+import numpy as np
+
+from . import _lib
+
+DEFAULT_OPTS = (1e-3, 1e-12, 1e-12, 1e-12, 0.0)     # SBA_INIT_MU, SBA_STOP_THRESH x3, 0 (sba.h:63-64, eucsbademo.c:1552-1555)
+DEFAULT_ITMAX = 150                                  # MAXITER2 (sbaprojs.c:31, eucsbademo.c:1566)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def shard_points(n, world, rank, nobs_per_point=None):
+    """Contiguous block of points [lo, hi) owned by ``rank``.  With ``nobs_per_point`` the cut points balance
+    observations instead of points."""
+    if nobs_per_point is None:
+        lo = (n * rank) // world
+        hi = (n * (rank + 1)) // world
+        return int(lo), int(hi)
+    csum = np.concatenate([[0], np.cumsum(np.asarray(nobs_per_point, dtype=np.int64))])
+    total = csum[-1]
+    cuts = [int(np.searchsorted(csum, total * r / world, side="left")) for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, n
+    return cuts[rank], cuts[rank + 1]
+
+
+class BundleAdjuster:
+    """Problem resident on one GPU.  ``vmask`` (n x m), ``p`` = [16 m | 3 n], ``rot0`` (4 m), ``x`` (nobs x 2)."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.argus_ba_create(ctypes.byref(h), int(device), ctypes.c_void_p(stream or 0)), "argus_ba_create")
+        self.h = h
+        self.n = self.m = 0
+        self._cb = None
+        self._keep = None
+
+    def close(self):
+        if self.h:
+            self.lib.argus_ba_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_comm(self, rank, world, allreduce):
+        """``allreduce(ptr, count, op, stream)`` -> 0; see ``torch_allreduce_hook``."""
+        def _cb(user, buf, count, op, stream):
+            try:
+                return int(allreduce(buf, count, op, stream) or 0)
+            except Exception as e:      # never let an exception cross the C boundary
+                import sys
+                print("argus_gui_b200: all-reduce hook raised: %r" % (e,), file=sys.stderr)
+                return 1
+        self._cb = _lib.ALLREDUCE_FN(_cb)
+        _lib.check(self.lib.argus_ba_set_comm(self.h, int(rank), int(world), self._cb, None), "argus_ba_set_comm")
+
+    def upload(self, vmask, p, rot0, x, nccalib=0, ncdist=0, ncon=0, mcon=0):
+        vmask = np.ascontiguousarray(vmask, dtype=np.int8)
+        n, m = vmask.shape
+        p = np.ascontiguousarray(p, dtype=np.float64).ravel()
+        rot0 = np.ascontiguousarray(rot0, dtype=np.float64).ravel()
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        if p.size != 16 * m + 3 * n or rot0.size != 4 * m or x.size != 2 * int((vmask != 0).sum()):
+            raise ValueError("inconsistent BA problem sizes")
+        self.n, self.m = n, m
+        rc = self.lib.argus_ba_upload(self.h, n, int(ncon), m, int(mcon), _ptr(vmask), _ptr(p), _ptr(rot0), _ptr(x),
+                                      int(nccalib), int(ncdist))
+        _lib.check(rc, "argus_ba_upload")
+        return self
+
+    def reset(self):
+        _lib.check(self.lib.argus_ba_reset(self.h), "argus_ba_reset")
+
+    def solve(self, itmax=DEFAULT_ITMAX, opts=DEFAULT_OPTS, verbose=0, compat=True, profile=False):
+        opts = np.ascontiguousarray(opts, dtype=np.float64)
+        info = np.zeros(10)
+        flags = (_lib.COMPAT_SBA16 if compat else 0) | (_lib.PROFILE if profile else 0)
+        ret = self.lib.argus_ba_solve(self.h, int(itmax), int(verbose), _ptr(opts), _ptr(info), flags)
+        if ret < _lib.ARGUS_E_SBA:
+            _lib.check(ret, "argus_ba_solve")
+        return ret, info
+
+    def download(self):
+        p = np.zeros(16 * self.m + 3 * self.n)
+        _lib.check(self.lib.argus_ba_download(self.h, _ptr(p)), "argus_ba_download")
+        return p
+
+    def num_observations(self):
+        return int(self.lib.argus_ba_num_observations(self.h))
+
+    def profile(self):
+        cap = 32
+        names = (ctypes.c_char_p * cap)()
+        ms = (ctypes.c_double * cap)()
+        cnt = (ctypes.c_int64 * cap)()
+        k = self.lib.argus_ba_get_profile(self.h, names, ms, cnt, cap)
+        return {names[i].decode(): (ms[i], cnt[i]) for i in range(k)}
+
+    def project(self):
+        hx = np.zeros((self.num_observations(), 2))
+        _lib.check(self.lib.argus_ba_project(self.h, _ptr(hx)), "argus_ba_project")
+        return hx
+
+    def normal_equations(self, mu, mcon=0):
+        m, n = self.m, self.n
+        N = 16 * (m - mcon)
+        out = {"U": np.zeros((m, 16, 16)), "ea": np.zeros((m, 16)), "V": np.zeros((n, 6)), "eb": np.zeros((n, 3)),
+               "S": np.zeros((N, N)), "E": np.zeros(N), "dp": np.zeros(16 * m + 3 * n), "scal": np.zeros(8)}
+        rc = self.lib.argus_ba_normal_equations(self.h, float(mu), _ptr(out["U"]), _ptr(out["ea"]), _ptr(out["V"]), _ptr(out["eb"]),
+                                                _ptr(out["S"]), _ptr(out["E"]), _ptr(out["dp"]), _ptr(out["scal"]))
+        _lib.check(rc, "argus_ba_normal_equations")
+        return out
+
+
+def solve_motstr(vmask, p, rot0, x, nccalib=0, ncdist=0, itmax=DEFAULT_ITMAX, opts=DEFAULT_OPTS, ncon=0, mcon=0,
+                 verbose=0, compat=True):
+    """One-shot host-pointer call ``argus_ba_motstr_kdrts``.  Returns (p_new, info[10], retval)."""
+    lib = _lib.load()
+    vmask = np.ascontiguousarray(vmask, dtype=np.int8)
+    n, m = vmask.shape
+    p = np.array(p, dtype=np.float64, copy=True).ravel()
+    rot0 = np.ascontiguousarray(rot0, dtype=np.float64).ravel()
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    opts = np.ascontiguousarray(opts, dtype=np.float64)
+    info = np.zeros(10)
+    ret = lib.argus_ba_motstr_kdrts(n, int(ncon), m, int(mcon), _ptr(vmask), _ptr(p), _ptr(rot0), _ptr(x), int(nccalib), int(ncdist),
+                                    int(itmax), int(verbose), _ptr(opts), _ptr(info), _lib.COMPAT_SBA16 if compat else 0)
+    if ret < _lib.ARGUS_E_SBA:
+        _lib.check(ret, "argus_ba_motstr_kdrts")
+    return p, info, ret
+
+
+def torch_allreduce_hook(group=None):
+    """All-reduce hook backed by ``torch.distributed`` (NCCL on GPUs).  The C solver hands a device pointer; it is
+    wrapped without a copy and reduced on the solver's stream."""
+    import torch
+    import torch.distributed as dist
+
+    def hook(ptr, count, op, stream):
+        dev = torch.cuda.current_device()
+        # zero-copy view of the solver's device buffer
+        iface = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 3, "strides": None}
+
+        class _Wrap:
+            __cuda_array_interface__ = iface
+        t = torch.as_tensor(_Wrap(), device="cuda:%d" % dev)
+        ext = torch.cuda.ExternalStream(int(stream), device=dev)
+        with torch.cuda.stream(ext):
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX, group=group)
+        return 0
+    return hook

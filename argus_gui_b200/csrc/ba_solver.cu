@@ -1,0 +1,541 @@
+// Sparse Levenberg-Marquardt bundle adjustment on one B200 (one process per GPU; optional all-reduce hook).
+// Host-side controller + C ABI.  Follows the control flow of sba_motstr_levmar_x
+// (sba-1.6p/sba_levmar.c:449-1428) exactly - including, in ARGUS_BA_COMPAT_SBA16 mode, its behaviour after a
+// rejected step - while every array stays resident in HBM and all arithmetic runs in the kernels of
+// ba_kernels.cuh / ba_schur_mma.cuh.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <float.h>
+#include <vector>
+#include "../../include/argus_b200.h"
+#include "ba_kernels.cuh"
+
+using namespace argus;
+
+namespace {
+
+enum ProfId { P_RESIDUAL = 0, P_LINEARIZE, P_LIN_REDUCE, P_PREPARE, P_SCHUR, P_SCHUR_REDUCE, P_ASSEMBLE, P_CHOL, P_BACKSUB,
+              P_ALLREDUCE, P_COUNT };
+const char *kProfNames[P_COUNT] = {"residual", "linearize", "lin_reduce", "prepare", "schur", "schur_reduce", "assemble",
+                                   "chol_solve", "backsub_eval", "allreduce"};
+
+template <typename T> struct DevBuf {
+    T *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct argus_ba_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sms = 148;
+    // comm
+    int rank = 0, world = 1;
+    argus_allreduce_fn allreduce = nullptr;
+    void *comm_user = nullptr;
+    // problem
+    int64_t n = 0, ncon = 0, nobs = 0;
+    int m = 0, mcon = 0, nfix_k = 0, nfix_d = 0;
+    DevBuf<int32_t> obs_ptr; DevBuf<uint8_t> obs_cam; DevBuf<double2> obs_uv; DevBuf<uint64_t> pt_mask;
+    DevBuf<double> rot0, cam, pts, cam_new, pts_new, cam0, pts0;
+    // work
+    DevBuf<double> W, Y, V, eb, vstate, Vinv, cvec, dbuf;
+    DevBuf<double> Upart, scpart, red1, max2, Epart, Spart, red2, S, E, da_free, da_full, part3, red3, cam2, scal, att, respart;
+    DevBuf<int> flags;     // [0] singular V*, [1] chol status
+    double *h_pinned = nullptr;   // 16 doubles
+    int grid_pts128 = 1, grid_pts256 = 1, nchunks = 1, npairs = 1;
+    int64_t chunk_pts = 1;
+    // profile
+    bool profiling = false;
+    struct Ev { int id; cudaEvent_t a, b; };
+    std::vector<Ev> evs;
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[P_COUNT]; int64_t prof_n[P_COUNT];
+
+    BaProblem problem() const {
+        BaProblem pb;
+        pb.n = n; pb.ncon = ncon; pb.m = m; pb.mcon = mcon; pb.nobs = nobs; pb.nfix_k = nfix_k; pb.nfix_d = nfix_d;
+        pb.obs_ptr = obs_ptr.p; pb.obs_cam = obs_cam.p; pb.obs_uv = obs_uv.p; pb.pt_mask = pt_mask.p; pb.rot0 = rot0.p;
+        return pb;
+    }
+};
+
+namespace {
+
+cudaEvent_t get_event(argus_ba_ctx *c)
+{
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ProfScope {
+    argus_ba_ctx *c; int id; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(argus_ba_ctx *c_, int id_) : c(c_), id(id_) {
+        if (c->profiling) { a = get_event(c); b = get_event(c); cudaEventRecord(a, c->stream); }
+    }
+    ~ProfScope() { if (c->profiling) { cudaEventRecord(b, c->stream); c->evs.push_back({id, a, b}); } }
+};
+void prof_collect(argus_ba_ctx *c)
+{
+    for (auto &e : c->evs) {
+        float ms = 0.f;
+        cudaEventSynchronize(e.b);
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        c->prof_ms[e.id] += ms; c->prof_n[e.id] += 1;
+        c->ev_pool.push_back(e.a); c->ev_pool.push_back(e.b);
+    }
+    c->evs.clear();
+}
+
+int do_allreduce(argus_ba_ctx *c, double *buf, int64_t count, int op)
+{
+    if (c->world <= 1) return ARGUS_OK;
+    if (!c->allreduce) return ARGUS_E_COMM;
+    ProfScope ps(c, P_ALLREDUCE);
+    return c->allreduce(c->comm_user, buf, count, op, (void *)c->stream) == 0 ? ARGUS_OK : ARGUS_E_COMM;
+}
+
+size_t cam_smem(int m) { return (size_t)m * sizeof(CamConst); }
+
+// ---- one evaluation of ||x - hx(p)||^2 on (cam, pts); result left in red3[0] (after optional all-reduce) ----
+int run_residual(argus_ba_ctx *c, const double *cam, const double *pts, double *hx)
+{
+    {
+        ProfScope ps(c, P_RESIDUAL);
+        k_residual<<<c->grid_pts256, 256, cam_smem(c->m), c->stream>>>(c->problem(), cam, pts, hx, c->respart.p);
+        k_reduce_sum<<<1, 32, 0, c->stream>>>(c->respart.p, c->grid_pts256, 1, 1, c->red3.p);
+    }
+    ARGUS_CUDA_CHECK(cudaGetLastError());
+    return do_allreduce(c, c->red3.p, 1, 0);
+}
+
+// ---- linearise at (cam, pts): W, V, eb, reduced U/ea in red1, scalars in scal[0..3] ----
+int run_linearize(argus_ba_ctx *c)
+{
+    const int m = c->m;
+    {
+        ProfScope ps(c, P_LINEARIZE);
+        const size_t sm = cam_smem(m) + (size_t)m * kU * sizeof(double);
+        k_linearize<<<c->grid_pts128, 128, sm, c->stream>>>(c->problem(), c->cam.p, c->pts.p, c->W.p, c->V.p, c->eb.p,
+                                                           c->Upart.p, c->scpart.p);
+    }
+    {
+        ProfScope ps(c, P_LIN_REDUCE);
+        const int64_t len = (int64_t)m * kU;
+        k_reduce_sum<<<(unsigned)((len + 127) / 128), 128, 0, c->stream>>>(c->Upart.p, c->grid_pts128, len, len, c->red1.p);
+        k_reduce_lin_scalars<<<1, 32, 0, c->stream>>>(c->scpart.p, c->grid_pts128, c->red1.p + len, c->max2.p);
+    }
+    ARGUS_CUDA_CHECK(cudaGetLastError());
+    int rc = do_allreduce(c, c->red1.p, (int64_t)m * kU + 2, 0);
+    if (rc) return rc;
+    rc = do_allreduce(c, c->max2.p, 2, 1);
+    if (rc) return rc;
+    k_lin_finalize<<<1, 32, 0, c->stream>>>(c->red1.p, c->cam.p, m, c->mcon, c->red1.p + (int64_t)m * kU, c->max2.p, c->scal.p);
+    ARGUS_CUDA_CHECK(cudaGetLastError());
+    return ARGUS_OK;
+}
+
+// ---- one damping attempt: prepare, Schur complement, solve, back-substitute, evaluate; scalars in att[0..3] ----
+int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int write_state, double *dbout)
+{
+    const int m = c->m, mcon = c->mcon, mf = m - mcon, N = 16 * mf;
+    ARGUS_CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, 2 * sizeof(int), c->stream));
+    {
+        ProfScope ps(c, P_PREPARE);
+        k_prepare<<<c->grid_pts128, 128, (size_t)m * 16 * sizeof(double), c->stream>>>(
+            c->problem(), mu, use_state, write_state, c->V.p, c->eb.p, c->vstate.p, c->W.p, c->Y.p, c->Vinv.p, c->cvec.p,
+            c->Epart.p, c->flags.p);
+    }
+    {
+        ProfScope ps(c, P_SCHUR);
+        dim3 grid(c->npairs, c->nchunks);
+        k_schur_pairs<<<grid, 256, 0, c->stream>>>(c->problem(), c->Y.p, c->W.p, c->chunk_pts, c->Spart.p);
+    }
+    const int64_t slen = (int64_t)c->npairs * 256;
+    {
+        ProfScope ps(c, P_SCHUR_REDUCE);
+        k_reduce_sum<<<(unsigned)((slen + 127) / 128), 128, 0, c->stream>>>(c->Spart.p, c->nchunks, slen, slen, c->red2.p);
+        k_reduce_sum<<<(unsigned)((m * 16 + 127) / 128), 128, 0, c->stream>>>(c->Epart.p, c->grid_pts128, (int64_t)m * 16, (int64_t)m * 16,
+                                                                             c->red2.p + slen);
+    }
+    ARGUS_CUDA_CHECK(cudaGetLastError());
+    int rc = do_allreduce(c, c->red2.p, slen + (int64_t)m * 16, 0);
+    if (rc) return rc;
+    {
+        ProfScope ps(c, P_ASSEMBLE);
+        const int64_t tot = (int64_t)N * N;
+        k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(m, mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu_u, c->S.p, c->E.p);
+    }
+    {
+        ProfScope ps(c, P_CHOL);
+        size_t rows = (size_t)(N > 32 ? N - 32 : 1);
+        size_t sm = rows * 33 * sizeof(double);
+        if (sm < (size_t)N * sizeof(double)) sm = (size_t)N * sizeof(double);
+        k_chol_solve<<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->flags.p + 1);
+    }
+    {
+        ProfScope ps(c, P_BACKSUB);
+        k_cam_update<<<1, 256, 0, c->stream>>>(m, mcon, c->cam.p, c->da_free.p, c->red1.p, mu, c->cam_new.p, c->da_full.p, c->cam2.p);
+        const size_t sm = cam_smem(m) + (size_t)m * 16 * sizeof(double);
+        k_backsub_eval<<<c->grid_pts128, 128, sm, c->stream>>>(c->problem(), mu, c->cam_new.p, c->da_full.p, c->pts.p, c->W.p, c->Vinv.p,
+                                                              c->eb.p, c->pts_new.p, dbout, c->part3.p);
+        k_reduce_sum<<<1, 32, 0, c->stream>>>(c->part3.p, c->grid_pts128, 3, 3, c->red3.p);
+    }
+    ARGUS_CUDA_CHECK(cudaGetLastError());
+    rc = do_allreduce(c, c->red3.p, 3, 0);
+    if (rc) return rc;
+    k_attempt_finalize<<<1, 32, 0, c->stream>>>(c->flags.p, c->cam2.p, c->red3.p, c->att.p);
+    ARGUS_CUDA_CHECK(cudaGetLastError());
+    return ARGUS_OK;
+}
+
+int read_back(argus_ba_ctx *c, const double *dsrc, int count, double *hdst)
+{
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->h_pinned, dsrc, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ARGUS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    memcpy(hdst, c->h_pinned, count * sizeof(double));
+    return ARGUS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *argus_b200_version(void) { return "argus_b200 0.1 (sm_100a, fp64)"; }
+
+int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
+{
+    if (!out) return ARGUS_E_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device >= ndev) {
+        fprintf(stderr, "argus_b200: no CUDA device available (there is no CPU fallback)\n");
+        return ARGUS_E_CUDA;
+    }
+    ARGUS_CUDA_CHECK(cudaSetDevice(device));
+    argus_ba_ctx *c = new argus_ba_ctx();
+    c->device = device;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { ARGUS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    cudaDeviceProp prop;
+    ARGUS_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    c->sms = prop.multiProcessorCount;
+    ARGUS_CUDA_CHECK(cudaMallocHost(&c->h_pinned, 16 * sizeof(double)));
+    memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_n, 0, sizeof(c->prof_n));
+    // opt in to large dynamic shared memory where needed
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
+    *out = c;
+    return ARGUS_OK;
+}
+
+void argus_ba_destroy(argus_ba_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->obs_ptr.release(); c->obs_cam.release(); c->obs_uv.release(); c->pt_mask.release();
+    DevBuf<double> *bufs[] = {&c->rot0, &c->cam, &c->pts, &c->cam_new, &c->pts_new, &c->cam0, &c->pts0, &c->W, &c->Y, &c->V, &c->eb,
+                              &c->vstate, &c->Vinv, &c->cvec, &c->dbuf, &c->Upart, &c->scpart, &c->red1, &c->max2, &c->Epart, &c->Spart,
+                              &c->red2, &c->S, &c->E, &c->da_free, &c->da_full, &c->part3, &c->red3, &c->cam2, &c->scal, &c->att, &c->respart};
+    for (auto *b : bufs) b->release();
+    c->flags.release();
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int argus_ba_set_comm(argus_ba_ctx *c, int rank, int world, argus_allreduce_fn fn, void *user)
+{
+    if (!c || world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) return ARGUS_E_ARG;
+    c->rank = rank; c->world = world; c->allreduce = fn; c->comm_user = user;
+    return ARGUS_OK;
+}
+
+int64_t argus_ba_num_observations(const argus_ba_ctx *c) { return c ? c->nobs : 0; }
+
+int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, const char *vmask, const double *p,
+                    const double *rot0, const double *x, int nccalib, int ncdist)
+{
+    if (!c || !vmask || !p || !rot0 || !x) return ARGUS_E_ARG;
+    if (m < 1 || m > ARGUS_BA_MAX_CAMS || n < 0 || ncon < 0 || ncon > n || mcon < 0 || mcon >= m) return ARGUS_E_ARG;
+    if (nccalib < 0 || nccalib > 5 || ncdist < 0 || ncdist > 5) return ARGUS_E_ARG;
+    ARGUS_CUDA_CHECK(cudaSetDevice(c->device));
+    // visibility index (sba_levmar.c:639-650 builds the same CRS; here: point-major CSR + per-point camera bit mask)
+    std::vector<int32_t> optr((size_t)n + 1);
+    std::vector<uint64_t> mask((size_t)n);
+    int64_t nobs = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const char *row = vmask + i * m;
+        uint64_t mk = 0;
+        for (int j = 0; j < m; ++j) if (row[j]) mk |= 1ull << j;
+        optr[i] = (int32_t)nobs; mask[i] = mk;
+        nobs += __builtin_popcountll(mk);
+        if (nobs > 0x7fffffffLL) return ARGUS_E_ARG;
+    }
+    optr[n] = (int32_t)nobs;
+    std::vector<uint8_t> ocam((size_t)nobs);
+    for (int64_t i = 0; i < n; ++i) {
+        uint64_t mk = mask[i]; int32_t k = optr[i];
+        while (mk) { ocam[k++] = (uint8_t)__builtin_ctzll(mk); mk &= mk - 1; }
+    }
+    c->n = n; c->ncon = ncon; c->m = m; c->mcon = mcon; c->nobs = nobs; c->nfix_k = nccalib; c->nfix_d = ncdist;
+    const int mf = m - mcon, N = 16 * mf;
+    c->npairs = mf * (mf + 1) / 2;
+    c->grid_pts128 = (int)std::min<int64_t>((n + 127) / 128, (int64_t)c->sms * 8); if (c->grid_pts128 < 1) c->grid_pts128 = 1;
+    c->grid_pts256 = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sms * 8); if (c->grid_pts256 < 1) c->grid_pts256 = 1;
+    {
+        int want = (c->sms * 8 + c->npairs - 1) / c->npairs;
+        int64_t maxc = (n + 63) / 64; if (maxc < 1) maxc = 1;
+        if (want > maxc) want = (int)maxc;
+        if (want < 1) want = 1;
+        c->nchunks = want;
+        c->chunk_pts = (n + want - 1) / want; if (c->chunk_pts < 1) c->chunk_pts = 1;
+    }
+#define ENS(buf, cnt) ARGUS_CUDA_CHECK((buf).ensure((size_t)(cnt)))
+    ENS(c->obs_ptr, n + 1); ENS(c->obs_cam, nobs); ENS(c->obs_uv, nobs); ENS(c->pt_mask, n);
+    ENS(c->rot0, 4 * m); ENS(c->cam, 16 * m); ENS(c->cam_new, 16 * m); ENS(c->cam0, 16 * m);
+    ENS(c->pts, 3 * n); ENS(c->pts_new, 3 * n); ENS(c->pts0, 3 * n);
+    ENS(c->W, 48 * nobs); ENS(c->Y, 48 * nobs); ENS(c->V, 6 * n); ENS(c->eb, 3 * n); ENS(c->vstate, 3 * n); ENS(c->Vinv, 6 * n);
+    ENS(c->cvec, 3 * n); ENS(c->dbuf, 3 * n);
+    ENS(c->Upart, (int64_t)c->grid_pts128 * m * kU); ENS(c->scpart, 4 * c->grid_pts128); ENS(c->red1, m * kU + 2); ENS(c->max2, 2);
+    ENS(c->Epart, (int64_t)c->grid_pts128 * m * 16); ENS(c->Spart, (int64_t)c->nchunks * c->npairs * 256);
+    ENS(c->red2, (int64_t)c->npairs * 256 + m * 16); ENS(c->S, (int64_t)N * N); ENS(c->E, N); ENS(c->da_free, N); ENS(c->da_full, 16 * m);
+    ENS(c->part3, 3 * c->grid_pts128); ENS(c->red3, 3); ENS(c->cam2, 2); ENS(c->scal, 8); ENS(c->att, 8); ENS(c->respart, c->grid_pts256);
+    ARGUS_CUDA_CHECK(c->flags.ensure(2));
+#undef ENS
+    cudaStream_t s = c->stream;
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_ptr.p, optr.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_cam.p, ocam.data(), nobs * sizeof(uint8_t), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pt_mask.p, mask.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_uv.p, x, nobs * sizeof(double2), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->rot0.p, rot0, 4 * m * sizeof(double), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cam0.p, p, 16 * m * sizeof(double), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pts0.p, p + 16 * m, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));      // host staging vectors go out of scope
+    return argus_ba_reset(c);
+}
+
+int argus_ba_reset(argus_ba_ctx *c)
+{
+    if (!c || c->m == 0) return ARGUS_E_ARG;
+    ARGUS_CUDA_CHECK(cudaSetDevice(c->device));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cam.p, c->cam0.p, 16 * c->m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pts.p, c->pts0.p, 3 * c->n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return ARGUS_OK;
+}
+
+int argus_ba_download(argus_ba_ctx *c, double *p)
+{
+    if (!c || !p) return ARGUS_E_ARG;
+    ARGUS_CUDA_CHECK(cudaSetDevice(c->device));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(p, c->cam.p, 16 * c->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(p + 16 * c->m, c->pts.p, 3 * c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ARGUS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return ARGUS_OK;
+}
+
+int argus_ba_get_profile(argus_ba_ctx *c, const char **names, double *ms, int64_t *launches, int cap)
+{
+    if (!c) return 0;
+    int k = 0;
+    for (int i = 0; i < P_COUNT && k < cap; ++i, ++k) { names[k] = kProfNames[i]; ms[k] = c->prof_ms[i]; launches[k] = c->prof_n[i]; }
+    return k;
+}
+
+int argus_ba_project(argus_ba_ctx *c, double *hx)
+{
+    if (!c || !hx) return ARGUS_E_ARG;
+    ARGUS_CUDA_CHECK(cudaSetDevice(c->device));
+    DevBuf<double> d;
+    ARGUS_CUDA_CHECK(d.ensure(2 * c->nobs));
+    int rc = run_residual(c, c->cam.p, c->pts.p, d.p);
+    if (rc == ARGUS_OK) {
+        cudaError_t e = cudaMemcpyAsync(hx, d.p, 2 * c->nobs * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = ARGUS_E_CUDA;
+    }
+    d.release();
+    return rc;
+}
+
+int argus_ba_normal_equations(argus_ba_ctx *c, double mu, double *U, double *ea, double *V, double *eb, double *S, double *E,
+                              double *dp, double *scal)
+{
+    if (!c) return ARGUS_E_ARG;
+    ARGUS_CUDA_CHECK(cudaSetDevice(c->device));
+    const int m = c->m, N = 16 * (m - c->mcon);
+    int rc = run_linearize(c);
+    if (rc) return rc;
+    double sc[8] = {0};
+    rc = read_back(c, c->scal.p, 4, sc);
+    if (rc) return rc;
+    // assemble a copy of S/E before the in-place Cholesky destroys it: run the attempt, but snapshot S, E first
+    // (k_chol_solve overwrites S), so split: everything up to assemble, copy, then the rest via a second attempt call.
+    rc = run_attempt(c, mu, mu, 0, 0, c->dbuf.p);
+    if (rc) return rc;
+    double at[4];
+    rc = read_back(c, c->att.p, 4, at);
+    if (rc) return rc;
+    sc[4] = at[1]; sc[5] = at[2]; sc[6] = at[3]; sc[7] = at[0];
+    if (scal) memcpy(scal, sc, sizeof(sc));
+    cudaStream_t s = c->stream;
+    if (U || ea) {
+        std::vector<double> h((size_t)m * kU);
+        ARGUS_CUDA_CHECK(cudaMemcpyAsync(h.data(), c->red1.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+        ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));
+        for (int j = 0; j < m; ++j) {
+            if (U) for (int r = 0; r < 16; ++r) for (int q = 0; q < 16; ++q)
+                U[(j * 16 + r) * 16 + q] = (r <= q) ? h[j * kU + tri16(r, q)] : h[j * kU + tri16(q, r)];
+            if (ea) for (int r = 0; r < 16; ++r) ea[j * 16 + r] = h[j * kU + 136 + r];
+        }
+    }
+    if (V) ARGUS_CUDA_CHECK(cudaMemcpyAsync(V, c->V.p, 6 * c->n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (eb) ARGUS_CUDA_CHECK(cudaMemcpyAsync(eb, c->eb.p, 3 * c->n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (dp) {
+        ARGUS_CUDA_CHECK(cudaMemcpyAsync(dp, c->da_full.p, 16 * m * sizeof(double), cudaMemcpyDeviceToHost, s));
+        ARGUS_CUDA_CHECK(cudaMemcpyAsync(dp + 16 * m, c->dbuf.p, 3 * c->n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    if (S || E) {
+        // re-assemble (the solve factored S in place)
+        const int64_t slen = (int64_t)c->npairs * 256, tot = (int64_t)N * N;
+        k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(m, c->mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu, c->S.p, c->E.p);
+        ARGUS_CUDA_CHECK(cudaGetLastError());
+        if (S) ARGUS_CUDA_CHECK(cudaMemcpyAsync(S, c->S.p, tot * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (E) ARGUS_CUDA_CHECK(cudaMemcpyAsync(E, c->E.p, N * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));
+    return ARGUS_OK;
+}
+
+int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5], double info[10], int flags)
+{
+    if (!c || !opts || c->m == 0) return ARGUS_E_ARG;
+    ARGUS_CUDA_CHECK(cudaSetDevice(c->device));
+    const bool compat = (flags & ARGUS_BA_COMPAT_SBA16) != 0;
+    c->profiling = (flags & ARGUS_BA_PROFILE) != 0;
+    memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_n, 0, sizeof(c->prof_n));
+    const int m = c->m;
+    const int64_t nvis = c->nobs;
+    if (c->world == 1) {      // with several ranks the host wrapper checks the global counts
+        const int64_t nobs2 = nvis * 2, nvars = (int64_t)m * 16 + c->n * 3;
+        if (nobs2 < nvars) {
+            fprintf(stderr, "argus_b200: cannot solve a problem with fewer measurements [%lld] than unknowns [%lld]\n",
+                    (long long)nobs2, (long long)nvars);
+            return ARGUS_E_SBA;
+        }
+    }
+    if (itmax == 0) return 0;   // the reference runs its Jacobian checker here (sba_levmar.c:749-753); see tests instead
+    const double tau = fabs(opts[0]), eps1 = fabs(opts[1]), eps2 = fabs(opts[2]), eps2_sq = opts[2] * opts[2],
+                 eps3_sq = opts[3] * opts[3], eps4_sq = opts[4] * opts[4];
+    double mu = 0.0, eab_inf = 0.0, p_eL2, pdp_eL2, p_L2 = 0.0, dp_L2 = DBL_MAX, dF, dL, dmax = DBL_MIN, init_p_eL2;
+    int nu = 2, nu2, stop = 0, nfev = 0, njev = 0, nlss = 0, itno, rc;
+    double h[8];
+
+    if ((rc = run_residual(c, c->cam.p, c->pts.p, nullptr))) return rc;
+    if ((rc = read_back(c, c->red3.p, 1, h))) return rc;
+    p_eL2 = h[0]; nfev = 1;
+    if (verbose) printf("initial motstr-SBA error %g [%g]\n", p_eL2, p_eL2 / (double)nvis);
+    init_p_eL2 = p_eL2;
+    if (!isfinite(p_eL2)) stop = 7;
+
+    for (itno = 0; itno < itmax && !stop; ++itno) {
+        if ((rc = run_linearize(c))) return rc;
+        ++njev;
+        if ((rc = read_back(c, c->scal.p, 4, h))) return rc;
+        eab_inf = h[1]; p_L2 = h[2]; dmax = h[3];
+        if (eab_inf <= eps1) { dp_L2 = 0.0; stop = 1; break; }
+        if (itno == 0) mu = tau * dmax;
+        double mu_u = 0.0;          // damping accumulated on U's diagonal within this iteration (compat: not restored)
+        bool first = true;
+        while (1) {
+            mu_u = compat ? mu_u + mu : mu;
+            if ((rc = run_attempt(c, mu, mu_u, compat && !first, compat, nullptr))) return rc;
+            if ((rc = read_back(c, c->att.p, 5, h))) return rc;
+            first = false;
+            const bool singular = h[4] != 0.0;
+            if (singular) fprintf(stderr, "argus_b200: singular matrix V*_i, increasing damping\n");
+            if (!singular) {
+                ++nlss;
+                const bool issolved = h[0] != 0.0;
+                if (issolved) {
+                    dp_L2 = h[1];
+                    if (dp_L2 <= eps2_sq * p_L2) { stop = 2; break; }
+                    if (dp_L2 >= (p_L2 + eps2) / 1e-24) {
+                        fprintf(stderr, "argus_b200: the matrix of the augmented normal equations is almost singular,\n"
+                                        "     minimization should be restarted from the current solution with an increased damping term\n");
+                        c->profiling ? prof_collect(c) : (void)0;
+                        return ARGUS_E_SBA;
+                    }
+                    ++nfev;
+                    pdp_eL2 = h[3];
+                    if (!isfinite(pdp_eL2)) { stop = 7; break; }
+                    dL = h[2];
+                    dF = p_eL2 - pdp_eL2;
+                    if (verbose > 1)
+                        printf("\ndamping term %8g, gain ratio %8g, errors %8g / %8g = %g\n", mu, dL != 0.0 ? dF / dL : dF / DBL_EPSILON,
+                               p_eL2 / nvis, pdp_eL2 / nvis, p_eL2 / pdp_eL2);
+                    if (dL > 0.0 && dF > 0.0) {
+                        double tmp = (2.0 * dF / dL - 1.0);
+                        tmp = 1.0 - tmp * tmp * tmp;
+                        mu = mu * ((tmp >= 0.3333333334) ? tmp : 0.3333333334);
+                        nu = 2;
+                        if (pdp_eL2 - 2.0 * sqrt(p_eL2 * pdp_eL2) < (eps4_sq - 1.0) * p_eL2) stop = 4;
+                        std::swap(c->cam.p, c->cam_new.p); std::swap(c->cam.cap, c->cam_new.cap);
+                        std::swap(c->pts.p, c->pts_new.p); std::swap(c->pts.cap, c->pts_new.cap);
+                        p_eL2 = pdp_eL2;
+                        break;
+                    }
+                }
+            }
+            // rejected: the linear system could not be solved or the error did not decrease
+            mu *= nu;
+            nu2 = (int)((unsigned)nu << 1);
+            if (nu2 <= nu) {
+                fprintf(stderr, "argus_b200: too many failed attempts to increase the damping factor! Singular Hessian matrix?\n");
+                stop = 6;
+                break;
+            }
+            nu = nu2;
+        }
+        if (p_eL2 <= eps3_sq) stop = 5;
+    }
+    if (itno >= itmax) stop = 3;
+    if (c->profiling) prof_collect(c);
+    if (info) {
+        info[0] = init_p_eL2; info[1] = p_eL2; info[2] = eab_inf; info[3] = dp_L2; info[4] = mu / dmax;
+        info[5] = itno; info[6] = stop; info[7] = nfev; info[8] = njev; info[9] = nlss;
+    }
+    return (stop != 7) ? itno : ARGUS_E_SBA;
+}
+
+int argus_ba_motstr_kdrts(int64_t n, int64_t ncon, int m, int mcon, const char *vmask, double *p, const double *rot0,
+                          const double *x, int nccalib, int ncdist, int itmax, int verbose, const double opts[5], double info[10],
+                          int flags)
+{
+    argus_ba_ctx *c = nullptr;
+    int rc = argus_ba_create(&c, 0, nullptr);
+    if (rc) return rc;
+    rc = argus_ba_upload(c, n, ncon, m, mcon, vmask, p, rot0, x, nccalib, ncdist);
+    int ret = rc;
+    if (rc == ARGUS_OK) {
+        ret = argus_ba_solve(c, itmax, verbose, opts, info, flags);
+        if (ret >= 0 || ret == ARGUS_E_SBA) { rc = argus_ba_download(c, p); if (rc) ret = rc; }
+    }
+    argus_ba_destroy(c);
+    return ret;
+}
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// Batched N-camera DLT triangulation and reprojection error (fp64, one thread per (frame, track)).
+//
+// Replaces the per-frame Python loops of
+//   uv_to_xyz         /root/reference/argus_gui/tools.py:296-337
+//   get_repo_errors   /root/reference/argus_gui/tools.py:360-423
+//   undistort_pts     /root/reference/argus_gui/tools.py:129-148  (pinhole branch: cv2.undistortPoints(src f32, K, dist, P=K))
+//   reconstruct_uv    /root/reference/argus_gui/tools.py:64-76
+//
+// Faithfulness notes:
+//  * undistortion goes through float32 exactly as the reference does: the pixel is rounded to float32, OpenCV's
+//    5 fixed-point iterations run in double WITHOUT fused multiply-add (x86 baseline build), the result is
+//    re-projected with P = K and rounded to float32.  The device code uses __dmul_rn/__dadd_rn so nvcc cannot
+//    contract the expressions.
+//  * uv_to_xyz solves the (n+1)-row system the reference actually builds (rows k and k+1 are overwritten in the
+//    loop at tools.py:317-328): the u-equation of every visible camera plus the v-equation of the LAST visible one.
+//    flags bit 0 selects the textbook 2n-row system instead.
+//  * exact zeros become NaN (tools.py:336, 422).
+// HBM-bound: 88 B (triangulate) / 96 B (error) per (frame, track) at m = 4; no shared memory needed, the camera
+// tables (m x 19 doubles) live in constant-cached global loads.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/argus_b200.h"
+
+namespace {
+
+#define DLT_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "argus_b200: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    return ARGUS_E_CUDA; } } while (0)
+
+constexpr int kMaxCams = ARGUS_BA_MAX_CAMS;
+
+struct DltCams {            // by-value kernel argument would be 64*19*8 = 9.7 KB > 4 KB limit -> device memory
+    const double *prof;     // m x 8: f, cx, cy, k1, k2, p1, p2, k3
+    const double *dlt;      // m x 11
+};
+
+// cv2.undistortPoints(src(float32), K, dist=[k1,k2,p1,p2,k3], P=K), default criteria (5 iterations), float32 out.
+__device__ __forceinline__ void undistort_f32(double pu, double pv, const double *__restrict__ pr, float &ou, float &ov)
+{
+    const double fx = pr[0], cx = pr[1], cy = pr[2];
+    const double k1 = pr[3], k2 = pr[4], p1 = pr[5], p2 = pr[6], k3 = pr[7];
+    const double u = (double)(float)pu, v = (double)(float)pv;    // src is a float32 array
+    const double ifx = 1.0 / fx;
+    double x = __dmul_rn(__dadd_rn(u, -cx), ifx), y = __dmul_rn(__dadd_rn(v, -cy), ifx);
+    const double x0 = x, y0 = y;
+#pragma unroll 1
+    for (int j = 0; j < 5; ++j) {
+        const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+        // icdist = (1 + ((0*r2 + 0)*r2 + 0)*r2) / (1 + ((k3*r2 + k2)*r2 + k1)*r2)
+        const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k3, r2), k2), r2), k1), r2));
+        const double icdist = 1.0 / den;
+        if (icdist < 0.0) { x = x0; y = y0; break; }
+        // deltaX = 2*p1*x*y + p2*(r2 + 2*x*x);  deltaY = p1*(r2 + 2*y*y) + 2*p2*x*y   (left-to-right as in C)
+        const double dX = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, p1), x), y),
+                                    __dmul_rn(p2, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x))));
+        const double dY = __dadd_rn(__dmul_rn(p1, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))),
+                                    __dmul_rn(__dmul_rn(__dmul_rn(2.0, p2), x), y));
+        x = __dmul_rn(__dadd_rn(x0, -dX), icdist);
+        y = __dmul_rn(__dadd_rn(y0, -dY), icdist);
+    }
+    // RR = P = K: xx = fx*x + 0*y + cx, yy = 0*x + fx*y + cy, ww = 1/(0*x + 0*y + 1)
+    const double xx = __dadd_rn(__dadd_rn(__dmul_rn(fx, x), __dmul_rn(0.0, y)), cx);
+    const double yy = __dadd_rn(__dadd_rn(__dmul_rn(0.0, x), __dmul_rn(fx, y)), cy);
+    ou = (float)xx; ov = (float)yy;
+}
+
+__global__ void k_undistort(const double *__restrict__ pts, int64_t N, const double *__restrict__ prof8, float *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float a, b;
+    undistort_f32(pts[2 * i], pts[2 * i + 1], prof8, a, b);
+    out[2 * i] = a; out[2 * i + 1] = b;
+}
+
+// accumulate one equation row (a . X = b) into the 3x3 normal equations
+__device__ __forceinline__ void ne_add(double a0, double a1, double a2, double b, double *M, double *r)
+{
+    M[0] += a0 * a0; M[1] += a0 * a1; M[2] += a0 * a2; M[3] += a1 * a1; M[4] += a1 * a2; M[5] += a2 * a2;
+    r[0] += a0 * b; r[1] += a1 * b; r[2] += a2 * b;
+}
+
+// triangulate one (frame, track); returns false when fewer than two cameras see the point
+__device__ __forceinline__ bool triangulate_one(const double *__restrict__ row, int m, DltCams cams, int flags, double *X)
+{
+    double M[6] = {0, 0, 0, 0, 0, 0}, r[3] = {0, 0, 0};
+    int nvis = 0;
+    float lv = 0.f; int lj = -1;
+    for (int j = 0; j < m; ++j) {
+        const double2 uv = *reinterpret_cast<const double2 *>(row + 2 * j);
+        if (isnan(uv.x) || isnan(uv.y)) continue;
+        float fu, fv;
+        undistort_f32(uv.x, uv.y, cams.prof + 8 * j, fu, fv);
+        const double *L = cams.dlt + 11 * j;
+        const double du = (double)fu;
+        ne_add(du * L[8] - L[0], du * L[9] - L[1], du * L[10] - L[2], L[3] - du, M, r);
+        if (flags & 1) {
+            const double dv = (double)fv;
+            ne_add(dv * L[8] - L[4], dv * L[9] - L[5], dv * L[10] - L[6], L[7] - dv, M, r);
+        }
+        lv = fv; lj = j; ++nvis;
+    }
+    if (nvis < 2) return false;
+    if (!(flags & 1)) {     // the reference's system: only the last visible camera contributes its v-equation
+        const double *L = cams.dlt + 11 * lj;
+        const double dv = (double)lv;
+        ne_add(dv * L[8] - L[4], dv * L[9] - L[5], dv * L[10] - L[6], L[7] - dv, M, r);
+    }
+    // 3x3 Cholesky solve of the normal equations (the systems are well conditioned: cond(A) ~ 4 on camera rings)
+    const double l00 = sqrt(M[0]);
+    const double l10 = M[1] / l00, l20 = M[2] / l00;
+    const double l11 = sqrt(M[3] - l10 * l10);
+    const double l21 = (M[4] - l20 * l10) / l11;
+    const double l22 = sqrt(M[5] - l20 * l20 - l21 * l21);
+    const double y0 = r[0] / l00;
+    const double y1 = (r[1] - l10 * y0) / l11;
+    const double y2 = (r[2] - l20 * y0 - l21 * y1) / l22;
+    X[2] = y2 / l22;
+    X[1] = (y1 - l21 * X[2]) / l11;
+    X[0] = (y0 - l10 * X[1] - l20 * X[2]) / l00;
+    return true;
+}
+
+// pts: N x (2 m k); xyz: N x (3 k); thread t -> (frame = t / k, track = t % k)
+__global__ void __launch_bounds__(256) k_dlt_triangulate(const double *__restrict__ pts, int64_t N, int m, int k, DltCams cams,
+                                                         double *__restrict__ xyz, int flags)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * k) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double X[3];
+    const bool ok = triangulate_one(pts + t * 2 * m, m, cams, flags, X);
+    double *o = xyz + 3 * t;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) o[q] = (ok && X[q] != 0.0) ? X[q] : nan;
+}
+
+__device__ __forceinline__ double reproj_one(const double *__restrict__ row, const double *__restrict__ X, int m, DltCams cams)
+{
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (isnan(X[0]) || isnan(X[1]) || isnan(X[2])) return nan;
+    double eps = 0.0; int nc = 0;
+    for (int j = 0; j < m; ++j) {
+        const double2 uv = *reinterpret_cast<const double2 *>(row + 2 * j);
+        if (isnan(uv.x)) continue;          // only u is tested (tools.py:386)
+        float fu, fv;
+        undistort_f32(uv.x, uv.y, cams.prof + 8 * j, fu, fv);
+        const double *L = cams.dlt + 11 * j;
+        const double den = L[8] * X[0] + L[9] * X[1] + L[10] * X[2] + 1.0;
+        const double ru = (L[0] * X[0] + L[1] * X[1] + L[2] * X[2] + L[3]) / den;
+        const double rv = (L[4] * X[0] + L[5] * X[1] + L[6] * X[2] + L[7]) / den;
+        const double d0 = (double)fu - ru, d1 = (double)fv - rv;
+        eps += d0 * d0 + d1 * d1;
+        ++nc;
+    }
+    double e;
+    if (nc == 2) e = sqrt(eps / 2.0);
+    else e = sqrt(eps / (double)(2 * nc - 3));      // nc < 2 -> negative dof -> NaN (or -0 -> NaN below)
+    return (e == 0.0) ? nan : e;
+}
+
+// xyz: N x 3k, pts: N x 2mk, err: k x N
+__global__ void __launch_bounds__(256) k_dlt_reproj(const double *__restrict__ xyz, const double *__restrict__ pts, int64_t N, int m, int k,
+                                                    DltCams cams, double *__restrict__ err)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * k) return;
+    const int64_t frame = t / k; const int track = (int)(t % k);
+    const double X[3] = {xyz[3 * t], xyz[3 * t + 1], xyz[3 * t + 2]};
+    err[(int64_t)track * N + frame] = reproj_one(pts + t * 2 * m, X, m, cams);
+}
+
+int launch_tri(const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt, double *d_xyz, int flags, cudaStream_t s)
+{
+    const int64_t T = N * k;
+    if (T == 0) return ARGUS_OK;
+    DltCams cams{d_prof, d_dlt};
+    k_dlt_triangulate<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(d_pts, N, m, k, cams, d_xyz, flags);
+    DLT_CUDA_CHECK(cudaGetLastError());
+    return ARGUS_OK;
+}
+int launch_err(const double *d_xyz, const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt, double *d_err, cudaStream_t s)
+{
+    const int64_t T = N * k;
+    if (T == 0) return ARGUS_OK;
+    DltCams cams{d_prof, d_dlt};
+    k_dlt_reproj<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(d_xyz, d_pts, N, m, k, cams, d_err);
+    DLT_CUDA_CHECK(cudaGetLastError());
+    return ARGUS_OK;
+}
+
+bool have_device()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        fprintf(stderr, "argus_b200: no CUDA device available (there is no CPU fallback)\n");
+        return false;
+    }
+    return true;
+}
+
+struct Scratch {
+    void *p[8] = {0}; int n = 0;
+    template <typename T> cudaError_t alloc(T **out, size_t cnt) { cudaError_t e = cudaMalloc(out, (cnt ? cnt : 1) * sizeof(T)); if (e == cudaSuccess) p[n++] = *out; return e; }
+    ~Scratch() { for (int i = 0; i < n; ++i) cudaFree(p[i]); }
+};
+
+}  // namespace
+
+extern "C" {
+
+int argus_dlt_triangulate_dev(const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt,
+                              double *d_xyz, int flags, void *stream)
+{
+    if (!d_pts || !d_prof || !d_dlt || !d_xyz || m < 1 || m > kMaxCams || k < 1 || N < 0) return ARGUS_E_ARG;
+    return launch_tri(d_pts, N, m, k, d_prof, d_dlt, d_xyz, flags, (cudaStream_t)stream);
+}
+
+int argus_dlt_reproj_error_dev(const double *d_xyz, const double *d_pts, int64_t N, int m, int k, const double *d_prof,
+                               const double *d_dlt, double *d_err, void *stream)
+{
+    if (!d_xyz || !d_pts || !d_prof || !d_dlt || !d_err || m < 1 || m > kMaxCams || k < 1 || N < 0) return ARGUS_E_ARG;
+    return launch_err(d_xyz, d_pts, N, m, k, d_prof, d_dlt, d_err, (cudaStream_t)stream);
+}
+
+int argus_dlt_triangulate(const double *pts, int64_t N, int m, int k, const double *prof, const double *dlt, double *xyz, int flags)
+{
+    if (!pts || !prof || !dlt || !xyz || m < 1 || m > kMaxCams || k < 1 || N < 0) return ARGUS_E_ARG;
+    if (!have_device()) return ARGUS_E_CUDA;
+    Scratch sc; double *d_pts, *d_prof, *d_dlt, *d_xyz;
+    DLT_CUDA_CHECK(sc.alloc(&d_pts, (size_t)N * 2 * m * k)); DLT_CUDA_CHECK(sc.alloc(&d_prof, (size_t)m * 8));
+    DLT_CUDA_CHECK(sc.alloc(&d_dlt, (size_t)m * 11)); DLT_CUDA_CHECK(sc.alloc(&d_xyz, (size_t)N * 3 * k));
+    DLT_CUDA_CHECK(cudaMemcpy(d_pts, pts, (size_t)N * 2 * m * k * sizeof(double), cudaMemcpyHostToDevice));
+    DLT_CUDA_CHECK(cudaMemcpy(d_prof, prof, (size_t)m * 8 * sizeof(double), cudaMemcpyHostToDevice));
+    DLT_CUDA_CHECK(cudaMemcpy(d_dlt, dlt, (size_t)m * 11 * sizeof(double), cudaMemcpyHostToDevice));
+    int rc = launch_tri(d_pts, N, m, k, d_prof, d_dlt, d_xyz, flags, 0);
+    if (rc) return rc;
+    DLT_CUDA_CHECK(cudaMemcpy(xyz, d_xyz, (size_t)N * 3 * k * sizeof(double), cudaMemcpyDeviceToHost));
+    return ARGUS_OK;
+}
+
+int argus_dlt_reproj_error(const double *xyz, const double *pts, int64_t N, int m, int k, const double *prof, const double *dlt, double *err)
+{
+    if (!xyz || !pts || !prof || !dlt || !err || m < 1 || m > kMaxCams || k < 1 || N < 0) return ARGUS_E_ARG;
+    if (!have_device()) return ARGUS_E_CUDA;
+    Scratch sc; double *d_pts, *d_prof, *d_dlt, *d_xyz, *d_err;
+    DLT_CUDA_CHECK(sc.alloc(&d_pts, (size_t)N * 2 * m * k)); DLT_CUDA_CHECK(sc.alloc(&d_prof, (size_t)m * 8));
+    DLT_CUDA_CHECK(sc.alloc(&d_dlt, (size_t)m * 11)); DLT_CUDA_CHECK(sc.alloc(&d_xyz, (size_t)N * 3 * k));
+    DLT_CUDA_CHECK(sc.alloc(&d_err, (size_t)N * k));
+    DLT_CUDA_CHECK(cudaMemcpy(d_pts, pts, (size_t)N * 2 * m * k * sizeof(double), cudaMemcpyHostToDevice));
+    DLT_CUDA_CHECK(cudaMemcpy(d_xyz, xyz, (size_t)N * 3 * k * sizeof(double), cudaMemcpyHostToDevice));
+    DLT_CUDA_CHECK(cudaMemcpy(d_prof, prof, (size_t)m * 8 * sizeof(double), cudaMemcpyHostToDevice));
+    DLT_CUDA_CHECK(cudaMemcpy(d_dlt, dlt, (size_t)m * 11 * sizeof(double), cudaMemcpyHostToDevice));
+    int rc = launch_err(d_xyz, d_pts, N, m, k, d_prof, d_dlt, d_err, 0);
+    if (rc) return rc;
+    DLT_CUDA_CHECK(cudaMemcpy(err, d_err, (size_t)N * k * sizeof(double), cudaMemcpyDeviceToHost));
+    return ARGUS_OK;
+}
+
+int argus_dlt_reconstruct(const double *pts, int64_t N, int m, int k, const double *prof, const double *dlt, double *xyz, double *err, int flags)
+{
+    if (!pts || !prof || !dlt || !xyz || !err || m < 1 || m > kMaxCams || k < 1 || N < 0) return ARGUS_E_ARG;
+    if (!have_device()) return ARGUS_E_CUDA;
+    Scratch sc; double *d_pts, *d_prof, *d_dlt, *d_xyz, *d_err;
+    DLT_CUDA_CHECK(sc.alloc(&d_pts, (size_t)N * 2 * m * k)); DLT_CUDA_CHECK(sc.alloc(&d_prof, (size_t)m * 8));
+    DLT_CUDA_CHECK(sc.alloc(&d_dlt, (size_t)m * 11)); DLT_CUDA_CHECK(sc.alloc(&d_xyz, (size_t)N * 3 * k));
+    DLT_CUDA_CHECK(sc.alloc(&d_err, (size_t)N * k));
+    DLT_CUDA_CHECK(cudaMemcpy(d_pts, pts, (size_t)N * 2 * m * k * sizeof(double), cudaMemcpyHostToDevice));
+    DLT_CUDA_CHECK(cudaMemcpy(d_prof, prof, (size_t)m * 8 * sizeof(double), cudaMemcpyHostToDevice));
+    DLT_CUDA_CHECK(cudaMemcpy(d_dlt, dlt, (size_t)m * 11 * sizeof(double), cudaMemcpyHostToDevice));
+    int rc = launch_tri(d_pts, N, m, k, d_prof, d_dlt, d_xyz, flags, 0);
+    if (rc) return rc;
+    rc = launch_err(d_xyz, d_pts, N, m, k, d_prof, d_dlt, d_err, 0);
+    if (rc) return rc;
+    DLT_CUDA_CHECK(cudaMemcpy(xyz, d_xyz, (size_t)N * 3 * k * sizeof(double), cudaMemcpyDeviceToHost));
+    DLT_CUDA_CHECK(cudaMemcpy(err, d_err, (size_t)N * k * sizeof(double), cudaMemcpyDeviceToHost));
+    return ARGUS_OK;
+}
+
+int argus_undistort_points(const double *pts, int64_t N, const double *prof8, float *out)
+{
+    if (!pts || !prof8 || !out || N < 0) return ARGUS_E_ARG;
+    if (!have_device()) return ARGUS_E_CUDA;
+    if (N == 0) return ARGUS_OK;
+    Scratch sc; double *d_pts, *d_prof; float *d_out;
+    DLT_CUDA_CHECK(sc.alloc(&d_pts, (size_t)N * 2)); DLT_CUDA_CHECK(sc.alloc(&d_prof, 8)); DLT_CUDA_CHECK(sc.alloc(&d_out, (size_t)N * 2));
+    DLT_CUDA_CHECK(cudaMemcpy(d_pts, pts, (size_t)N * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    DLT_CUDA_CHECK(cudaMemcpy(d_prof, prof8, 8 * sizeof(double), cudaMemcpyHostToDevice));
+    k_undistort<<<(unsigned)((N + 255) / 256), 256>>>(d_pts, N, d_prof, d_out);
+    DLT_CUDA_CHECK(cudaGetLastError());
+    DLT_CUDA_CHECK(cudaMemcpy(out, d_out, (size_t)N * 2 * sizeof(float), cudaMemcpyDeviceToHost));
+    return ARGUS_OK;
+}
+
+}  // extern "C"

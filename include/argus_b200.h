@@ -1,0 +1,126 @@
+/* argus_b200.h - C ABI of the B200-native bundle-adjustment + DLT hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch / C++ types) and is what a
+ * binding on the reference side (python-sba's ctypes layer, or argus_gui/tools.py) would bind instead of
+ * the reference's own native layer.  INTEGRATION.md shows those bindings.
+ *
+ * Reference interfaces replaced (R/ = /root/reference, SBA/ = inside
+ * R/argus_gui/resources/sba_lib_sources.tar.gz, directory sba-1.6p/):
+ *
+ *   argus_ba_motstr_kdrts      <- sba_motstr_levmar_x           SBA/sba.h:111-116, SBA/sba_levmar.c:449-1428
+ *                                 with func/fjac = img_projsKDRTS_x / img_projsKDRTS_jac_x
+ *                                 (SBA/libsbaprojs/sbaprojs.h:113-114, sbaprojs.c:1135-1250) and
+ *                                 adata = struct globs_ {rot0params, nccalib, ncdist, cnp=16, pnp=3, mnp=2}
+ *                                 (sbaprojs.h:123-156); call site R/argus_gui/sbaDriver.py:292 through
+ *                                 python-sba's sba.SparseBundleAdjust.
+ *   argus_dlt_triangulate      <- uv_to_xyz                     R/argus_gui/tools.py:296-337
+ *   argus_dlt_reproj_error     <- get_repo_errors               R/argus_gui/tools.py:360-423
+ *   argus_undistort_points     <- undistort_pts (pinhole)       R/argus_gui/tools.py:129-148
+ *
+ * Ownership: the caller owns every array; outputs are written into caller-allocated memory.  No entry point
+ * calls exit(); errors are negative return codes (ARGUS_E_*).  There is no CPU fallback: without a CUDA
+ * device every compute entry point returns ARGUS_E_CUDA.
+ */
+#ifndef ARGUS_B200_H_
+#define ARGUS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARGUS_OK            0
+#define ARGUS_E_SBA        -1   /* == SBA_ERROR (SBA/sba.h:62): the reference's failure return            */
+#define ARGUS_E_CUDA       -2   /* CUDA runtime error / no device                                         */
+#define ARGUS_E_ARG        -3   /* bad argument (m > 64, null pointer, ...)                               */
+#define ARGUS_E_COMM       -4   /* the all-reduce callback reported an error                              */
+
+#define ARGUS_BA_CNP 16   /* camera parameters: fu,u0,v0,ar,s | k1,k2,p1,p2,k3 | local rot (3) | t (3) */
+#define ARGUS_BA_PNP 3
+#define ARGUS_BA_MNP 2
+#define ARGUS_BA_MAX_CAMS 64
+
+/* flags for argus_ba_solve / argus_ba_motstr_kdrts */
+#define ARGUS_BA_COMPAT_SBA16  1  /* emulate sba 1.6's damping behaviour after a rejected step: U/V diagonals are
+                                     not restored (SBA/sba_levmar.c:1339-1353 is #if 0) and V's diagonal holds the
+                                     inverse's diagonal (SBA/sba_lapack.c:1118-1121).  Without it the diagonals are
+                                     restored (textbook LM). */
+#define ARGUS_BA_PROFILE       2  /* record per-kernel CUDA-event times (argus_ba_get_profile)             */
+
+typedef struct argus_ba_ctx argus_ba_ctx;
+
+/* All-reduce hook for the multi-GPU path (one process per GPU).  `buf` is DEVICE memory holding `count`
+ * doubles; op 0 = sum, 1 = max; `stream` is the cudaStream_t the solver enqueues on - the hook must order
+ * the collective after work already enqueued on it and make later work on it wait for the result
+ * (torch.distributed.all_reduce issued under torch.cuda.stream(ExternalStream(stream)) does exactly that).
+ * Return 0 on success. */
+typedef int (*argus_allreduce_fn)(void *user, double *buf, int64_t count, int op, void *stream);
+
+/* ---- one-shot, host pointers: the drop-in for sba_motstr_levmar_x + img_projsKDRTS_x/_jac_x ----
+ * n, ncon, m, mcon, vmask (n x m, non-zero = visible), p ([16 per camera | 3 per point], updated in place),
+ * x (2 per visible projection, point-major, cameras ascending), itmax, verbose, opts[5], info[10]: exactly
+ * the reference's arguments (SBA/sba_levmar.c:449-518).  rot0 (4 per camera, scalar first), nccalib, ncdist:
+ * the fields of struct globs_.  cnp/pnp/mnp are fixed at 16/3/2 and covx is not supported (Argus passes NULL).
+ * Returns the number of iterations (>= 0) or ARGUS_E_*; info[] as the reference fills it. */
+int argus_ba_motstr_kdrts(int64_t n, int64_t ncon, int m, int mcon, const char *vmask, double *p,
+                          const double *rot0, const double *x, int nccalib, int ncdist,
+                          int itmax, int verbose, const double opts[5], double info[10], int flags);
+
+/* ---- resident-data interface (what the one-shot call is built from; used by bench.py and the multi-GPU host) ---- */
+int  argus_ba_create(argus_ba_ctx **ctx, int device, void *stream /* cudaStream_t or NULL */);
+void argus_ba_destroy(argus_ba_ctx *ctx);
+/* rank/world and the hook; world == 1 (default) needs no hook.  ncon/mcon passed to upload are LOCAL counts. */
+int  argus_ba_set_comm(argus_ba_ctx *ctx, int rank, int world, argus_allreduce_fn fn, void *user);
+/* copy a problem (or this rank's shard of the points, with all cameras) to the device and build the indices */
+int  argus_ba_upload(argus_ba_ctx *ctx, int64_t n, int64_t ncon, int m, int mcon, const char *vmask,
+                     const double *p, const double *rot0, const double *x, int nccalib, int ncdist);
+/* restore the parameter vector uploaded last (device-side copy), e.g. between timed repetitions */
+int  argus_ba_reset(argus_ba_ctx *ctx);
+int  argus_ba_solve(argus_ba_ctx *ctx, int itmax, int verbose, const double opts[5], double info[10], int flags);
+int  argus_ba_download(argus_ba_ctx *ctx, double *p);
+int64_t argus_ba_num_observations(const argus_ba_ctx *ctx);
+
+/* profile of the last solve: names[i] (static strings), total ms and launch count per kernel; returns the
+ * number of entries written (<= cap). */
+int  argus_ba_get_profile(argus_ba_ctx *ctx, const char **names, double *ms, int64_t *launches, int cap);
+
+/* ---- parity hooks (the pieces of one LM attempt, for tests against the oracle) ---- */
+/* hx (2 per projection) at the resident p  (img_projsKDRTS_x) */
+int  argus_ba_project(argus_ba_ctx *ctx, double *hx);
+/* One linearisation + one damping attempt at the resident p with damping mu.  Any output may be NULL.
+ * U (m x 16 x 16), ea (m x 16), V (n x 6, upper triangle 00 01 02 11 12 22), eb (n x 3),
+ * S (Sdim x Sdim, Sdim = 16 (m - mcon), symmetric), E (Sdim), dp (16 m + 3 n), scal[8] =
+ * {||e||^2, ||J^T e||_inf, ||p||^2, max diag, ||dp||^2, dL, ||e(p+dp)||^2, solved flag}. */
+int  argus_ba_normal_equations(argus_ba_ctx *ctx, double mu, double *U, double *ea, double *V, double *eb,
+                               double *S, double *E, double *dp, double *scal);
+
+/* ---- DLT path ---- */
+/* pts: N x (2 m k): for every frame, k track blocks of 2m values (u,v per camera, NaN = not seen) - the layout of
+ * the Clicker/DLC point matrix (argus-click:3287 slices one track block per uv_to_xyz call; k = 1 reproduces that
+ * call exactly).  prof: m x 8 [f,cx,cy,k1,k2,p1,p2,k3]; dlt: m x 11.
+ * xyz: N x 3k (NaN where fewer than two cameras see the point or a component is exactly 0, as the reference).
+ * flags bit 0: textbook 2n-row system instead of the reference's (n+1)-row system (tools.py:317-328). */
+int  argus_dlt_triangulate(const double *pts, int64_t N, int m, int k, const double *prof, const double *dlt,
+                           double *xyz, int flags);
+/* xyz: N x 3k, pts: N x 2mk, err: k x N (tools.py:360-423) */
+int  argus_dlt_reproj_error(const double *xyz, const double *pts, int64_t N, int m, int k,
+                            const double *prof, const double *dlt, double *err);
+/* both in one host round trip (pts copied to the device once): xyz N x 3k, err k x N */
+int  argus_dlt_reconstruct(const double *pts, int64_t N, int m, int k, const double *prof, const double *dlt,
+                           double *xyz, double *err, int flags);
+/* pts: N x 2 pixels -> out: N x 2 undistorted pixels, float32-faithful to cv2.undistortPoints(P=K) (tools.py:129-148) */
+int  argus_undistort_points(const double *pts, int64_t N, const double *prof8, float *out);
+
+/* device-pointer variants (inputs already resident in HBM; used for the kernel-only timings) */
+int  argus_dlt_triangulate_dev(const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt,
+                               double *d_xyz, int flags, void *stream);
+int  argus_dlt_reproj_error_dev(const double *d_xyz, const double *d_pts, int64_t N, int m, int k,
+                                const double *d_prof, const double *d_dlt, double *d_err, void *stream);
+
+const char *argus_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARGUS_B200_H_ */
