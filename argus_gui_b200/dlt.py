@@ -1,0 +1,73 @@
+"""Python host of the DLT path (C ABI: argus_dlt_*).  Array-level functions; the reference-named wrappers
+(uv_to_xyz, get_repo_errors, undistort_pts) live in argus_gui_b200/tools.py."""
+import ctypes
+import numpy as np
+from . import _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _prep(pts, prof, dlt, k=None):
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    prof = np.ascontiguousarray(np.asarray([np.asarray(p, dtype=np.float64) for p in prof]), dtype=np.float64)
+    dlt = np.ascontiguousarray(dlt, dtype=np.float64)
+    m = prof.shape[0]
+    if prof.ndim != 2 or prof.shape[1] < 8:
+        raise ValueError("pinhole profiles must have 8 values [f, cx, cy, k1, k2, p1, p2, k3]")
+    if prof.shape[1] > 8:       # tools.undistort_pts uses prof[0:3] and prof[-5:]
+        prof = np.ascontiguousarray(np.hstack([prof[:, :3], prof[:, -5:]]))
+    if dlt.shape != (m, 11):
+        raise ValueError("DLT coefficients must be (cameras x 11)")
+    if pts.ndim != 2 or pts.shape[1] % (2 * m) != 0:
+        raise ValueError("pts must be N x (2 * cameras * tracks)")
+    kk = pts.shape[1] // (2 * m)
+    if k is not None and k != kk:
+        raise ValueError("track count mismatch")
+    return pts, prof, dlt, m, kk
+
+
+def triangulate(pts, prof, dlt, textbook=False):
+    """pts N x (2 m k) -> xyz N x 3k (argus_dlt_triangulate)."""
+    lib = _lib.load()
+    pts, prof, dlt, m, k = _prep(pts, prof, dlt)
+    N = pts.shape[0]
+    xyz = np.empty((N, 3 * k))
+    _lib.check(lib.argus_dlt_triangulate(_ptr(pts), N, m, k, _ptr(prof), _ptr(dlt), _ptr(xyz), 1 if textbook else 0), "argus_dlt_triangulate")
+    return xyz
+
+
+def reproj_error(xyz, pts, prof, dlt):
+    """xyz N x 3k, pts N x 2mk -> err k x N (argus_dlt_reproj_error)."""
+    lib = _lib.load()
+    pts, prof, dlt, m, k = _prep(pts, prof, dlt)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    N = pts.shape[0]
+    if xyz.shape != (N, 3 * k):
+        raise ValueError("xyz must be N x 3k")
+    err = np.empty((k, N))
+    _lib.check(lib.argus_dlt_reproj_error(_ptr(xyz), _ptr(pts), N, m, k, _ptr(prof), _ptr(dlt), _ptr(err)), "argus_dlt_reproj_error")
+    return err
+
+
+def reconstruct(pts, prof, dlt, textbook=False):
+    """Both in one device round trip: -> (xyz N x 3k, err k x N)."""
+    lib = _lib.load()
+    pts, prof, dlt, m, k = _prep(pts, prof, dlt)
+    N = pts.shape[0]
+    xyz = np.empty((N, 3 * k)); err = np.empty((k, N))
+    _lib.check(lib.argus_dlt_reconstruct(_ptr(pts), N, m, k, _ptr(prof), _ptr(dlt), _ptr(xyz), _ptr(err), 1 if textbook else 0),
+               "argus_dlt_reconstruct")
+    return xyz, err
+
+
+def undistort(pts, prof8):
+    """N x 2 pixels -> N x 2 float32, faithful to cv2.undistortPoints(src f32, K, dist, P=K)."""
+    lib = _lib.load()
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 2)
+    prof8 = np.asarray(prof8, dtype=np.float64)
+    prof8 = np.ascontiguousarray(np.concatenate([prof8[:3], prof8[-5:]]))
+    out = np.empty((pts.shape[0], 2), dtype=np.float32)
+    _lib.check(lib.argus_undistort_points(_ptr(pts), pts.shape[0], _ptr(prof8), _ptr(out)), "argus_undistort_points")
+    return out

@@ -1,7 +1,7 @@
 """Synthetic scenes for the BA and DLT hot paths.
 
 Everything is generated with ``numpy.random.default_rng(seed)`` so the same arrays can be handed to the
-CUDA path, to the oracle and to the compiled reference.  The camera model is the one of SURVEY.md
+CUDA path and to the CPU checkers used by the tests.  The camera model is the one of SURVEY.md
 appendix A (sba-1.6p/libsbaprojs/imgproj.c:1206-1270): pinhole + Bouguet distortion,
 camera row = [f, cx, cy, AR, s, r2, r4, t1, t2, r6, qw, qx, qy, qz, tx, ty, tz].
 """
@@ -88,7 +88,7 @@ def make_ring_cameras(m, radius=8.0, height_amp=1.0, dist=(-0.05, 0.01, 0.001, -
 
 
 def make_ba_scene(m, n, views, seed, noise=0.5, radius=8.0, perturb=True, outlier_frac=0.0,
-                  dist=(-0.05, 0.01, 0.001, -0.001, 0.0), point_sigma=1.0, pert_scale=1.0):
+                  dist=(-0.05, 0.01, 0.001, -0.001, 0.0), point_sigma=1.0, pert_scale=1.0, cam_seed=None):
     """Synthetic BA problem (SURVEY.md 8d, configs C3/C4/C5 by argument).
 
     Returns a dict with the truth, the perturbed start, and the *sparse* problem in the layout the
@@ -119,11 +119,14 @@ def make_ba_scene(m, n, views, seed, noise=0.5, radius=8.0, perturb=True, outlie
         x[k, 1] = rng.uniform(0, 1080, size=nout)
     cams0 = cams.copy()
     pts0 = pts.copy()
+    # the camera perturbation can be seeded separately so that every rank of a sharded run (points seeded per rank)
+    # starts from the same cameras
+    crng = rng if cam_seed is None else np.random.default_rng(cam_seed)
     if perturb:
         s = pert_scale
         cams0[:, 0] *= 1.0 + 0.01 * s
         cams0[:, 5:10] *= 1.0 - 0.1 * s
-        dq = np.concatenate([np.ones((m, 1)), rng.normal(0, 0.0025 * s, size=(m, 3))], axis=1)
+        dq = np.concatenate([np.ones((m, 1)), crng.normal(0, 0.0025 * s, size=(m, 3))], axis=1)
         dq /= np.linalg.norm(dq, axis=1, keepdims=True)
         q = cams0[:, 10:14]
         # q <- dq (x) q  (Hamilton product)
@@ -133,7 +136,7 @@ def make_ba_scene(m, n, views, seed, noise=0.5, radius=8.0, perturb=True, outlie
                                     w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
                                     w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2,
                                     w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2], axis=1)
-        cams0[:, 14:17] += rng.uniform(-0.02 * s, 0.02 * s, size=(m, 3))
+        cams0[:, 14:17] += crng.uniform(-0.02 * s, 0.02 * s, size=(m, 3))
         pts0 += rng.uniform(-0.02 * s, 0.02 * s, size=(n, 3))
     return {"m": m, "n": n, "cams_true": cams, "pts_true": pts, "cams0": cams0, "pts0": pts0,
             "vmask": vmask, "x": x, "nobs": int(x.shape[0])}

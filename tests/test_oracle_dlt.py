@@ -1,0 +1,52 @@
+"""CPU: the numpy DLT oracle (oracle/dlt_port.py) against golden vectors produced by the reference's own
+argus_gui/tools.py (tests/golden/make_dlt_golden.py)."""
+import numpy as np
+from oracle import dlt_port
+
+
+def test_undistort_bit_exact_float32(golden_dlt):
+    g = golden_dlt
+    out = dlt_port.undistort_pts_f32(g["U_px"], g["U_prof"])
+    assert out.dtype == np.float32
+    assert np.array_equal(out, g["U_out"])
+
+
+def _check_case(g, c, m, k):
+    pts, prof, dlt = g[c + "_pts"], g[c + "_prof"], g[c + "_dlt"]
+    xyz = np.hstack([dlt_port.uv_to_xyz(pts[:, t * 2 * m:(t + 1) * 2 * m], prof, dlt) for t in range(k)])
+    ref = g[c + "_xyz"]
+    assert np.array_equal(np.isnan(xyz), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert np.abs(xyz[ok] - ref[ok]).max() <= 1e-12 * np.abs(ref[ok]).max()
+    err = dlt_port.get_repo_errors(ref, pts, prof, dlt)
+    rerr = g[c + "_err"]
+    assert err.shape == rerr.shape
+    assert np.array_equal(np.isnan(err), np.isnan(rerr))
+    ok = ~np.isnan(rerr)
+    assert np.abs(err[ok] - rerr[ok]).max() <= 1e-12 * np.abs(rerr[ok]).max()
+
+
+def test_uv_to_xyz_and_errors_case_a(golden_dlt):
+    _check_case(golden_dlt, "A", 4, 3)
+
+
+def test_uv_to_xyz_and_errors_case_b(golden_dlt):
+    _check_case(golden_dlt, "B", 6, 2)
+
+
+def test_quirk_differs_from_textbook(golden_dlt):
+    """The reference's (n+1)-row system is NOT the textbook 2n-row one."""
+    g = golden_dlt
+    pts, prof, dlt = g["A_pts"][:50, :8], g["A_prof"], g["A_dlt"]
+    a = dlt_port.uv_to_xyz(pts, prof, dlt)
+    b = dlt_port.uv_to_xyz(pts, prof, dlt, textbook=True)
+    ok = ~np.isnan(a).any(axis=1) & ~np.isnan(b).any(axis=1)
+    assert np.abs(a[ok] - b[ok]).max() > 1e-6
+
+
+def test_edge_rows(golden_dlt):
+    g = golden_dlt
+    xyz = g["A_xyz"]
+    assert np.isnan(xyz[0, :3]).all()        # nothing visible
+    assert np.isnan(xyz[1, :3]).all()        # a single camera
+    assert not np.isnan(xyz[2, :3]).any()    # exactly two cameras
