@@ -40,6 +40,7 @@ SIGNATURES = {
     "argus_ba_num_observations": (ctypes.c_int64, [ctypes.c_void_p]),
     "argus_ba_get_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_char_p), c_double_p,
                                             ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
+    "argus_ba_get_counters": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64)]),
     "argus_ba_project": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "argus_ba_normal_equations": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_double] + [ctypes.c_void_p] * 8),
     "argus_dlt_triangulate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,

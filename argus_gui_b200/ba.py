@@ -110,6 +110,11 @@ class BundleAdjuster:
         k = self.lib.argus_ba_get_profile(self.h, names, ms, cnt, cap)
         return {names[i].decode(): (ms[i], cnt[i]) for i in range(k)}
 
+    def counters(self):
+        out = (ctypes.c_int64 * 4)()
+        self.lib.argus_ba_get_counters(self.h, out)
+        return {"launches": out[0], "allreduces": out[1], "h2d_bytes": out[2], "d2h_bytes": out[3]}
+
     def project(self):
         hx = np.zeros((self.num_observations(), 2))
         _lib.check(self.lib.argus_ba_project(self.h, _ptr(hx)), "argus_ba_project")

@@ -64,6 +64,7 @@ struct argus_ba_ctx {
     std::vector<Ev> evs;
     std::vector<cudaEvent_t> ev_pool;
     double prof_ms[P_COUNT]; int64_t prof_n[P_COUNT];
+    int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0, n_allreduce = 0;
 
     BaProblem problem() const {
         BaProblem pb;
@@ -104,6 +105,7 @@ int do_allreduce(argus_ba_ctx *c, double *buf, int64_t count, int op)
     if (c->world <= 1) return ARGUS_OK;
     if (!c->allreduce) return ARGUS_E_COMM;
     ProfScope ps(c, P_ALLREDUCE);
+    c->n_allreduce += 1;
     return c->allreduce(c->comm_user, buf, count, op, (void *)c->stream) == 0 ? ARGUS_OK : ARGUS_E_COMM;
 }
 
@@ -116,6 +118,7 @@ int run_residual(argus_ba_ctx *c, const double *cam, const double *pts, double *
         ProfScope ps(c, P_RESIDUAL);
         k_residual<<<c->grid_pts256, 256, cam_smem(c->m), c->stream>>>(c->problem(), cam, pts, hx, c->respart.p);
         k_reduce_sum<<<1, 32, 0, c->stream>>>(c->respart.p, c->grid_pts256, 1, 1, c->red3.p);
+        c->launches += 2;
     }
     ARGUS_CUDA_CHECK(cudaGetLastError());
     return do_allreduce(c, c->red3.p, 1, 0);
@@ -143,6 +146,7 @@ int run_linearize(argus_ba_ctx *c)
     rc = do_allreduce(c, c->max2.p, 2, 1);
     if (rc) return rc;
     k_lin_finalize<<<1, 32, 0, c->stream>>>(c->red1.p, c->cam.p, m, c->mcon, c->red1.p + (int64_t)m * kU, c->max2.p, c->scal.p);
+    c->launches += 4;
     ARGUS_CUDA_CHECK(cudaGetLastError());
     return ARGUS_OK;
 }
@@ -197,6 +201,7 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
     rc = do_allreduce(c, c->red3.p, 3, 0);
     if (rc) return rc;
     k_attempt_finalize<<<1, 32, 0, c->stream>>>(c->flags.p, c->cam2.p, c->red3.p, c->att.p);
+    c->launches += 10;
     ARGUS_CUDA_CHECK(cudaGetLastError());
     return ARGUS_OK;
 }
@@ -206,6 +211,7 @@ int read_back(argus_ba_ctx *c, const double *dsrc, int count, double *hdst)
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->h_pinned, dsrc, count * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ARGUS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     memcpy(hdst, c->h_pinned, count * sizeof(double));
+    c->d2h_bytes += count * sizeof(double);
     return ARGUS_OK;
 }
 
@@ -325,6 +331,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cam0.p, p, 16 * m * sizeof(double), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pts0.p, p + 16 * m, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));      // host staging vectors go out of scope
+    c->h2d_bytes += (n + 1) * sizeof(int32_t) + nobs * (sizeof(uint8_t) + sizeof(double2)) + n * sizeof(uint64_t) + (4 + 16) * m * sizeof(double) + 3 * n * sizeof(double);
     return argus_ba_reset(c);
 }
 
@@ -344,6 +351,14 @@ int argus_ba_download(argus_ba_ctx *c, double *p)
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(p, c->cam.p, 16 * c->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(p + 16 * c->m, c->pts.p, 3 * c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ARGUS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += (16 * c->m + 3 * c->n) * sizeof(double);
+    return ARGUS_OK;
+}
+
+int argus_ba_get_counters(argus_ba_ctx *c, int64_t out[4])
+{
+    if (!c || !out) return ARGUS_E_ARG;
+    out[0] = c->launches; out[1] = c->n_allreduce; out[2] = c->h2d_bytes; out[3] = c->d2h_bytes;
     return ARGUS_OK;
 }
 

@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the bundle-adjustment hot path (and the DLT path) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...      (the reference's own CPU implementation, oracle/_ref, on a bounded sample)
+
+Workload (BASELINE.json config 4 per GPU, weak scaling): 16 cameras, 2,000,000 points x 10 views = 20,000,000
+observations per rank, all 10 Argus intrinsics + pose free (nccalib = ncdist = 0), cameras shared by all ranks.
+A "step" is one pass of the hot path over that batch: ITERS_PER_STEP (5) Levenberg-Marquardt iterations from the same
+perturbed start (stop tests disabled so every step does identical work; asserted).
+metric = observations x LM iterations per second, whole job (all ranks).  The reduced camera system and three
+scalars are all-reduced (NCCL) per iteration when N > 1; points/observations never move.
+
+One JSON line on rank 0; see DESIGN.md for the roofline definitions.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP64_PEAK_TFLOPS = 37.1      # measured on this pool's B200 with tools/microbench/fp64_peak.cu (DMMA.8x8x4, sustained);
+                             # MEASURED_PEAKS.json has no fp64 entry - see profiles/r01_fp64_peak.txt
+ITERS_PER_STEP = 5
+WORKLOADS = {
+    # name: (cameras, points per rank, views per point, nccalib, ncdist)
+    "c4": (16, 2_000_000, 10, 0, 0),
+    "c3": (8, 200_000, 6, 0, 0),
+    "small": (8, 20_000, 6, 0, 0),
+}
+OPTS_FIXED_WORK = [1e-3, 0.0, 0.0, 0.0, 0.0]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index; self.proc = None; self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_scene(workload, rank):
+    from argus_gui_b200 import scenes
+    m, n, views, nk, nd = WORKLOADS[workload]
+    s = scenes.make_ba_scene(m, n, views, seed=4 + 1000 * rank, cam_seed=4)
+    p0, rot0 = scenes.pack_ba_problem(s["cams0"], s["pts0"])
+    return s, p0, rot0, (m, n, views, nk, nd)
+
+
+def algorithmic_counts(vmask, m):
+    """per LM iteration flops = nobs*(1025 + 90 + 1316) + 768 * sum_i v_i (v_i + 1) + Sdim^3/3,
+    bytes = 40 nobs + 72 npts + 8 Sdim^2; the Schur kernel alone: 768 * sum_i v_i (v_i + 1) flops."""
+    v = vmask.sum(axis=1).astype(np.float64)
+    nobs = float(v.sum()); n = float(vmask.shape[0]); sdim = 16.0 * m
+    schur = 768.0 * float((v * (v + 1.0)).sum())
+    return {"nobs": nobs, "flops_iter": nobs * 2431.0 + schur + sdim ** 3 / 3.0, "bytes_iter": 40.0 * nobs + 72.0 * n + 8.0 * sdim * sdim,
+            "schur_flops": schur}
+
+
+def reference_sample(s, p0, m, n_sample):
+    """First n_sample points of the scene with all their observations (same cameras): the bounded CPU sample."""
+    n_sample = min(n_sample, s["vmask"].shape[0])
+    vm = s["vmask"][:n_sample]
+    nobs = int(vm.sum())
+    return vm, s["x"][:nobs], np.concatenate([p0[:16 * m], p0[16 * m:16 * m + 3 * n_sample]])
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the reference's own C code (oracle/_ref: sba 1.6 + libsbaprojs + OpenBLAS, single thread - the
+    reference is single-threaded and more BLAS threads slow it down) on a bounded sample of the workload."""
+    if rank != 0:
+        return
+    from oracle import sba_ref, ba_port
+    s, p0, rot0, (m, n, views, nk, nd) = make_scene(args.workload, 0)
+    vm, x, p = reference_sample(s, p0, m, args.ref_points)
+    nobs = int(vm.sum())
+    if sba_ref.available():
+        kind = "reference"
+        run = lambda: sba_ref.ref_motstr(p, x, vm, rot0, nk, nd, itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+    else:
+        kind = "port"
+        run = lambda: ba_port.port_motstr(p, x, vm, rot0, nk, nd, itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, info, ret = run()
+        assert int(info[5]) == ITERS_PER_STEP, info
+    dt = time.perf_counter() - t0
+    value = nobs * ITERS_PER_STEP * args.steps / dt
+    sample = "first %d points (%d observations) of the %s scene, %d cameras, %d LM iterations per step" % (vm.shape[0], nobs, args.workload, m, ITERS_PER_STEP)
+    line = {"impl": "reference", "metric": "ba_observations_per_second", "value": value, "unit": "obs*iters/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: BA %d cameras, bounded sample" % (args.workload, m), "sample": sample, "iters_per_step": ITERS_PER_STEP},
+            "cpu_baseline": {"value": value, "unit": "obs*iters/s", "cores": 1, "kind": kind, "sample": sample, "host_cores": os.cpu_count()},
+            "lm_iters_per_sec": ITERS_PER_STEP * args.steps / dt,
+            "e2e": {"value": value, "unit": "obs*iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def bench_dlt(torch, device, stream, steps, warmup, rank, world, hbm_peak):
+    """BASELINE config 2 per rank: 1M frames x 4 cameras x 10 tracks; triangulation + reprojection error."""
+    import ctypes
+    from argus_gui_b200 import scenes, dlt as dlt_host, _lib
+    lib = _lib.load()
+    N, m, k = 1_000_000, 4, 10
+    d = scenes.make_dlt_scene(N, m=m, ntracks=k, seed=2 + rank)
+    with torch.cuda.stream(stream):
+        t_pts = torch.from_numpy(d["pts"]).to(device)
+        t_prof = torch.from_numpy(np.ascontiguousarray(d["prof"])).to(device)
+        t_dlt = torch.from_numpy(np.ascontiguousarray(d["dlt"])).to(device)
+        t_xyz = torch.empty((N, 3 * k), dtype=torch.float64, device=device)
+        t_err = torch.empty((k, N), dtype=torch.float64, device=device)
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)   # > 126 MB L2
+        vp = ctypes.c_void_p
+        sp = vp(stream.cuda_stream)
+
+        def step():
+            rc = lib.argus_dlt_triangulate_dev(vp(t_pts.data_ptr()), N, m, k, vp(t_prof.data_ptr()), vp(t_dlt.data_ptr()), vp(t_xyz.data_ptr()), 0, sp)
+            rc |= lib.argus_dlt_reproj_error_dev(vp(t_xyz.data_ptr()), vp(t_pts.data_ptr()), N, m, k, vp(t_prof.data_ptr()), vp(t_dlt.data_ptr()),
+                                                 vp(t_err.data_ptr()), sp)
+            assert rc == 0
+        for _ in range(warmup):
+            step()
+        tri_ms = err_ms = 0.0
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        for _ in range(steps):
+            flush.zero_()
+            e[0].record(stream)
+            lib.argus_dlt_triangulate_dev(vp(t_pts.data_ptr()), N, m, k, vp(t_prof.data_ptr()), vp(t_dlt.data_ptr()), vp(t_xyz.data_ptr()), 0, sp)
+            e[1].record(stream)
+            lib.argus_dlt_reproj_error_dev(vp(t_xyz.data_ptr()), vp(t_pts.data_ptr()), N, m, k, vp(t_prof.data_ptr()), vp(t_dlt.data_ptr()),
+                                           vp(t_err.data_ptr()), sp)
+            e[2].record(stream)
+            e[2].synchronize()
+            tri_ms += e[0].elapsed_time(e[1]); err_ms += e[1].elapsed_time(e[2])
+    tri_ms /= steps; err_ms /= steps
+    npts = N * k
+    tri_bytes = npts * (2 * m * 8 + 24); err_bytes = npts * (2 * m * 8 + 24 + 8)
+    # end to end through the host API (pageable numpy in, numpy out), one repetition
+    t0 = time.perf_counter()
+    xyz, err = dlt_host.reconstruct(d["pts"], d["prof"], d["dlt"])
+    e2e_s = time.perf_counter() - t0
+    out = {"workload": "c2: %d frames x %d cameras x %d tracks per rank" % (N, m, k), "points_per_sec": npts / ((tri_ms + err_ms) * 1e-3),
+           "ms_triangulate": tri_ms, "ms_reproj_error": err_ms,
+           "roofline_triangulate": {"bound": "hbm", "achieved": tri_bytes / (tri_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": tri_bytes / (tri_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+           "roofline_reproj_error": {"bound": "hbm", "achieved": err_bytes / (err_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                     "frac": err_bytes / (err_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+           "e2e": {"value": npts / e2e_s, "unit": "points/s", "h2d_bytes_per_step": int(d["pts"].nbytes), "d2h_bytes_per_step": int(xyz.nbytes + err.nbytes)},
+           "gpu_launches": 2 * steps}
+    if rank == 0 and world == 1:
+        from oracle import dlt_port
+        ns = 1500
+        t0 = time.perf_counter()
+        for t in range(k):
+            xo = dlt_port.uv_to_xyz(d["pts"][:ns, t * 2 * m:(t + 1) * 2 * m], d["prof"], d["dlt"])
+        eo = dlt_port.get_repo_errors(xyz[:ns], d["pts"][:ns], d["prof"], d["dlt"])
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": ns * k / dt, "unit": "points/s", "cores": 1, "kind": "port",
+                               "sample": "first %d frames x %d tracks (numpy restatement of tools.uv_to_xyz + get_repo_errors)" % (ns, k)}
+    del t_pts, t_xyz, t_err, flush
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-points", type=int, default=4096, help="points in the bounded CPU sample")
+    ap.add_argument("--cpu-baseline-points", type=int, default=8192)
+    ap.add_argument("--no-dlt", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from argus_gui_b200 import ba
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the BA / DLT path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    hbm_peak, hbm_src = measured_peaks()
+    stream = torch.cuda.Stream(device=device)
+
+    s, p0, rot0, (m, n, views, nk, nd) = make_scene(args.workload, rank)
+    counts = algorithmic_counts(s["vmask"], m)
+    nobs_local = s["nobs"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        B = ba.BundleAdjuster(device=local, stream=stream.cuda_stream)
+        if world > 1:
+            B.set_comm(rank, world, ba.torch_allreduce_hook())
+        B.upload(s["vmask"], p0, rot0, s["x"], nk, nd)
+        for _ in range(args.warmup):
+            B.reset(); ret, info = B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+            assert ret == ITERS_PER_STEP, (ret, info)
+        c0 = B.counters()
+        sampler = ClockSampler(local); sampler.start()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        prof = {}
+        e0.record(stream)
+        for _ in range(args.steps):
+            B.reset(); ret, info = B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK, profile=True)
+            assert ret == ITERS_PER_STEP and int(info[5]) == ITERS_PER_STEP, (ret, info)
+            for kname, (ms, cnt) in B.profile().items():
+                a = prof.setdefault(kname, [0.0, 0]); a[0] += ms; a[1] += cnt
+        e1.record(stream)
+        barrier()
+        clocks = sampler.stop()
+        ms_total = e0.elapsed_time(e1)
+        c1 = B.counters()
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    tot_obs = torch.tensor([float(nobs_local)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX); dist.all_reduce(tot_obs, op=dist.ReduceOp.SUM)
+    ms_total = float(t_ms.item()); total_obs = float(tot_obs.item())
+    value = total_obs * ITERS_PER_STEP * args.steps / (ms_total * 1e-3)
+    final_cost = float(info[1])
+
+    # ---- end to end through the C ABI with HOST buffers: create + upload (H2D) + solve + download (D2H) + destroy ----
+    e2e = None
+    if not args.no_e2e:
+        hp = torch.from_numpy(p0.copy()).pin_memory().numpy()
+        hx = torch.from_numpy(np.ascontiguousarray(s["x"])).pin_memory().numpy()
+        hv = torch.from_numpy(np.ascontiguousarray(s["vmask"]).view(np.int8)).pin_memory().numpy()
+        n_e2e = max(1, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            if world == 1:
+                pe, ie, re_ = ba.solve_motstr(hv, hp, rot0, hx, nk, nd, itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+            else:
+                with torch.cuda.stream(stream):
+                    Be = ba.BundleAdjuster(device=local, stream=stream.cuda_stream)
+                    Be.set_comm(rank, world, ba.torch_allreduce_hook())
+                    Be.upload(hv, hp, rot0, hx, nk, nd)
+                    re_, ie = Be.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+                    pe = Be.download(); Be.close()
+            assert re_ == ITERS_PER_STEP
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        per_step_h2d = int((c1["h2d_bytes"]) / 1)      # bytes of one upload (counted by the library from the arrays it copies)
+        e2e = {"value": total_obs * ITERS_PER_STEP * n_e2e / float(dt.item()), "unit": "obs*iters/s",
+               "h2d_bytes_per_step": per_step_h2d, "d2h_bytes_per_step": int(8 * (16 * m + 3 * n)), "steps": n_e2e,
+               "api": "argus_ba_motstr_kdrts (host pointers: alloc + index build + H2D + %d LM iterations + D2H)" % ITERS_PER_STEP}
+
+    # ---- roofline of the dominant kernel (CUDA events on the launching stream, inside the timed region) ----
+    kern = {k_: v for k_, v in prof.items() if v[1] > 0 and k_ != "allreduce"}
+    dom = max(kern, key=lambda k_: kern[k_][0])
+    dom_ms = kern[dom][0] / kern[dom][1]
+    sum_ms = sum(v[0] for v in kern.values())
+    if dom == "schur":
+        rl = {"kernel": dom, "bound": "tensor", "achieved": counts["schur_flops"] / (dom_ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS,
+              "unit": "TFLOP/s", "peak_source": "fp64 DMMA/DFMA peak measured with tools/microbench/fp64_peak.cu (profiles/r01_fp64_peak.txt)"}
+    else:
+        per = {"linearize": 40.0 * counts["nobs"] + 72.0 * n, "backsub_eval": 40.0 * counts["nobs"] + 72.0 * n}.get(dom, 40.0 * counts["nobs"])
+        rl = {"kernel": dom, "bound": "hbm", "achieved": per / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src}
+    rl["frac"] = rl["achieved"] / rl["peak"]
+    rl["traffic"] = None
+    rl["ms_per_launch"] = dom_ms
+    rl["share_of_kernel_time"] = kern[dom][0] / sum_ms
+    t_iter = ms_total * 1e-3 / (ITERS_PER_STEP * args.steps)
+    rl["iteration"] = {"ms": t_iter * 1e3, "fp64_frac": counts["flops_iter"] / t_iter / 1e12 / FP64_PEAK_TFLOPS,
+                       "hbm_frac": counts["bytes_iter"] / t_iter / 1e9 / hbm_peak,
+                       "algorithmic_gflop": counts["flops_iter"] / 1e9, "algorithmic_gbyte": counts["bytes_iter"] / 1e9}
+    rl["kernels_ms_per_iteration"] = {k_: v[0] / (ITERS_PER_STEP * args.steps) for k_, v in sorted(prof.items())}
+
+    # ---- CPU baseline: the reference's own C code on the host cores of this box (rank 0, N = 1) ----
+    cpu = None
+    if rank == 0 and world == 1:
+        from oracle import sba_ref, ba_port
+        vm, xs, ps = reference_sample(s, p0, m, args.cpu_baseline_points)
+        kind = "reference" if sba_ref.available() else "port"
+        fn = sba_ref.ref_motstr if kind == "reference" else ba_port.port_motstr
+        t0 = time.perf_counter()
+        _, iref, _ = fn(ps, xs, vm, rot0, nk, nd, itmax=2, opts=OPTS_FIXED_WORK)
+        dt_ref = time.perf_counter() - t0
+        cpu = {"value": int(vm.sum()) * 2 / dt_ref, "unit": "obs*iters/s", "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
+               "sample": "first %d points (%d observations) of the same scene, %d cameras, 2 LM iterations, %.1f s" % (vm.shape[0], int(vm.sum()), m, dt_ref)}
+
+    B.close()
+    dlt_res = None
+    if not args.no_dlt:
+        dlt_res = bench_dlt(torch, device, stream, max(3, min(args.steps, 10)), 3, rank, world, hbm_peak)
+        if world > 1:
+            v = torch.tensor([dlt_res["points_per_sec"]], dtype=torch.float64, device=device)
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+            dlt_res["points_per_sec"] = float(v.item())
+
+    if rank == 0:
+        line = {"metric": "ba_observations_per_second", "value": value, "unit": "obs*iters/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "%s: BA %d cameras, %d points x %d views = %d observations per GPU, 16 free parameters per camera"
+                                       % (args.workload, m, n, views, nobs_local),
+                           "iters_per_step": ITERS_PER_STEP, "parallelism": "points sharded x%d, cameras replicated" % world,
+                           "l2": "inputs larger than L2 (>= %.1f GB of per-observation blocks per pass)" % (nobs_local * 48 * 8 / 1e9),
+                           "final_cost": final_cost},
+                "lm_iters_per_sec": ITERS_PER_STEP * args.steps / (ms_total * 1e-3),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(c1["launches"] - c0["launches"]),
+                "allreduces": int(c1["allreduces"] - c0["allreduces"]), "roofline": rl, "cpu_baseline": cpu, "dlt": dlt_res}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

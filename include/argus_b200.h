@@ -85,6 +85,9 @@ int64_t argus_ba_num_observations(const argus_ba_ctx *ctx);
  * number of entries written (<= cap). */
 int  argus_ba_get_profile(argus_ba_ctx *ctx, const char **names, double *ms, int64_t *launches, int cap);
 
+/* counters since creation: out = {kernel launches, all-reduce calls, host->device bytes, device->host bytes} */
+int  argus_ba_get_counters(argus_ba_ctx *ctx, int64_t out[4]);
+
 /* ---- parity hooks (the pieces of one LM attempt, for tests against the oracle) ---- */
 /* hx (2 per projection) at the resident p  (img_projsKDRTS_x) */
 int  argus_ba_project(argus_ba_ctx *ctx, double *hx);
