@@ -1,0 +1,306 @@
+// Generation-2 Schur-complement kernel: fp64 tensor-pipe (DMMA m8n8k4) rank-3 updates with S-blocks stationary in
+// registers, operands streamed through shared memory by bulk-async (TMA) copies.
+//
+// Math.  With V*_i = L_i D_i L_i^T (3x3, per point) and  Z_ij = W_ij L_i^-T |D_i|^-1/2  (16x3, per observation),
+//     sum_i Y_ij W_ik^T = sum_i Z_ij diag(sign D_i) Z_ik^T            (sba_levmar.c:1075-1114 computes the left side)
+// so the whole Schur complement is a sum of signed rank-3 outer products of ONE operand array Z (384 B per
+// observation) instead of two (Y and W).  For a damped, positive-definite V* all signs are +.
+//
+// Work decomposition.  The upper-triangular 16x16 camera blocks (j <= k) are dealt to G groups x 8 warps x NB slots.
+// A CTA = (chunk of point tiles, group); each warp keeps its NB blocks as DMMA accumulators (8 doubles per lane per
+// block) for the whole chunk.  Per tile (<= 32 points, <= TO observations) the CTA's Z rows arrive by cp.async.bulk
+// into a double-buffered shared-memory tile; per block the warp ballots the points that see both cameras, compacts
+// them into a hit list and feeds the K dimension (3 per hit, 4 per DMMA step) without padding.
+// Fragment layout of mma.m8n8k4.f64: A: lane -> (row = lane>>2, k = lane&3); B: (k = lane&3, col = lane>>2);
+// C: (row = lane>>2, cols 2*(lane&3), +1).  The Z rows of an observation are stored as ((r%8)*3 + c)*2 + r/8 so one
+// 16-byte load gives a lane the (row, row+8) pair of its fragment - the same load serves the A and the B operand.
+#pragma once
+#include "ba_common.cuh"
+
+namespace argus {
+
+constexpr int kTilePts = 32;        // points per tile (one ballot)
+constexpr int kSchurWarps = 8;
+
+__host__ __device__ __forceinline__ int zperm(int r, int c) { return ((r & 7) * 3 + c) * 2 + (r >> 3); }
+
+struct TilePlan {
+    int ntiles;
+    int tile_obs;                   // TO: max observations per tile
+    const int32_t *tile_pt;         // ntiles + 1: first point of each tile
+};
+
+struct SchurPlan {
+    int G;                          // block groups
+    int nchunk;                     // point-tile chunks (grid.x)
+    int npairs;                     // upper-triangular camera pairs among the free cameras
+    const uint16_t *blk_jk;         // [G][8][NB]: j | k << 8 (absolute camera ids), 0xFFFF = empty slot
+    const int32_t *blk_pair;        // [G][8][NB]: pair index (row-major upper triangle over free cameras) or -1
+};
+
+// ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Bridge from the generation-1 linearisation (W, V, eb resident): per point damp + LDL^T, Z = W L^-T |D|^-1/2, sign mask,
+// V*^-1 (for the back-substitution) and c_i = V*^-1 eb_i; E_j partials as in k_prepare.  One thread per point.
+__global__ void __launch_bounds__(128) k_make_z(BaProblem pb, double mu, int use_state, int write_state,
+                                                const double *__restrict__ V, const double *__restrict__ eb,
+                                                double *__restrict__ vstate, const double *__restrict__ W, double *__restrict__ Z,
+                                                uint8_t *__restrict__ zsign, double *__restrict__ Vinv, double *__restrict__ Epart,
+                                                int *__restrict__ flag)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *Es = reinterpret_cast<double *>(smem_raw);      // m x 16
+    for (int t = threadIdx.x; t < pb.m * 16; t += blockDim.x) Es[t] = 0.0;
+    __syncthreads();
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < pb.n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        if (i >= pb.n) continue;
+        if (i < pb.ncon) { zsign[i] = 0; continue; }
+        double v[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) v[t] = V[6 * i + t];
+        if (use_state) { v[0] = vstate[3 * i]; v[3] = vstate[3 * i + 1]; v[5] = vstate[3 * i + 2]; }
+        v[0] += mu; v[3] += mu; v[5] += mu;
+        double li[3], di[3];
+        if (!sym3_ldl_inv(v, li, di)) { atomicOr(flag, 1); zsign[i] = 0; continue; }
+        const double n00 = di[0] + li[0] * li[0] * di[1] + li[1] * li[1] * di[2];
+        const double n01 = li[0] * di[1] + li[1] * li[2] * di[2];
+        const double n02 = li[1] * di[2];
+        const double n11 = di[1] + li[2] * li[2] * di[2];
+        const double n12 = li[2] * di[2];
+        const double n22 = di[2];
+        double *Ni = Vinv + 6 * i;
+        Ni[0] = n00; Ni[1] = n01; Ni[2] = n02; Ni[3] = n11; Ni[4] = n12; Ni[5] = n22;
+        if (write_state) { vstate[3 * i] = n00; vstate[3 * i + 1] = n11; vstate[3 * i + 2] = n22; }
+        const double b0 = eb[3 * i], b1 = eb[3 * i + 1], b2 = eb[3 * i + 2];
+        const double c0 = n00 * b0 + n01 * b1 + n02 * b2, c1 = n01 * b0 + n11 * b1 + n12 * b2, c2 = n02 * b0 + n12 * b1 + n22 * b2;
+        const double s0 = sqrt(fabs(di[0])), s1 = sqrt(fabs(di[1])), s2 = sqrt(fabs(di[2]));
+        zsign[i] = (uint8_t)((di[0] < 0.0 ? 1 : 0) | (di[1] < 0.0 ? 2 : 0) | (di[2] < 0.0 ? 4 : 0));
+        const int k1 = pb.obs_ptr[i + 1];
+        for (int k = pb.obs_ptr[i]; k < k1; ++k) {
+            const int j = pb.obs_cam[k];
+            double *Zk = Z + 48 * (int64_t)k;
+            if (j < pb.mcon) {
+#pragma unroll
+                for (int t = 0; t < 48; ++t) Zk[t] = 0.0;
+                continue;
+            }
+            const double *Wk = W + 48 * (int64_t)k;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const double w0 = Wk[3 * r], w1 = Wk[3 * r + 1], w2 = Wk[3 * r + 2];
+                Zk[zperm(r, 0)] = w0 * s0;
+                Zk[zperm(r, 1)] = (li[0] * w0 + w1) * s1;
+                Zk[zperm(r, 2)] = (li[1] * w0 + li[2] * w1 + w2) * s2;
+                const double s = w0 * c0 + w1 * c1 + w2 * c2;
+                if (s != 0.0) atomicAdd(Es + 16 * j + r, s);
+            }
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < pb.m * 16; t += blockDim.x) Epart[(int64_t)blockIdx.x * pb.m * 16 + t] = Es[t];
+}
+
+// The Schur kernel.  grid = (nchunk, G), 256 threads.  Dynamic shared memory: 2 tiles of TO x 48 doubles.
+// Spart[chunk][pair][256]: per-chunk partial sums in fragment order (lane * 8 + q), q = (ri*2 + ci)*2 + e for the
+// 8x8 sub-tile (ri, ci) of the block: element (row = ri*8 + lane>>2, col = ci*8 + 2*(lane&3) + e).
+template <int NB>
+__global__ void __launch_bounds__(kSchurWarps * 32, 1) k_schur_mma(BaProblem pb, TilePlan tp, SchurPlan sp, const double *__restrict__ Z,
+                                                                    const uint8_t *__restrict__ zsign, double *__restrict__ Spart)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *zbuf0 = reinterpret_cast<double *>(smem_raw);
+    double *zbuf1 = zbuf0 + (size_t)tp.tile_obs * 48;
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ uint32_t hitlist[kSchurWarps][kTilePts];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g8 = lane >> 2, kk = lane & 3;
+    const int chunk = blockIdx.x, grp = blockIdx.y;
+
+    // this warp's block slots
+    int bj[NB], bk[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const uint16_t jk = sp.blk_jk[((size_t)grp * kSchurWarps + warp) * NB + b];
+        bj[b] = (jk == 0xFFFF) ? -1 : (jk & 0xFF);
+        bk[b] = (jk == 0xFFFF) ? -1 : (jk >> 8);
+    }
+    double acc[NB][8];
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[b][q] = 0.0;
+
+    if (threadIdx.x == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const int ntl = (tp.ntiles > chunk) ? (tp.ntiles - chunk + sp.nchunk - 1) / sp.nchunk : 0;   // tiles of this chunk
+
+    auto issue = [&](int it) {       // warp 0: start the bulk copies of local tile `it` into buffer it & 1
+        const int t = chunk + it * sp.nchunk;
+        const int p0 = tp.tile_pt[t], p1 = tp.tile_pt[t + 1];
+        const int o0 = pb.obs_ptr[p0], o1 = pb.obs_ptr[p1];
+        const uint32_t bytes = (uint32_t)(o1 - o0) * 384u;
+        uint64_t *bar = &mbar[it & 1];
+        char *dst = reinterpret_cast<char *>((it & 1) ? zbuf1 : zbuf0);
+        const char *src = reinterpret_cast<const char *>(Z + 48 * (int64_t)o0);
+        if (lane == 0) mbar_expect_tx(bar, bytes);
+        __syncwarp();
+        for (uint32_t off = (uint32_t)lane * 4096u; off < bytes; off += 32u * 4096u) {
+            const uint32_t sz = (bytes - off < 4096u) ? (bytes - off) : 4096u;
+            bulk_g2s(dst + off, src + off, sz, bar);
+        }
+    };
+
+    // per-lane metadata of the point this lane represents in a tile
+    auto load_meta = [&](int it, uint64_t &mk, int &ob, uint32_t &sg) {
+        mk = 0; ob = 0; sg = 0;
+        if (it < ntl) {
+            const int t = chunk + it * sp.nchunk;
+            const int p0 = tp.tile_pt[t], p1 = tp.tile_pt[t + 1];
+            const int p = p0 + lane;
+            if (p < p1) {
+                if (p >= pb.ncon) mk = pb.pt_mask[p];
+                ob = pb.obs_ptr[p] - pb.obs_ptr[p0];
+                sg = zsign[p];
+            }
+        }
+    };
+
+    if (ntl > 0 && warp == 0) issue(0);
+    uint64_t mk_n; int ob_n; uint32_t sg_n;
+    load_meta(0, mk_n, ob_n, sg_n);
+
+    for (int it = 0; it < ntl; ++it) {
+        const uint64_t mk = mk_n; const int ob = ob_n; const uint32_t sg = sg_n;
+        if (it + 1 < ntl && warp == 0) issue(it + 1);       // buffer (it+1)&1 was released by the barrier ending iteration it-1
+        load_meta(it + 1, mk_n, ob_n, sg_n);
+        mbar_wait(&mbar[it & 1], (uint32_t)((it >> 1) & 1));
+        const double *zt = (it & 1) ? zbuf1 : zbuf0;
+
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int j = bj[b], k = bk[b];
+            if (j < 0) continue;
+            const bool hit = ((mk >> j) & (mk >> k) & 1ull) != 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+            const int nh = __popc(bal);
+            if (nh == 0) continue;
+            if (hit) {
+                const int pos = __popc(bal & ((1u << lane) - 1u));
+                const int oj = ob + __popcll(mk & ((1ull << j) - 1ull));
+                const int ok = ob + __popcll(mk & ((1ull << k) - 1ull));
+                hitlist[warp][pos] = (uint32_t)oj | ((uint32_t)ok << 12) | ((uint32_t)lane << 24);
+            }
+            __syncwarp();
+            const int nslots = 3 * nh;
+            if (j == k) {
+                for (int s0 = 0; s0 < nslots; s0 += 4) {
+                    const int slot = s0 + kk;
+                    const bool valid = slot < nslots;
+                    const int h = valid ? slot / 3 : 0;
+                    const int comp = slot - 3 * (slot / 3);
+                    const uint32_t ent = hitlist[warp][h];
+                    const int oj = ent & 0xFFF, pt = ent >> 24;
+                    const uint32_t sgn = __shfl_sync(0xffffffffu, sg, pt);
+                    double2 a = *reinterpret_cast<const double2 *>(zt + (size_t)oj * 48 + (g8 * 3 + comp) * 2);
+                    if (!valid) { a.x = 0.0; a.y = 0.0; }
+                    double2 as = a;
+                    if ((sgn >> comp) & 1u) { as.x = -as.x; as.y = -as.y; }
+                    dmma884(acc[b][0], acc[b][1], as.x, a.x);     // (lo, lo)
+                    dmma884(acc[b][2], acc[b][3], as.x, a.y);     // (lo, hi)
+                    dmma884(acc[b][6], acc[b][7], as.y, a.y);     // (hi, hi)
+                }
+            } else {
+                for (int s0 = 0; s0 < nslots; s0 += 4) {
+                    const int slot = s0 + kk;
+                    const bool valid = slot < nslots;
+                    const int h = valid ? slot / 3 : 0;
+                    const int comp = slot - 3 * (slot / 3);
+                    const uint32_t ent = hitlist[warp][h];
+                    const int oj = ent & 0xFFF, ok = (ent >> 12) & 0xFFF, pt = ent >> 24;
+                    const uint32_t sgn = __shfl_sync(0xffffffffu, sg, pt);
+                    double2 a = *reinterpret_cast<const double2 *>(zt + (size_t)oj * 48 + (g8 * 3 + comp) * 2);
+                    double2 bb = *reinterpret_cast<const double2 *>(zt + (size_t)ok * 48 + (g8 * 3 + comp) * 2);
+                    if (!valid) { a.x = 0.0; a.y = 0.0; }
+                    if ((sgn >> comp) & 1u) { a.x = -a.x; a.y = -a.y; }
+                    dmma884(acc[b][0], acc[b][1], a.x, bb.x);
+                    dmma884(acc[b][2], acc[b][3], a.x, bb.y);
+                    dmma884(acc[b][4], acc[b][5], a.y, bb.x);
+                    dmma884(acc[b][6], acc[b][7], a.y, bb.y);
+                }
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int pair = sp.blk_pair[((size_t)grp * kSchurWarps + warp) * NB + b];
+        if (pair < 0) continue;
+        double *o = Spart + ((size_t)chunk * sp.npairs + pair) * 256 + lane * 8;
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) *reinterpret_cast<double2 *>(o + q) = make_double2(acc[b][q], acc[b][q + 1]);
+    }
+}
+
+// Assemble S, E from fragment-ordered Schur sums (see k_schur_mma) and the reduced U / ea:
+//   S_jk = delta_jk (U_j + mu_u I) - P_jk,  E_j = ea_j - Ered_j; the lower block triangle (and the (hi,lo) sub-tile of the
+//   diagonal blocks, which the MMA kernel skips) is mirrored.
+__global__ void k_assemble_mma(int m, int mcon, const double *__restrict__ Ured, const double *__restrict__ Sred,
+                               const double *__restrict__ Ered, double mu_u, double *__restrict__ S, double *__restrict__ E)
+{
+    const int mf = m - mcon, N = 16 * mf;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (int64_t)N * N) {
+        const int row = (int)(t / N), col = (int)(t % N);
+        int a = row >> 4, b = col >> 4, r = row & 15, c = col & 15;
+        if (a > b || (a == b && r > c)) { int q = a; a = b; b = q; q = r; r = c; c = q; }
+        const int pair = a * mf - (a * (a - 1)) / 2 + (b - a);
+        const int ri = r >> 3, ci = c >> 3;
+        const int ln = ((r & 7) << 2) | ((c & 7) >> 1);
+        const int q = (ri * 2 + ci) * 2 + (c & 1);
+        double s = -Sred[(int64_t)pair * 256 + ln * 8 + q];
+        if (a == b) {
+            s += Ured[(mcon + a) * kU + tri16(r, c)];
+            if (r == c) s += mu_u;
+        }
+        S[t] = s;
+    }
+    if (t < N) {
+        const int j = mcon + (int)(t >> 4), r = (int)(t & 15);
+        E[t] = Ured[j * kU + 136 + r] - Ered[j * 16 + r];
+    }
+}
+
+}  // namespace argus

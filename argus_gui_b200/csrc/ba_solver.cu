@@ -10,8 +10,10 @@
 #include <math.h>
 #include <float.h>
 #include <vector>
+#include <algorithm>
 #include "../../include/argus_b200.h"
 #include "ba_kernels.cuh"
+#include "ba_schur_mma.cuh"
 
 using namespace argus;
 
@@ -55,6 +57,10 @@ struct argus_ba_ctx {
     DevBuf<double> W, Y, V, eb, vstate, Vinv, cvec, dbuf;
     DevBuf<double> Upart, scpart, red1, max2, Epart, Spart, red2, S, E, da_free, da_full, part3, red3, cam2, scal, att, respart;
     DevBuf<int> flags;     // [0] singular V*, [1] chol status
+    // generation-2 (tile / MMA) plan
+    int gen = 2;
+    DevBuf<int32_t> tile_pt; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
+    int ntiles = 0, tile_obs = 256, schur_G = 1, schur_NB = 1, schur_nchunk = 1;
     double *h_pinned = nullptr;   // 16 doubles
     int grid_pts128 = 1, grid_pts256 = 1, nchunks = 1, npairs = 1;
     int64_t chunk_pts = 1;
@@ -66,6 +72,11 @@ struct argus_ba_ctx {
     double prof_ms[P_COUNT]; int64_t prof_n[P_COUNT];
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0, n_allreduce = 0;
 
+    TilePlan tile_plan() const { TilePlan tp; tp.ntiles = ntiles; tp.tile_obs = tile_obs; tp.tile_pt = tile_pt.p; return tp; }
+    SchurPlan schur_plan() const {
+        SchurPlan sp; sp.G = schur_G; sp.nchunk = schur_nchunk; sp.npairs = npairs; sp.blk_jk = blk_jk.p; sp.blk_pair = blk_pair.p;
+        return sp;
+    }
     BaProblem problem() const {
         BaProblem pb;
         pb.n = n; pb.ncon = ncon; pb.m = m; pb.mcon = mcon; pb.nobs = nobs; pb.nfix_k = nfix_k; pb.nfix_d = nfix_d;
@@ -156,21 +167,41 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
 {
     const int m = c->m, mcon = c->mcon, mf = m - mcon, N = 16 * mf;
     ARGUS_CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, 2 * sizeof(int), c->stream));
-    {
-        ProfScope ps(c, P_PREPARE);
-        k_prepare<<<c->grid_pts128, 128, (size_t)m * 16 * sizeof(double), c->stream>>>(
-            c->problem(), mu, use_state, write_state, c->V.p, c->eb.p, c->vstate.p, c->W.p, c->Y.p, c->Vinv.p, c->cvec.p,
-            c->Epart.p, c->flags.p);
-    }
-    {
-        ProfScope ps(c, P_SCHUR);
-        dim3 grid(c->npairs, c->nchunks);
-        k_schur_pairs<<<grid, 256, 0, c->stream>>>(c->problem(), c->Y.p, c->W.p, c->chunk_pts, c->Spart.p);
+    if (c->gen >= 2) {
+        {
+            ProfScope ps(c, P_PREPARE);
+            k_make_z<<<c->grid_pts128, 128, (size_t)m * 16 * sizeof(double), c->stream>>>(
+                c->problem(), mu, use_state, write_state, c->V.p, c->eb.p, c->vstate.p, c->W.p, c->Z.p, c->zsign.p, c->Vinv.p,
+                c->Epart.p, c->flags.p);
+        }
+        {
+            ProfScope ps(c, P_SCHUR);
+            dim3 grid(c->schur_nchunk, c->schur_G);
+            const size_t sm = (size_t)2 * c->tile_obs * 48 * sizeof(double);
+            switch (c->schur_NB) {
+                case 1: k_schur_mma<1><<<grid, kSchurWarps * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, c->zsign.p, c->Spart.p); break;
+                case 3: k_schur_mma<3><<<grid, kSchurWarps * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, c->zsign.p, c->Spart.p); break;
+                case 5: k_schur_mma<5><<<grid, kSchurWarps * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, c->zsign.p, c->Spart.p); break;
+                default: k_schur_mma<9><<<grid, kSchurWarps * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, c->zsign.p, c->Spart.p); break;
+            }
+        }
+    } else {
+        {
+            ProfScope ps(c, P_PREPARE);
+            k_prepare<<<c->grid_pts128, 128, (size_t)m * 16 * sizeof(double), c->stream>>>(
+                c->problem(), mu, use_state, write_state, c->V.p, c->eb.p, c->vstate.p, c->W.p, c->Y.p, c->Vinv.p, c->cvec.p,
+                c->Epart.p, c->flags.p);
+        }
+        {
+            ProfScope ps(c, P_SCHUR);
+            dim3 grid(c->npairs, c->nchunks);
+            k_schur_pairs<<<grid, 256, 0, c->stream>>>(c->problem(), c->Y.p, c->W.p, c->chunk_pts, c->Spart.p);
+        }
     }
     const int64_t slen = (int64_t)c->npairs * 256;
     {
         ProfScope ps(c, P_SCHUR_REDUCE);
-        k_reduce_sum<<<(unsigned)((slen + 127) / 128), 128, 0, c->stream>>>(c->Spart.p, c->nchunks, slen, slen, c->red2.p);
+        k_reduce_sum<<<(unsigned)((slen + 127) / 128), 128, 0, c->stream>>>(c->Spart.p, c->gen >= 2 ? c->schur_nchunk : c->nchunks, slen, slen, c->red2.p);
         k_reduce_sum<<<(unsigned)((m * 16 + 127) / 128), 128, 0, c->stream>>>(c->Epart.p, c->grid_pts128, (int64_t)m * 16, (int64_t)m * 16,
                                                                              c->red2.p + slen);
     }
@@ -180,7 +211,8 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
     {
         ProfScope ps(c, P_ASSEMBLE);
         const int64_t tot = (int64_t)N * N;
-        k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(m, mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu_u, c->S.p, c->E.p);
+        if (c->gen >= 2) k_assemble_mma<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(m, mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu_u, c->S.p, c->E.p);
+        else k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(m, mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu_u, c->S.p, c->E.p);
     }
     {
         ProfScope ps(c, P_CHOL);
@@ -242,6 +274,11 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
     // opt in to large dynamic shared memory where needed
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
+    if (const char *e = getenv("ARGUS_BA_GEN")) c->gen = atoi(e);
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 384));
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 384));
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 384));
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 384));
     *out = c;
     return ARGUS_OK;
 }
@@ -256,7 +293,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
                               &c->vstate, &c->Vinv, &c->cvec, &c->dbuf, &c->Upart, &c->scpart, &c->red1, &c->max2, &c->Epart, &c->Spart,
                               &c->red2, &c->S, &c->E, &c->da_free, &c->da_full, &c->part3, &c->red3, &c->cam2, &c->scal, &c->att, &c->respart};
     for (auto *b : bufs) b->release();
-    c->flags.release();
+    c->flags.release(); c->tile_pt.release(); c->blk_jk.release(); c->blk_pair.release(); c->zsign.release(); c->Z.release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -310,19 +347,61 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         c->nchunks = want;
         c->chunk_pts = (n + want - 1) / want; if (c->chunk_pts < 1) c->chunk_pts = 1;
     }
+    // ---- generation-2 plans: point tiles (<= 32 points, <= tile_obs observations) and the block -> (group, warp, slot) map ----
+    std::vector<int32_t> tiles;
+    c->tile_obs = 256;
+    {
+        int64_t i = 0;
+        while (i < n) {
+            tiles.push_back((int32_t)i);
+            int64_t e = i; int32_t o0 = optr[i];
+            while (e < n && e - i < kTilePts && optr[e + 1] - o0 <= c->tile_obs) ++e;
+            if (e == i) ++e;
+            i = e;
+        }
+        tiles.push_back((int32_t)n);
+        c->ntiles = (int)tiles.size() - 1;
+    }
+    {
+        const int cand[4] = {1, 3, 5, 9};
+        int NB = 9;
+        for (int q = 0; q < 4; ++q) if (kSchurWarps * cand[q] >= c->npairs) { NB = cand[q]; break; }
+        c->schur_NB = NB;
+        c->schur_G = (c->npairs + kSchurWarps * NB - 1) / (kSchurWarps * NB);
+        int nch = c->sms / c->schur_G; if (nch < 1) nch = 1;
+        if (nch > c->ntiles) nch = c->ntiles > 0 ? c->ntiles : 1;
+        c->schur_nchunk = nch;
+    }
+    std::vector<uint16_t> hjk((size_t)c->schur_G * kSchurWarps * c->schur_NB, 0xFFFF);
+    std::vector<int32_t> hpair((size_t)c->schur_G * kSchurWarps * c->schur_NB, -1);
+    {
+        int pidx = 0;
+        for (int a = 0; a < mf; ++a)
+            for (int b = a; b < mf; ++b, ++pidx) {
+                const int grp = pidx % c->schur_G, q = pidx / c->schur_G, w = q % kSchurWarps, slot = q / kSchurWarps;
+                const size_t at = ((size_t)grp * kSchurWarps + w) * c->schur_NB + slot;
+                hjk[at] = (uint16_t)((mcon + a) | ((mcon + b) << 8));
+                hpair[at] = pidx;
+            }
+    }
 #define ENS(buf, cnt) ARGUS_CUDA_CHECK((buf).ensure((size_t)(cnt)))
+    ARGUS_CUDA_CHECK(c->tile_pt.ensure(tiles.size())); ARGUS_CUDA_CHECK(c->blk_jk.ensure(hjk.size())); ARGUS_CUDA_CHECK(c->blk_pair.ensure(hpair.size()));
+    ARGUS_CUDA_CHECK(c->zsign.ensure((size_t)n)); ENS(c->Z, 48 * nobs);
     ENS(c->obs_ptr, n + 1); ENS(c->obs_cam, nobs); ENS(c->obs_uv, nobs); ENS(c->pt_mask, n);
     ENS(c->rot0, 4 * m); ENS(c->cam, 16 * m); ENS(c->cam_new, 16 * m); ENS(c->cam0, 16 * m);
     ENS(c->pts, 3 * n); ENS(c->pts_new, 3 * n); ENS(c->pts0, 3 * n);
     ENS(c->W, 48 * nobs); ENS(c->Y, 48 * nobs); ENS(c->V, 6 * n); ENS(c->eb, 3 * n); ENS(c->vstate, 3 * n); ENS(c->Vinv, 6 * n);
     ENS(c->cvec, 3 * n); ENS(c->dbuf, 3 * n);
     ENS(c->Upart, (int64_t)c->grid_pts128 * m * kU); ENS(c->scpart, 4 * c->grid_pts128); ENS(c->red1, m * kU + 2); ENS(c->max2, 2);
-    ENS(c->Epart, (int64_t)c->grid_pts128 * m * 16); ENS(c->Spart, (int64_t)c->nchunks * c->npairs * 256);
+    ENS(c->Epart, (int64_t)c->grid_pts128 * m * 16); ENS(c->Spart, (int64_t)std::max(c->nchunks, c->schur_nchunk) * c->npairs * 256);
     ENS(c->red2, (int64_t)c->npairs * 256 + m * 16); ENS(c->S, (int64_t)N * N); ENS(c->E, N); ENS(c->da_free, N); ENS(c->da_full, 16 * m);
     ENS(c->part3, 3 * c->grid_pts128); ENS(c->red3, 3); ENS(c->cam2, 2); ENS(c->scal, 8); ENS(c->att, 8); ENS(c->respart, c->grid_pts256);
     ARGUS_CUDA_CHECK(c->flags.ensure(2));
 #undef ENS
     cudaStream_t s = c->stream;
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_pt.p, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_jk.p, hjk.data(), hjk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_pair.p, hpair.data(), hpair.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_ptr.p, optr.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_cam.p, ocam.data(), nobs * sizeof(uint8_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pt_mask.p, mask.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
@@ -426,7 +505,8 @@ int argus_ba_normal_equations(argus_ba_ctx *c, double mu, double *U, double *ea,
     if (S || E) {
         // re-assemble (the solve factored S in place)
         const int64_t slen = (int64_t)c->npairs * 256, tot = (int64_t)N * N;
-        k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(m, c->mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu, c->S.p, c->E.p);
+        if (c->gen >= 2) k_assemble_mma<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(m, c->mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu, c->S.p, c->E.p);
+        else k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(m, c->mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu, c->S.p, c->E.p);
         ARGUS_CUDA_CHECK(cudaGetLastError());
         if (S) ARGUS_CUDA_CHECK(cudaMemcpyAsync(S, c->S.p, tot * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (E) ARGUS_CUDA_CHECK(cudaMemcpyAsync(E, c->E.p, N * sizeof(double), cudaMemcpyDeviceToHost, s));

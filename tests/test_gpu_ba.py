@@ -174,10 +174,7 @@ def test_full_size_properties_c3():
     # permutation of the points
     perm = np.random.default_rng(0).permutation(n)
     vm_p = s["vmask"][perm]
-    order = np.argsort(perm, kind="stable")
-    rowptr = np.concatenate([[0], np.cumsum(s["vmask"].sum(axis=1))])
-    xs = [s["x"][rowptr[i]:rowptr[i + 1]] for i in perm[:0]]   # (avoid a Python loop over 200k points below)
-    obs_pt = np.repeat(np.arange(n), s["vmask"].sum(axis=1))
+    obs_pt = np.repeat(np.arange(n), s["vmask"].sum(axis=1).astype(np.int64))
     newpos = np.empty(n, dtype=np.int64); newpos[perm] = np.arange(n)
     key = newpos[obs_pt]
     o = np.argsort(key, kind="stable")
@@ -202,7 +199,7 @@ def test_m0_two_shards_equal_single(golden_ba):
     p0, rot0 = scenes.pack_ba_problem(s["cams0"], s["pts0"])
     p_ref, info_ref, ret_ref = ba.solve_motstr(s["vmask"], p0, rot0, s["x"], 2, 3, itmax=8)
     world = 2
-    rowptr = np.concatenate([[0], np.cumsum(s["vmask"].sum(axis=1))])
+    rowptr = np.concatenate([[0], np.cumsum(s["vmask"].sum(axis=1).astype(np.int64))])
     barrier = threading.Barrier(world)
     slots = [None] * world
     results = [None] * world
