@@ -1,0 +1,322 @@
+// Generation-2 linearisation: one CTA per tile of points (<= 32 points, <= TO observations), one thread per observation.
+//
+// Fuses, per LM attempt, everything the reference does between the Jacobian evaluation and the reduced system's right
+// hand side (sba_levmar.c:795-1016 and the E_j part of :1164-1185), without ever materialising the Jacobian or W:
+//   P1  per observation: project, Jacobian A (2x16), B (2x3), residual e              (img_projsKDRTS_jac_x)
+//   P2  per point (8 threads, shuffle reduction): V_i, eb_i, damping, V*_i = L D L^T, V*^-1, c_i = V*^-1 eb_i
+//   P3  per observation: e' = e - B c_i (so that E_j = sum A^T e'), W = A^T B, Z = W L^-T |D|^-1/2  -> HBM (384 B / obs)
+//   P4  per camera (one warp each, DMMA m8n8k4): Gram matrix of G = [A^T ; e^T ; e'^T] over the camera's observations
+//       in the tile: U_j (16x16), ea_j = col 16, E_j = col 17.  Deterministic: fixed order inside a tile, per-CTA
+//       shared-memory accumulators with a single owner per element, fixed-order reduction over CTAs afterwards.
+// mode 0 (first iteration, damping not known yet) does P1, P2 (V, eb only) and P4 (U, ea): the statistics for
+// mu = tau * max diag (sba_levmar.c:980-987).
+#pragma once
+#include "ba_common.cuh"
+#include "ba_schur_mma.cuh"
+
+namespace argus {
+
+constexpr int kGa = 36;          // doubles per observation in the Gram operand tile: 32 (A rows, (g, g+8) pairs) + 4 (e, e')
+constexpr int kUfrag = 320;      // per camera: 5 DMMA tiles x 64 fragment elements (lane * 10 + q)
+constexpr int kPs = 16;          // per point scratch: li[3], sq[3], c[3], sign, free
+
+struct LinTilePlan {
+    const uint8_t *obs_lpt;      // nobs: local point index of each observation inside its tile
+    const uint8_t *corder;       // nobs: per tile, local observation indices sorted by camera
+    const uint16_t *cstart;      // ntiles x (m+1): start of each camera's run in corder (local)
+};
+
+struct LinTileOut {
+    double *Z;                   // nobs x 48 (permuted, see zperm)
+    uint8_t *zsign;              // n
+    double *Vinv;                // n x 6
+    double *V;                   // n x 6 (undamped, for the parity hook)
+    double *eb;                  // n x 3
+    double *vstate;              // n x 3 (sba-1.6 compatibility state)
+    double *Upart;               // grid x m x 320
+    double *scpart;              // grid x 4: cost, max|eb|, max diag V, sum pts^2
+    int *flag;
+};
+
+__global__ void __launch_bounds__(256) k_lin_tile(BaProblem pb, TilePlan tp, LinTilePlan lp, const double *__restrict__ cam,
+                                                  const double *__restrict__ pts, int mode, double mu, int use_state, int write_state,
+                                                  LinTileOut out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);
+    double *Us = reinterpret_cast<double *>(smem_raw + (((size_t)pb.m * sizeof(CamConst) + 15) & ~(size_t)15));   // m x 320 (16-byte aligned)
+    double *Ga = Us + (size_t)pb.m * kUfrag;                        // TO x 36
+    double *Bs = Ga + (size_t)tp.tile_obs * kGa;                    // TO x 8
+    double *Ps = Bs + (size_t)tp.tile_obs * 8;                      // 32 x 16
+    __shared__ double red[32];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g8 = lane >> 2, kk = lane & 3;
+    for (int t = tid; t < pb.m * kUfrag; t += blockDim.x) Us[t] = 0.0;
+    load_cameras(sc, cam, pb.rot0, pb.m);
+
+    double cost = 0.0, ebmax = 0.0, vdmax = -1.79769313486231570e308, ptsq = 0.0;
+
+    for (int tile = blockIdx.x; tile < tp.ntiles; tile += gridDim.x) {
+        const int p0 = tp.tile_pt[tile], p1 = tp.tile_pt[tile + 1];
+        const int o0 = pb.obs_ptr[p0], nobs_t = pb.obs_ptr[p1] - o0, npts = p1 - p0;
+
+        // ---- P1: one thread per observation ----
+        int my_lp = 0, my_cam = 0;
+        if (tid < nobs_t) {
+            const int k = o0 + tid;
+            my_cam = pb.obs_cam[k];
+            my_lp = lp.obs_lpt[k];
+            const int64_t i = p0 + my_lp;
+            const double M0 = pts[3 * i], M1 = pts[3 * i + 1], M2 = pts[3 * i + 2];
+            double u, v, A[32], B[6];
+            cam_project_jac(sc[my_cam], M0, M1, M2, pb.nfix_k, pb.nfix_d, u, v, A, B);
+            const double2 z = pb.obs_uv[k];
+            const double e0 = z.x - u, e1 = z.y - v;
+            cost += e0 * e0 + e1 * e1;
+            double *g = Ga + (size_t)tid * kGa;
+            const bool cfree = my_cam >= pb.mcon;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                *reinterpret_cast<double2 *>(g + r * 2) = cfree ? make_double2(A[r], A[r + 8]) : make_double2(0.0, 0.0);
+                *reinterpret_cast<double2 *>(g + 16 + r * 2) = cfree ? make_double2(A[16 + r], A[24 + r]) : make_double2(0.0, 0.0);
+            }
+            g[32] = e0; g[33] = 0.0; g[34] = e1; g[35] = 0.0;        // [comp][{e, e'}]
+            double *b = Bs + (size_t)tid * 8;
+            const bool pfree = i >= pb.ncon;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) b[q] = pfree ? B[q] : 0.0;
+            b[6] = e0; b[7] = e1;
+        }
+        __syncthreads();
+
+        // ---- P2: 8 threads per point ----
+        {
+            const int lpt = tid >> 3, q = tid & 7;
+            double v00 = 0, v01 = 0, v02 = 0, v11 = 0, v12 = 0, v22 = 0, b0 = 0, b1 = 0, b2 = 0;
+            const bool have = lpt < npts;
+            const int64_t i = p0 + (have ? lpt : 0);
+            if (have) {
+                const int ob = pb.obs_ptr[i] - o0, oe = pb.obs_ptr[i + 1] - o0;
+                for (int o = ob + q; o < oe; o += 8) {
+                    const double *b = Bs + (size_t)o * 8;
+                    const double B0 = b[0], B1 = b[1], B2 = b[2], B3 = b[3], B4 = b[4], B5 = b[5], e0 = b[6], e1 = b[7];
+                    v00 += B0 * B0 + B3 * B3; v01 += B0 * B1 + B3 * B4; v02 += B0 * B2 + B3 * B5;
+                    v11 += B1 * B1 + B4 * B4; v12 += B1 * B2 + B4 * B5; v22 += B2 * B2 + B5 * B5;
+                    b0 += B0 * e0 + B3 * e1; b1 += B1 * e0 + B4 * e1; b2 += B2 * e0 + B5 * e1;
+                }
+            }
+#pragma unroll
+            for (int off = 4; off > 0; off >>= 1) {       // fixed-order butterfly: every lane of the group ends with the same sum
+                v00 += __shfl_xor_sync(0xffffffffu, v00, off); v01 += __shfl_xor_sync(0xffffffffu, v01, off);
+                v02 += __shfl_xor_sync(0xffffffffu, v02, off); v11 += __shfl_xor_sync(0xffffffffu, v11, off);
+                v12 += __shfl_xor_sync(0xffffffffu, v12, off); v22 += __shfl_xor_sync(0xffffffffu, v22, off);
+                b0 += __shfl_xor_sync(0xffffffffu, b0, off); b1 += __shfl_xor_sync(0xffffffffu, b1, off);
+                b2 += __shfl_xor_sync(0xffffffffu, b2, off);
+            }
+            if (have && q == 0) {
+                const bool pfree = i >= pb.ncon;
+                const double M0 = pts[3 * i], M1 = pts[3 * i + 1], M2 = pts[3 * i + 2];
+                ptsq += M0 * M0 + M1 * M1 + M2 * M2;
+                double *Vi = out.V + 6 * i;
+                Vi[0] = v00; Vi[1] = v01; Vi[2] = v02; Vi[3] = v11; Vi[4] = v12; Vi[5] = v22;
+                out.eb[3 * i] = b0; out.eb[3 * i + 1] = b1; out.eb[3 * i + 2] = b2;
+                double *P = Ps + lpt * kPs;
+#pragma unroll
+                for (int t = 0; t < 10; ++t) P[t] = 0.0;
+                if (pfree) {
+                    ebmax = fmax(ebmax, fmax(fabs(b0), fmax(fabs(b1), fabs(b2))));
+                    vdmax = fmax(vdmax, fmax(v00, fmax(v11, v22)));
+                    if (mode != 0) {
+                        double vv[6] = {v00, v01, v02, v11, v12, v22};
+                        if (use_state) { vv[0] = out.vstate[3 * i]; vv[3] = out.vstate[3 * i + 1]; vv[5] = out.vstate[3 * i + 2]; }
+                        vv[0] += mu; vv[3] += mu; vv[5] += mu;
+                        double li[3], di[3];
+                        if (!sym3_ldl_inv(vv, li, di)) {
+                            atomicOr(out.flag, 1);
+                            out.zsign[i] = 0;
+                        } else {
+                            const double n00 = di[0] + li[0] * li[0] * di[1] + li[1] * li[1] * di[2];
+                            const double n01 = li[0] * di[1] + li[1] * li[2] * di[2];
+                            const double n02 = li[1] * di[2];
+                            const double n11 = di[1] + li[2] * li[2] * di[2];
+                            const double n12 = li[2] * di[2];
+                            const double n22 = di[2];
+                            double *Ni = out.Vinv + 6 * i;
+                            Ni[0] = n00; Ni[1] = n01; Ni[2] = n02; Ni[3] = n11; Ni[4] = n12; Ni[5] = n22;
+                            if (write_state) { out.vstate[3 * i] = n00; out.vstate[3 * i + 1] = n11; out.vstate[3 * i + 2] = n22; }
+                            P[0] = li[0]; P[1] = li[1]; P[2] = li[2];
+                            P[3] = sqrt(fabs(di[0])); P[4] = sqrt(fabs(di[1])); P[5] = sqrt(fabs(di[2]));
+                            P[6] = n00 * b0 + n01 * b1 + n02 * b2; P[7] = n01 * b0 + n11 * b1 + n12 * b2; P[8] = n02 * b0 + n12 * b1 + n22 * b2;
+                            out.zsign[i] = (uint8_t)((di[0] < 0.0 ? 1 : 0) | (di[1] < 0.0 ? 2 : 0) | (di[2] < 0.0 ? 4 : 0));
+                        }
+                    }
+                } else if (mode != 0) {
+                    out.zsign[i] = 0;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- P3: per observation: e' and Z ----
+        if (mode != 0 && tid < nobs_t) {
+            const double *P = Ps + my_lp * kPs;
+            const double *b = Bs + (size_t)tid * 8;
+            const double B0 = b[0], B1 = b[1], B2 = b[2], B3 = b[3], B4 = b[4], B5 = b[5];
+            double *g = Ga + (size_t)tid * kGa;
+            const double c0 = P[6], c1 = P[7], c2 = P[8];
+            g[33] = b[6] - (B0 * c0 + B1 * c1 + B2 * c2);
+            g[35] = b[7] - (B3 * c0 + B4 * c1 + B5 * c2);
+            const double l0 = P[0], l1 = P[1], l2 = P[2], s0 = P[3], s1 = P[4], s2 = P[5];
+            double *Zk = out.Z + 48 * (int64_t)(o0 + tid);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const double2 a0 = *reinterpret_cast<const double2 *>(g + r * 2);          // du/da_r, du/da_{r+8}
+                const double2 a1 = *reinterpret_cast<const double2 *>(g + 16 + r * 2);     // dv/da_r, dv/da_{r+8}
+                const double wl0 = a0.x * B0 + a1.x * B3, wl1 = a0.x * B1 + a1.x * B4, wl2 = a0.x * B2 + a1.x * B5;   // row r
+                const double wh0 = a0.y * B0 + a1.y * B3, wh1 = a0.y * B1 + a1.y * B4, wh2 = a0.y * B2 + a1.y * B5;   // row r + 8
+                // layout ((r%8)*3 + c)*2 + r/8: the (r, r+8) pair of one component is one 16-byte store
+                *reinterpret_cast<double2 *>(Zk + (r * 3 + 0) * 2) = make_double2(wl0 * s0, wh0 * s0);
+                *reinterpret_cast<double2 *>(Zk + (r * 3 + 1) * 2) = make_double2((l0 * wl0 + wl1) * s1, (l0 * wh0 + wh1) * s1);
+                *reinterpret_cast<double2 *>(Zk + (r * 3 + 2) * 2) = make_double2((l1 * wl0 + l2 * wl1 + wl2) * s2, (l1 * wh0 + l2 * wh1 + wh2) * s2);
+            }
+        }
+        __syncthreads();
+
+        // ---- P4: Gram per camera on the tensor pipe ----
+        {
+            const uint16_t *cs = lp.cstart + (size_t)tile * (pb.m + 1);
+            const uint8_t *co = lp.corder + o0;
+            for (int j = pb.mcon + warp; j < pb.m; j += 8) {
+                const int c0 = cs[j], nj = cs[j + 1] - c0;
+                if (nj == 0) continue;
+                double a00[2] = {0, 0}, a01[2] = {0, 0}, a11[2] = {0, 0}, a02[2] = {0, 0}, a12[2] = {0, 0};
+                for (int s = 0; s < nj; s += 2) {
+                    const int idx = s + (kk >> 1);
+                    const bool valid = idx < nj;
+                    const int o = co[c0 + (valid ? idx : 0)];
+                    const int comp = kk & 1;
+                    const double *g = Ga + (size_t)o * kGa;
+                    double2 a = *reinterpret_cast<const double2 *>(g + comp * 16 + g8 * 2);
+                    double ax = (g8 < 2) ? g[32 + comp * 2 + g8] : 0.0;
+                    if (!valid) { a.x = 0.0; a.y = 0.0; ax = 0.0; }
+                    dmma884(a00[0], a00[1], a.x, a.x);
+                    dmma884(a01[0], a01[1], a.x, a.y);
+                    dmma884(a11[0], a11[1], a.y, a.y);
+                    dmma884(a02[0], a02[1], a.x, ax);
+                    dmma884(a12[0], a12[1], a.y, ax);
+                }
+                double *u = Us + (size_t)j * kUfrag + lane * 10;
+                u[0] += a00[0]; u[1] += a00[1]; u[2] += a01[0]; u[3] += a01[1]; u[4] += a11[0]; u[5] += a11[1];
+                u[6] += a02[0]; u[7] += a02[1]; u[8] += a12[0]; u[9] += a12[1];
+            }
+        }
+        __syncthreads();
+    }
+
+    for (int t = tid; t < pb.m * kUfrag; t += blockDim.x) out.Upart[(size_t)blockIdx.x * pb.m * kUfrag + t] = Us[t];
+    const double s0 = block_sum(cost, red), s1 = block_max(ebmax, red), s2 = block_max(vdmax, red), s3 = block_sum(ptsq, red);
+    if (tid == 0) {
+        out.scpart[4 * blockIdx.x + 0] = s0; out.scpart[4 * blockIdx.x + 1] = s1;
+        out.scpart[4 * blockIdx.x + 2] = s2; out.scpart[4 * blockIdx.x + 3] = s3;
+    }
+}
+
+// Fixed-order reduction of the per-CTA Gram fragments into the packed per-camera layout the rest of the solver uses:
+//   Ured[j][0..135] upper triangle of U_j, [136..151] ea_j;  Eout[j][0..15] = E_j (= sum A^T e').
+// Also reduces the scalar partials: sum2 = {cost, sum pts^2}, max2 = {max|eb|, max diag V}.  grid = m blocks of 192.
+__global__ void __launch_bounds__(192) k_lin_tile_reduce(int m, int nparts, const double *__restrict__ Upart, const double *__restrict__ scpart,
+                                                         double *__restrict__ Ured, double *__restrict__ Eout, double *__restrict__ sum2,
+                                                         double *__restrict__ max2)
+{
+    const int j = blockIdx.x, t = threadIdx.x;
+    if (t < 168) {
+        // element -> (tile, row, col) of the 24-column Gram matrix
+        int r, c;
+        if (t < 136) { r = 0; int q = t; while (q >= 16 - r) { q -= 16 - r; ++r; } c = r + q; }
+        else if (t < 152) { r = t - 136; c = 16; }
+        else { r = t - 152; c = 17; }
+        int tl, rr = r & 7, cc;
+        if (c < 8) { tl = 0; cc = c; }                    // (0,0)
+        else if (c < 16) { tl = (r < 8) ? 1 : 2; cc = c - 8; }   // (0,1) or (1,1)
+        else { tl = (r < 8) ? 3 : 4; cc = c - 16; }       // (0,2) or (1,2)
+        const int ln = (rr << 2) | (cc >> 1);
+        const int idx = ln * 10 + tl * 2 + (cc & 1);
+        double s = 0.0;
+        const double *p = Upart + (size_t)j * kUfrag + idx;
+        for (int q = 0; q < nparts; ++q) s += p[(size_t)q * m * kUfrag];
+        if (t < 152) Ured[j * kU + t] = s; else Eout[j * 16 + (t - 152)] = s;
+    }
+    if (j == 0 && t >= 168 && t < 172) {
+        const int w = t - 168;
+        double s = (w == 1) ? 0.0 : ((w == 2) ? -1.79769313486231570e308 : 0.0);
+        for (int q = 0; q < nparts; ++q) {
+            const double v = scpart[4 * q + w];
+            if (w == 1 || w == 2) s = fmax(s, v); else s += v;
+        }
+        if (w == 0) sum2[0] = s; else if (w == 3) sum2[1] = s; else if (w == 1) max2[0] = s; else max2[1] = s;
+    }
+}
+
+// Generation-2 back-substitution + trial evaluation, one thread per point, nothing per-observation is read back from
+// HBM except the measurement: the Jacobian is re-evaluated (about 6x cheaper than streaming 384 B of W per observation).
+//   db_i = V*_i^-1 (eb_i - sum_j B_ij^T (A_ij da_j))      (sba_levmar.c:1215-1256, W_ij^T da_j = B_ij^T A_ij da_j)
+//   trial point, cost at (cam_new, pts_new)                 (sba_levmar.c:1261-1288)
+__global__ void __launch_bounds__(128) k_backsub_recompute(BaProblem pb, double mu, const double *__restrict__ cam,
+                                                           const double *__restrict__ cam_new, const double *__restrict__ da,
+                                                           const double *__restrict__ pts, const double *__restrict__ Vinv,
+                                                           const double *__restrict__ eb, double *__restrict__ pts_new,
+                                                           double *__restrict__ dbout, double *__restrict__ part)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);          // old cameras
+    CamConst *sn = sc + pb.m;                                        // trial cameras
+    double *das = reinterpret_cast<double *>(sn + pb.m);             // 16 m
+    __shared__ double red[32];
+    for (int t = threadIdx.x; t < 16 * pb.m; t += blockDim.x) das[t] = da[t];
+    for (int j = threadIdx.x; j < pb.m; j += blockDim.x) { cam_precompute(cam + 16 * j, pb.rot0 + 4 * j, sc[j]); cam_precompute(cam_new + 16 * j, pb.rot0 + 4 * j, sn[j]); }
+    __syncthreads();
+    double cost = 0.0, dbsq = 0.0, dl = 0.0;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < pb.n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + threadIdx.x;
+        if (i >= pb.n) continue;
+        const double M0 = pts[3 * i], M1 = pts[3 * i + 1], M2 = pts[3 * i + 2];
+        const int k0 = pb.obs_ptr[i], k1 = pb.obs_ptr[i + 1];
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+        if (i >= pb.ncon) {
+            const double b0 = eb[3 * i], b1 = eb[3 * i + 1], b2 = eb[3 * i + 2];
+            double t0 = b0, t1 = b1, t2 = b2;
+            for (int k = k0; k < k1; ++k) {
+                const int j = pb.obs_cam[k];
+                if (j < pb.mcon) continue;
+                double u, v, A[32], B[6];
+                cam_project_jac(sc[j], M0, M1, M2, pb.nfix_k, pb.nfix_d, u, v, A, B);
+                const double *dj = das + 16 * j;
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) { s0 += A[r] * dj[r]; s1 += A[16 + r] * dj[r]; }
+                t0 -= B[0] * s0 + B[3] * s1; t1 -= B[1] * s0 + B[4] * s1; t2 -= B[2] * s0 + B[5] * s1;
+            }
+            const double *Ni = Vinv + 6 * i;
+            d0 = Ni[0] * t0 + Ni[1] * t1 + Ni[2] * t2;
+            d1 = Ni[1] * t0 + Ni[3] * t1 + Ni[4] * t2;
+            d2 = Ni[2] * t0 + Ni[4] * t1 + Ni[5] * t2;
+            dbsq += d0 * d0 + d1 * d1 + d2 * d2;
+            dl += d0 * (mu * d0 + b0) + d1 * (mu * d1 + b1) + d2 * (mu * d2 + b2);
+        }
+        if (dbout) { dbout[3 * i] = d0; dbout[3 * i + 1] = d1; dbout[3 * i + 2] = d2; }
+        const double N0 = M0 + d0, N1 = M1 + d1, N2 = M2 + d2;
+        pts_new[3 * i] = N0; pts_new[3 * i + 1] = N1; pts_new[3 * i + 2] = N2;
+        for (int k = k0; k < k1; ++k) {
+            double u, v;
+            cam_project(sn[pb.obs_cam[k]], N0, N1, N2, u, v);
+            const double2 z = pb.obs_uv[k];
+            const double e0 = z.x - u, e1 = z.y - v;
+            cost += e0 * e0 + e1 * e1;
+        }
+    }
+    const double s0 = block_sum(cost, red), s1 = block_sum(dbsq, red), s2 = block_sum(dl, red);
+    if (threadIdx.x == 0) { part[3 * blockIdx.x] = s0; part[3 * blockIdx.x + 1] = s1; part[3 * blockIdx.x + 2] = s2; }
+}
+
+}  // namespace argus

@@ -275,10 +275,10 @@ __global__ void __launch_bounds__(kSchurWarps * 32, 1) k_schur_mma(BaProblem pb,
 }
 
 // Assemble S, E from fragment-ordered Schur sums (see k_schur_mma) and the reduced U / ea:
-//   S_jk = delta_jk (U_j + mu_u I) - P_jk,  E_j = ea_j - Ered_j; the lower block triangle (and the (hi,lo) sub-tile of the
+//   S_jk = delta_jk (U_j + mu_u I) - P_jk,  E_j = ea_j - Ered_j (or Ered_j itself when the tile kernel produced E directly); the lower block triangle (and the (hi,lo) sub-tile of the
 //   diagonal blocks, which the MMA kernel skips) is mirrored.
 __global__ void k_assemble_mma(int m, int mcon, const double *__restrict__ Ured, const double *__restrict__ Sred,
-                               const double *__restrict__ Ered, double mu_u, double *__restrict__ S, double *__restrict__ E)
+                               const double *__restrict__ Ered, double mu_u, double *__restrict__ S, double *__restrict__ E, bool e_direct)
 {
     const int mf = m - mcon, N = 16 * mf;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -299,7 +299,7 @@ __global__ void k_assemble_mma(int m, int mcon, const double *__restrict__ Ured,
     }
     if (t < N) {
         const int j = mcon + (int)(t >> 4), r = (int)(t & 15);
-        E[t] = Ured[j * kU + 136 + r] - Ered[j * 16 + r];
+        E[t] = e_direct ? Ered[j * 16 + r] : Ured[j * kU + 136 + r] - Ered[j * 16 + r];
     }
 }
 

@@ -14,6 +14,7 @@
 #include "../../include/argus_b200.h"
 #include "ba_kernels.cuh"
 #include "ba_schur_mma.cuh"
+#include "ba_lin_tile.cuh"
 
 using namespace argus;
 
@@ -58,8 +59,10 @@ struct argus_ba_ctx {
     DevBuf<double> Upart, scpart, red1, max2, Epart, Spart, red2, S, E, da_free, da_full, part3, red3, cam2, scal, att, respart;
     DevBuf<int> flags;     // [0] singular V*, [1] chol status
     // generation-2 (tile / MMA) plan
-    int gen = 2;
+    int gen = 3;
     DevBuf<int32_t> tile_pt; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
+    DevBuf<uint8_t> obs_lpt, corder; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect;
+    int grid_lin = 1; size_t lin_smem = 0;
     int ntiles = 0, tile_obs = 256, schur_G = 1, schur_NB = 1, schur_nchunk = 1;
     double *h_pinned = nullptr;   // 16 doubles
     int grid_pts128 = 1, grid_pts256 = 1, nchunks = 1, npairs = 1;
@@ -76,6 +79,11 @@ struct argus_ba_ctx {
     SchurPlan schur_plan() const {
         SchurPlan sp; sp.G = schur_G; sp.nchunk = schur_nchunk; sp.npairs = npairs; sp.blk_jk = blk_jk.p; sp.blk_pair = blk_pair.p;
         return sp;
+    }
+    LinTilePlan lin_plan() const { LinTilePlan lp; lp.obs_lpt = obs_lpt.p; lp.corder = corder.p; lp.cstart = cstart.p; return lp; }
+    LinTileOut lin_out() {
+        LinTileOut o; o.Z = Z.p; o.zsign = zsign.p; o.Vinv = Vinv.p; o.V = V.p; o.eb = eb.p; o.vstate = vstate.p; o.Upart = Upart2.p;
+        o.scpart = scpart.p; o.flag = flags.p; return o;
     }
     BaProblem problem() const {
         BaProblem pb;
@@ -135,10 +143,13 @@ int run_residual(argus_ba_ctx *c, const double *cam, const double *pts, double *
     return do_allreduce(c, c->red3.p, 1, 0);
 }
 
+int run_lin_tile(argus_ba_ctx *c, int mode, double mu, int use_state, int write_state);
+
 // ---- linearise at (cam, pts): W, V, eb, reduced U/ea in red1, scalars in scal[0..3] ----
 int run_linearize(argus_ba_ctx *c)
 {
     const int m = c->m;
+    if (c->gen >= 3) return run_lin_tile(c, 0, 0.0, 0, 0);
     {
         ProfScope ps(c, P_LINEARIZE);
         const size_t sm = cam_smem(m) + (size_t)m * kU * sizeof(double);
@@ -162,13 +173,44 @@ int run_linearize(argus_ba_ctx *c)
     return ARGUS_OK;
 }
 
+// ---- generation 2: tile linearisation (mode 0: statistics only; mode 1: + damping, Z, E) ----
+int run_lin_tile(argus_ba_ctx *c, int mode, double mu, int use_state, int write_state)
+{
+    const int m = c->m;
+    if (mode != 0) ARGUS_CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, sizeof(int), c->stream));
+    {
+        ProfScope ps(c, P_LINEARIZE);
+        k_lin_tile<<<c->grid_lin, 256, c->lin_smem, c->stream>>>(c->problem(), c->tile_plan(), c->lin_plan(), c->cam.p, c->pts.p, mode, mu,
+                                                                use_state, write_state, c->lin_out());
+    }
+    const int64_t slen = (int64_t)c->npairs * 256;
+    {
+        ProfScope ps(c, P_LIN_REDUCE);
+        k_lin_tile_reduce<<<m, 192, 0, c->stream>>>(m, c->grid_lin, c->Upart2.p, c->scpart.p, c->red1.p, c->red2.p + slen,
+                                                   c->red1.p + (int64_t)m * kU, c->max2.p);
+    }
+    c->launches += 2;
+    ARGUS_CUDA_CHECK(cudaGetLastError());
+    int rc = do_allreduce(c, c->red1.p, (int64_t)m * kU + 2, 0);
+    if (rc) return rc;
+    rc = do_allreduce(c, c->max2.p, 2, 1);
+    if (rc) return rc;
+    k_lin_finalize<<<1, 32, 0, c->stream>>>(c->red1.p, c->cam.p, m, c->mcon, c->red1.p + (int64_t)m * kU, c->max2.p, c->scal.p);
+    c->launches += 1;
+    ARGUS_CUDA_CHECK(cudaGetLastError());
+    return ARGUS_OK;
+}
+
 // ---- one damping attempt: prepare, Schur complement, solve, back-substitute, evaluate; scalars in att[0..3] ----
-int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int write_state, double *dbout)
+int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int write_state, double *dbout, bool need_lin = true)
 {
     const int m = c->m, mcon = c->mcon, mf = m - mcon, N = 16 * mf;
-    ARGUS_CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, 2 * sizeof(int), c->stream));
+    if (c->gen < 3) ARGUS_CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, 2 * sizeof(int), c->stream));
+    else ARGUS_CUDA_CHECK(cudaMemsetAsync(c->flags.p + 1, 0, sizeof(int), c->stream));
     if (c->gen >= 2) {
-        {
+        if (c->gen >= 3) {
+            if (need_lin) { int rc0 = run_lin_tile(c, 1, mu, use_state, write_state); if (rc0) return rc0; }
+        } else {
             ProfScope ps(c, P_PREPARE);
             k_make_z<<<c->grid_pts128, 128, (size_t)m * 16 * sizeof(double), c->stream>>>(
                 c->problem(), mu, use_state, write_state, c->V.p, c->eb.p, c->vstate.p, c->W.p, c->Z.p, c->zsign.p, c->Vinv.p,
@@ -202,8 +244,9 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
     {
         ProfScope ps(c, P_SCHUR_REDUCE);
         k_reduce_sum<<<(unsigned)((slen + 127) / 128), 128, 0, c->stream>>>(c->Spart.p, c->gen >= 2 ? c->schur_nchunk : c->nchunks, slen, slen, c->red2.p);
-        k_reduce_sum<<<(unsigned)((m * 16 + 127) / 128), 128, 0, c->stream>>>(c->Epart.p, c->grid_pts128, (int64_t)m * 16, (int64_t)m * 16,
-                                                                             c->red2.p + slen);
+        if (c->gen < 3)
+            k_reduce_sum<<<(unsigned)((m * 16 + 127) / 128), 128, 0, c->stream>>>(c->Epart.p, c->grid_pts128, (int64_t)m * 16, (int64_t)m * 16,
+                                                                                 c->red2.p + slen);
     }
     ARGUS_CUDA_CHECK(cudaGetLastError());
     int rc = do_allreduce(c, c->red2.p, slen + (int64_t)m * 16, 0);
@@ -211,7 +254,7 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
     {
         ProfScope ps(c, P_ASSEMBLE);
         const int64_t tot = (int64_t)N * N;
-        if (c->gen >= 2) k_assemble_mma<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(m, mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu_u, c->S.p, c->E.p);
+        if (c->gen >= 2) k_assemble_mma<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(m, mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu_u, c->S.p, c->E.p, c->gen >= 3);
         else k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(m, mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu_u, c->S.p, c->E.p);
     }
     {
@@ -224,9 +267,15 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
     {
         ProfScope ps(c, P_BACKSUB);
         k_cam_update<<<1, 256, 0, c->stream>>>(m, mcon, c->cam.p, c->da_free.p, c->red1.p, mu, c->cam_new.p, c->da_full.p, c->cam2.p);
-        const size_t sm = cam_smem(m) + (size_t)m * 16 * sizeof(double);
-        k_backsub_eval<<<c->grid_pts128, 128, sm, c->stream>>>(c->problem(), mu, c->cam_new.p, c->da_full.p, c->pts.p, c->W.p, c->Vinv.p,
-                                                              c->eb.p, c->pts_new.p, dbout, c->part3.p);
+        if (c->gen >= 3) {
+            const size_t sm = 2 * cam_smem(m) + (size_t)m * 16 * sizeof(double);
+            k_backsub_recompute<<<c->grid_pts128, 128, sm, c->stream>>>(c->problem(), mu, c->cam.p, c->cam_new.p, c->da_full.p, c->pts.p,
+                                                                       c->Vinv.p, c->eb.p, c->pts_new.p, dbout, c->part3.p);
+        } else {
+            const size_t sm = cam_smem(m) + (size_t)m * 16 * sizeof(double);
+            k_backsub_eval<<<c->grid_pts128, 128, sm, c->stream>>>(c->problem(), mu, c->cam_new.p, c->da_full.p, c->pts.p, c->W.p, c->Vinv.p,
+                                                                  c->eb.p, c->pts_new.p, dbout, c->part3.p);
+        }
         k_reduce_sum<<<1, 32, 0, c->stream>>>(c->part3.p, c->grid_pts128, 3, 3, c->red3.p);
     }
     ARGUS_CUDA_CHECK(cudaGetLastError());
@@ -293,6 +342,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
                               &c->vstate, &c->Vinv, &c->cvec, &c->dbuf, &c->Upart, &c->scpart, &c->red1, &c->max2, &c->Epart, &c->Spart,
                               &c->red2, &c->S, &c->E, &c->da_free, &c->da_full, &c->part3, &c->red3, &c->cam2, &c->scal, &c->att, &c->respart};
     for (auto *b : bufs) b->release();
+    c->obs_lpt.release(); c->corder.release(); c->cstart.release(); c->Upart2.release(); c->Edirect.release();
     c->flags.release(); c->tile_pt.release(); c->blk_jk.release(); c->blk_pair.release(); c->zsign.release(); c->Z.release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -349,7 +399,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     }
     // ---- generation-2 plans: point tiles (<= 32 points, <= tile_obs observations) and the block -> (group, warp, slot) map ----
     std::vector<int32_t> tiles;
-    c->tile_obs = 256;
+    c->tile_obs = (m > 36) ? 128 : 256;
     {
         int64_t i = 0;
         while (i < n) {
@@ -372,6 +422,28 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         if (nch > c->ntiles) nch = c->ntiles > 0 ? c->ntiles : 1;
         c->schur_nchunk = nch;
     }
+    // per-observation local point index, per-tile camera-sorted observation order (static: visibility never changes)
+    std::vector<uint8_t> hlpt((size_t)nobs), hcord((size_t)nobs);
+    std::vector<uint16_t> hcst((size_t)c->ntiles * (m + 1));
+    {
+        std::vector<int> cnt(m + 1);
+        for (int tl = 0; tl < c->ntiles; ++tl) {
+            const int32_t p0 = tiles[tl], p1 = tiles[tl + 1], o0 = optr[p0], o1 = optr[p1];
+            std::fill(cnt.begin(), cnt.end(), 0);
+            for (int32_t p = p0; p < p1; ++p)
+                for (int32_t k = optr[p]; k < optr[p + 1]; ++k) { hlpt[k] = (uint8_t)(p - p0); cnt[ocam[k] + 1]++; }
+            for (int j = 0; j < m; ++j) cnt[j + 1] += cnt[j];
+            uint16_t *cs = hcst.data() + (size_t)tl * (m + 1);
+            for (int j = 0; j <= m; ++j) cs[j] = (uint16_t)cnt[j];
+            for (int32_t k = o0; k < o1; ++k) hcord[o0 + cnt[ocam[k]]++] = (uint8_t)(k - o0);
+        }
+    }
+    c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)m * kUfrag * sizeof(double) + (size_t)c->tile_obs * (kGa + 8) * sizeof(double) +
+                  (size_t)kTilePts * kPs * sizeof(double);
+    {
+        int occ = (int)((220 * 1024) / (c->lin_smem + 1024)); if (occ < 1) occ = 1; if (occ > 4) occ = 4;
+        c->grid_lin = std::min(c->ntiles > 0 ? c->ntiles : 1, c->sms * occ);
+    }
     std::vector<uint16_t> hjk((size_t)c->schur_G * kSchurWarps * c->schur_NB, 0xFFFF);
     std::vector<int32_t> hpair((size_t)c->schur_G * kSchurWarps * c->schur_NB, -1);
     {
@@ -386,19 +458,26 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     }
 #define ENS(buf, cnt) ARGUS_CUDA_CHECK((buf).ensure((size_t)(cnt)))
     ARGUS_CUDA_CHECK(c->tile_pt.ensure(tiles.size())); ARGUS_CUDA_CHECK(c->blk_jk.ensure(hjk.size())); ARGUS_CUDA_CHECK(c->blk_pair.ensure(hpair.size()));
-    ARGUS_CUDA_CHECK(c->zsign.ensure((size_t)n)); ENS(c->Z, 48 * nobs);
+    ARGUS_CUDA_CHECK(c->zsign.ensure((size_t)n)); if (c->gen >= 2) { ENS(c->Z, 48 * nobs); }
+    ARGUS_CUDA_CHECK(c->obs_lpt.ensure((size_t)nobs)); ARGUS_CUDA_CHECK(c->corder.ensure((size_t)nobs)); ARGUS_CUDA_CHECK(c->cstart.ensure(hcst.size()));
+    ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag);
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_lin_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lin_smem));
     ENS(c->obs_ptr, n + 1); ENS(c->obs_cam, nobs); ENS(c->obs_uv, nobs); ENS(c->pt_mask, n);
     ENS(c->rot0, 4 * m); ENS(c->cam, 16 * m); ENS(c->cam_new, 16 * m); ENS(c->cam0, 16 * m);
     ENS(c->pts, 3 * n); ENS(c->pts_new, 3 * n); ENS(c->pts0, 3 * n);
-    ENS(c->W, 48 * nobs); ENS(c->Y, 48 * nobs); ENS(c->V, 6 * n); ENS(c->eb, 3 * n); ENS(c->vstate, 3 * n); ENS(c->Vinv, 6 * n);
+    if (c->gen < 3) { ENS(c->W, 48 * nobs); }
+    if (c->gen < 2) { ENS(c->Y, 48 * nobs); } ENS(c->V, 6 * n); ENS(c->eb, 3 * n); ENS(c->vstate, 3 * n); ENS(c->Vinv, 6 * n);
     ENS(c->cvec, 3 * n); ENS(c->dbuf, 3 * n);
-    ENS(c->Upart, (int64_t)c->grid_pts128 * m * kU); ENS(c->scpart, 4 * c->grid_pts128); ENS(c->red1, m * kU + 2); ENS(c->max2, 2);
+    ENS(c->Upart, (int64_t)c->grid_pts128 * m * kU); ENS(c->scpart, 4 * std::max(c->grid_pts128, c->grid_lin)); ENS(c->red1, m * kU + 2); ENS(c->max2, 2);
     ENS(c->Epart, (int64_t)c->grid_pts128 * m * 16); ENS(c->Spart, (int64_t)std::max(c->nchunks, c->schur_nchunk) * c->npairs * 256);
     ENS(c->red2, (int64_t)c->npairs * 256 + m * 16); ENS(c->S, (int64_t)N * N); ENS(c->E, N); ENS(c->da_free, N); ENS(c->da_full, 16 * m);
     ENS(c->part3, 3 * c->grid_pts128); ENS(c->red3, 3); ENS(c->cam2, 2); ENS(c->scal, 8); ENS(c->att, 8); ENS(c->respart, c->grid_pts256);
     ARGUS_CUDA_CHECK(c->flags.ensure(2));
 #undef ENS
     cudaStream_t s = c->stream;
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_lpt.p, hlpt.data(), hlpt.size(), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->corder.p, hcord.data(), hcord.size(), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cstart.p, hcst.data(), hcst.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_pt.p, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_jk.p, hjk.data(), hjk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_pair.p, hpair.data(), hpair.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
@@ -505,7 +584,7 @@ int argus_ba_normal_equations(argus_ba_ctx *c, double mu, double *U, double *ea,
     if (S || E) {
         // re-assemble (the solve factored S in place)
         const int64_t slen = (int64_t)c->npairs * 256, tot = (int64_t)N * N;
-        if (c->gen >= 2) k_assemble_mma<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(m, c->mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu, c->S.p, c->E.p);
+        if (c->gen >= 2) k_assemble_mma<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(m, c->mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu, c->S.p, c->E.p, c->gen >= 3);
         else k_assemble<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(m, c->mcon, c->red1.p, c->red2.p, c->red2.p + slen, mu, c->S.p, c->E.p);
         ARGUS_CUDA_CHECK(cudaGetLastError());
         if (S) ARGUS_CUDA_CHECK(cudaMemcpyAsync(S, c->S.p, tot * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -547,7 +626,11 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
     if (!isfinite(p_eL2)) stop = 7;
 
     for (itno = 0; itno < itmax && !stop; ++itno) {
-        if ((rc = run_linearize(c))) return rc;
+        // generation 3: once mu is known the tile kernel linearises AND prepares the first attempt (Z, E) in one pass
+        bool z_valid = false;
+        if (c->gen >= 3 && itno > 0) { rc = run_lin_tile(c, 1, mu, 0, compat ? 1 : 0); z_valid = true; }
+        else rc = run_linearize(c);
+        if (rc) return rc;
         ++njev;
         if ((rc = read_back(c, c->scal.p, 4, h))) return rc;
         eab_inf = h[1]; p_L2 = h[2]; dmax = h[3];
@@ -557,7 +640,9 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
         bool first = true;
         while (1) {
             mu_u = compat ? mu_u + mu : mu;
-            if ((rc = run_attempt(c, mu, mu_u, compat && !first, compat, nullptr))) return rc;
+            // generation 3: Z / E depend on mu, so the tile linearisation runs once per attempt with the damping applied
+            if ((rc = run_attempt(c, mu, mu_u, compat && !first, compat, nullptr, !z_valid))) return rc;
+            z_valid = false;
             if ((rc = read_back(c, c->att.p, 5, h))) return rc;
             first = false;
             const bool singular = h[4] != 0.0;
