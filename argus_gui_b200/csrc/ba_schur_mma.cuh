@@ -128,28 +128,78 @@ __global__ void __launch_bounds__(128) k_make_z(BaProblem pb, double mu, int use
     for (int t = threadIdx.x; t < pb.m * 16; t += blockDim.x) Epart[(int64_t)blockIdx.x * pb.m * 16 + t] = Es[t];
 }
 
-// The Schur kernel.  grid = (nchunk, G), 256 threads.  Dynamic shared memory: 2 tiles of TO x 48 doubles.
+// The Schur kernel.  grid = (nchunk, G); NW warps, each owning NB blocks; lane 0 of warp 0 doubles as the copy producer.
+// Dynamic shared memory: 2 x [Z tile: TO x 48 doubles | rank tile: 32 x mp bytes], then a 64-byte block of zeros.
 // Spart[chunk][pair][256]: per-chunk partial sums in fragment order (lane * 8 + q), q = (ri*2 + ci)*2 + e for the
 // 8x8 sub-tile (ri, ci) of the block: element (row = ri*8 + lane>>2, col = ci*8 + 2*(lane&3) + e).
-template <int NB>
-__global__ void __launch_bounds__(kSchurWarps * 32, 1) k_schur_mma(BaProblem pb, TilePlan tp, SchurPlan sp, const double *__restrict__ Z,
-                                                                    const uint8_t *__restrict__ zsign, double *__restrict__ Spart)
+//
+// pt_rank[n][mp] (uint8, static): position of camera j in point i's observation list, 0xFF when i does not see j (or i is
+// a fixed point).  It travels with the Z tile, so finding the points that see both cameras of a block is two byte loads.
+// K mapping: one hit (K = 3, padded to the DMMA's 4) per step; the k-lanes 0..2 of a step read the three components of the
+// same observation at consecutive 16-byte addresses, which is free of shared-memory bank conflicts (a 4-hits-per-3-steps
+// packing was measured slower: its four k-lanes read different observations at the same in-row offset = 4-way conflicts).
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
+{
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ double flip_sign(double v, uint32_t bit)      // bit = 0 or 1
+{
+    return __hiloint2double(__double2hiint(v) ^ (int)(bit << 31), __double2loint(v));
+}
+
+template <int NB, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(BaProblem pb, TilePlan tp, SchurPlan sp, const double *__restrict__ Z,
+                                                                 const uint8_t *__restrict__ zsign, const uint8_t *__restrict__ pt_rank,
+                                                                 int mp, double *__restrict__ Spart)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *zbuf0 = reinterpret_cast<double *>(smem_raw);
-    double *zbuf1 = zbuf0 + (size_t)tp.tile_obs * 48;
-    __shared__ __align__(8) uint64_t mbar[2];
-    __shared__ uint32_t hitlist[kSchurWarps][kTilePts];
+    const uint32_t zbytes = (uint32_t)tp.tile_obs * 384u;
+    const uint32_t stage = zbytes + (uint32_t)kTilePts * (uint32_t)mp;          // multiple of 16
+    unsigned char *zero_blk = smem_raw + 2 * stage;
+    __shared__ __align__(8) uint64_t mfull[2], mempty[2];
+    __shared__ uint32_t hitlist[NW][kTilePts];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g8 = lane >> 2, kk = lane & 3;
     const int chunk = blockIdx.x, grp = blockIdx.y;
+    const int ntl = (tp.ntiles > chunk) ? (tp.ntiles - chunk + sp.nchunk - 1) / sp.nchunk : 0;   // tiles of this chunk
 
-    // this warp's block slots
+    if (threadIdx.x < 16) reinterpret_cast<uint32_t *>(zero_blk)[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) { mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1); mbar_init(&mempty[0], NW); mbar_init(&mempty[1], NW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    // producer duty (warp 0, lane 0): bulk-async copies of the Z rows and the rank rows of local tile `it` into stage it & 1,
+    // after every warp has released that stage (mempty)
+    auto produce = [&](int it) {
+        if (warp == 0 && lane == 0) {
+            const int b = it & 1;
+            if (it >= 2) mbar_wait(&mempty[b], (uint32_t)(((it >> 1) - 1) & 1));
+            const int t = chunk + it * sp.nchunk;
+            const int p0 = tp.tile_pt[t], p1 = tp.tile_pt[t + 1];
+            const int o0 = pb.obs_ptr[p0], o1 = pb.obs_ptr[p1];
+            const uint32_t zb = (uint32_t)(o1 - o0) * 384u, rb = (uint32_t)(p1 - p0) * (uint32_t)mp;
+            unsigned char *dst = smem_raw + (size_t)b * stage;
+            const char *src = reinterpret_cast<const char *>(Z + 48 * (int64_t)o0);
+            mbar_expect_tx(&mfull[b], zb + rb);
+            for (uint32_t off = 0; off < zb; off += 8192u) bulk_g2s(dst + off, src + off, (zb - off < 8192u) ? (zb - off) : 8192u, &mfull[b]);
+            bulk_g2s(dst + zbytes, pt_rank + (size_t)p0 * mp, rb, &mfull[b]);
+        }
+        __syncwarp();
+    };
+    if (ntl > 0) produce(0);
+
+    // ---------------- consumer warps ----------------
     int bj[NB], bk[NB];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        const uint16_t jk = sp.blk_jk[((size_t)grp * kSchurWarps + warp) * NB + b];
+        const uint16_t jk = sp.blk_jk[((size_t)grp * NW + warp) * NB + b];
         bj[b] = (jk == 0xFFFF) ? -1 : (jk & 0xFF);
         bk[b] = (jk == 0xFFFF) ? -1 : (jk >> 8);
     }
@@ -159,114 +209,85 @@ __global__ void __launch_bounds__(kSchurWarps * 32, 1) k_schur_mma(BaProblem pb,
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[b][q] = 0.0;
 
-    if (threadIdx.x == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
+    const uint32_t smem_base = smem_u32(smem_raw);
+    const uint32_t zero_ent = (2u * stage) >> 4;            // 16-byte units from smem_base
+    uint32_t *hl = hitlist[warp];
 
-    const int ntl = (tp.ntiles > chunk) ? (tp.ntiles - chunk + sp.nchunk - 1) / sp.nchunk : 0;   // tiles of this chunk
-
-    auto issue = [&](int it) {       // warp 0: start the bulk copies of local tile `it` into buffer it & 1
-        const int t = chunk + it * sp.nchunk;
-        const int p0 = tp.tile_pt[t], p1 = tp.tile_pt[t + 1];
-        const int o0 = pb.obs_ptr[p0], o1 = pb.obs_ptr[p1];
-        const uint32_t bytes = (uint32_t)(o1 - o0) * 384u;
-        uint64_t *bar = &mbar[it & 1];
-        char *dst = reinterpret_cast<char *>((it & 1) ? zbuf1 : zbuf0);
-        const char *src = reinterpret_cast<const char *>(Z + 48 * (int64_t)o0);
-        if (lane == 0) mbar_expect_tx(bar, bytes);
-        __syncwarp();
-        for (uint32_t off = (uint32_t)lane * 4096u; off < bytes; off += 32u * 4096u) {
-            const uint32_t sz = (bytes - off < 4096u) ? (bytes - off) : 4096u;
-            bulk_g2s(dst + off, src + off, sz, bar);
-        }
-    };
-
-    // per-lane metadata of the point this lane represents in a tile
-    auto load_meta = [&](int it, uint64_t &mk, int &ob, uint32_t &sg) {
-        mk = 0; ob = 0; sg = 0;
+    // per-lane metadata of the point this lane represents in a tile: local observation base and the sign bits of D
+    auto load_meta = [&](int it, int &ob, uint32_t &sg, bool &have) {
+        ob = 0; sg = 0; have = false;
         if (it < ntl) {
             const int t = chunk + it * sp.nchunk;
             const int p0 = tp.tile_pt[t], p1 = tp.tile_pt[t + 1];
             const int p = p0 + lane;
-            if (p < p1) {
-                if (p >= pb.ncon) mk = pb.pt_mask[p];
-                ob = pb.obs_ptr[p] - pb.obs_ptr[p0];
-                sg = zsign[p];
-            }
+            if (p < p1) { ob = pb.obs_ptr[p] - pb.obs_ptr[p0]; sg = zsign[p]; have = true; }
         }
     };
-
-    if (ntl > 0 && warp == 0) issue(0);
-    uint64_t mk_n; int ob_n; uint32_t sg_n;
-    load_meta(0, mk_n, ob_n, sg_n);
+    int ob_n; uint32_t sg_n; bool hv_n;
+    load_meta(0, ob_n, sg_n, hv_n);
 
     for (int it = 0; it < ntl; ++it) {
-        const uint64_t mk = mk_n; const int ob = ob_n; const uint32_t sg = sg_n;
-        if (it + 1 < ntl && warp == 0) issue(it + 1);       // buffer (it+1)&1 was released by the barrier ending iteration it-1
-        load_meta(it + 1, mk_n, ob_n, sg_n);
-        mbar_wait(&mbar[it & 1], (uint32_t)((it >> 1) & 1));
-        const double *zt = (it & 1) ? zbuf1 : zbuf0;
+        const int ob = ob_n; const uint32_t sg = sg_n; const bool have = hv_n;
+        if (it + 1 < ntl) produce(it + 1);
+        load_meta(it + 1, ob_n, sg_n, hv_n);
+        const int sb = it & 1;
+        mbar_wait(&mfull[sb], (uint32_t)((it >> 1) & 1));
+        const uint32_t zoff = (uint32_t)sb * stage;                           // byte offset of this stage from smem_base
+        const unsigned char *rk = smem_raw + zoff + zbytes + (size_t)lane * mp;
+        const bool anyneg = __any_sync(0xffffffffu, sg != 0);
 
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             const int j = bj[b], k = bk[b];
             if (j < 0) continue;
-            const bool hit = ((mk >> j) & (mk >> k) & 1ull) != 0;
+            const uint32_t rj = have ? rk[j] : 0xFFu, rkk = have ? rk[k] : 0xFFu;
+            const bool hit = (rj | rkk) < 0x80u;
             const uint32_t bal = __ballot_sync(0xffffffffu, hit);
             const int nh = __popc(bal);
             if (nh == 0) continue;
             if (hit) {
                 const int pos = __popc(bal & ((1u << lane) - 1u));
-                const int oj = ob + __popcll(mk & ((1ull << j) - 1ull));
-                const int ok = ob + __popcll(mk & ((1ull << k) - 1ull));
-                hitlist[warp][pos] = (uint32_t)oj | ((uint32_t)ok << 12) | ((uint32_t)lane << 24);
+                // 16-byte units from smem_base: (stage offset + observation * 384) / 16
+                const uint32_t ej = (zoff >> 4) + (uint32_t)(ob + (int)rj) * 24u, ek = (zoff >> 4) + (uint32_t)(ob + (int)rkk) * 24u;
+                hl[pos] = ej | (ek << 14) | (sg << 28);
             }
             __syncwarp();
-            const int nslots = 3 * nh;
+            // One hit per DMMA step: k-lanes 0..2 carry the three components of the hit, k-lane 3 carries zeros.  All lanes of a
+            // step read the same observation(s), 16 bytes each at consecutive addresses: no shared-memory bank conflicts.
+            const uint32_t lane_off = (uint32_t)g8 * 48u + (uint32_t)kk * 16u;
             if (j == k) {
-                for (int s0 = 0; s0 < nslots; s0 += 4) {
-                    const int slot = s0 + kk;
-                    const bool valid = slot < nslots;
-                    const int h = valid ? slot / 3 : 0;
-                    const int comp = slot - 3 * (slot / 3);
-                    const uint32_t ent = hitlist[warp][h];
-                    const int oj = ent & 0xFFF, pt = ent >> 24;
-                    const uint32_t sgn = __shfl_sync(0xffffffffu, sg, pt);
-                    double2 a = *reinterpret_cast<const double2 *>(zt + (size_t)oj * 48 + (g8 * 3 + comp) * 2);
-                    if (!valid) { a.x = 0.0; a.y = 0.0; }
-                    double2 as = a;
-                    if ((sgn >> comp) & 1u) { as.x = -as.x; as.y = -as.y; }
-                    dmma884(acc[b][0], acc[b][1], as.x, a.x);     // (lo, lo)
-                    dmma884(acc[b][2], acc[b][3], as.x, a.y);     // (lo, hi)
-                    dmma884(acc[b][6], acc[b][7], as.y, a.y);     // (hi, hi)
+#pragma unroll 2
+                for (int h = 0; h < nh; ++h) {
+                    const uint32_t ent = hl[h];
+                    double2 a = make_double2(0.0, 0.0);
+                    if (kk < 3) a = lds_f64x2(smem_base + ((ent & 0x3FFFu) << 4) + lane_off);
+                    double2 sa = a;
+                    if (anyneg) { const uint32_t bit = ((ent >> 28) >> kk) & 1u; sa.x = flip_sign(sa.x, bit); sa.y = flip_sign(sa.y, bit); }
+                    dmma884(acc[b][0], acc[b][1], sa.x, a.x); dmma884(acc[b][2], acc[b][3], sa.x, a.y); dmma884(acc[b][6], acc[b][7], sa.y, a.y);
                 }
             } else {
-                for (int s0 = 0; s0 < nslots; s0 += 4) {
-                    const int slot = s0 + kk;
-                    const bool valid = slot < nslots;
-                    const int h = valid ? slot / 3 : 0;
-                    const int comp = slot - 3 * (slot / 3);
-                    const uint32_t ent = hitlist[warp][h];
-                    const int oj = ent & 0xFFF, ok = (ent >> 12) & 0xFFF, pt = ent >> 24;
-                    const uint32_t sgn = __shfl_sync(0xffffffffu, sg, pt);
-                    double2 a = *reinterpret_cast<const double2 *>(zt + (size_t)oj * 48 + (g8 * 3 + comp) * 2);
-                    double2 bb = *reinterpret_cast<const double2 *>(zt + (size_t)ok * 48 + (g8 * 3 + comp) * 2);
-                    if (!valid) { a.x = 0.0; a.y = 0.0; }
-                    if ((sgn >> comp) & 1u) { a.x = -a.x; a.y = -a.y; }
-                    dmma884(acc[b][0], acc[b][1], a.x, bb.x);
-                    dmma884(acc[b][2], acc[b][3], a.x, bb.y);
-                    dmma884(acc[b][4], acc[b][5], a.y, bb.x);
-                    dmma884(acc[b][6], acc[b][7], a.y, bb.y);
+#pragma unroll 2
+                for (int h = 0; h < nh; ++h) {
+                    const uint32_t ent = hl[h];
+                    double2 a = make_double2(0.0, 0.0), bb = make_double2(0.0, 0.0);
+                    if (kk < 3) {
+                        a = lds_f64x2(smem_base + ((ent & 0x3FFFu) << 4) + lane_off);
+                        bb = lds_f64x2(smem_base + (((ent >> 14) & 0x3FFFu) << 4) + lane_off);
+                    }
+                    if (anyneg) { const uint32_t bit = ((ent >> 28) >> kk) & 1u; a.x = flip_sign(a.x, bit); a.y = flip_sign(a.y, bit); }
+                    dmma884(acc[b][0], acc[b][1], a.x, bb.x); dmma884(acc[b][2], acc[b][3], a.x, bb.y);
+                    dmma884(acc[b][4], acc[b][5], a.y, bb.x); dmma884(acc[b][6], acc[b][7], a.y, bb.y);
                 }
             }
             __syncwarp();
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&mempty[sb]);       // this warp is done with the stage
     }
 
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        const int pair = sp.blk_pair[((size_t)grp * kSchurWarps + warp) * NB + b];
+        const int pair = sp.blk_pair[((size_t)grp * NW + warp) * NB + b];
         if (pair < 0) continue;
         double *o = Spart + ((size_t)chunk * sp.npairs + pair) * 256 + lane * 8;
 #pragma unroll

@@ -60,10 +60,11 @@ struct argus_ba_ctx {
     DevBuf<int> flags;     // [0] singular V*, [1] chol status
     // generation-2 (tile / MMA) plan
     int gen = 3;
+    int schur_nw_pref = 8;
     DevBuf<int32_t> tile_pt; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
-    DevBuf<uint8_t> obs_lpt, corder; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect;
+    DevBuf<uint8_t> obs_lpt, corder, pt_rank; int rank_mp = 16; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect;
     int grid_lin = 1; size_t lin_smem = 0;
-    int ntiles = 0, tile_obs = 256, schur_G = 1, schur_NB = 1, schur_nchunk = 1;
+    int ntiles = 0, tile_obs = 256, schur_G = 1, schur_NB = 1, schur_NW = 8, schur_nchunk = 1;
     double *h_pinned = nullptr;   // 16 doubles
     int grid_pts128 = 1, grid_pts256 = 1, nchunks = 1, npairs = 1;
     int64_t chunk_pts = 1;
@@ -219,13 +220,17 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
         {
             ProfScope ps(c, P_SCHUR);
             dim3 grid(c->schur_nchunk, c->schur_G);
-            const size_t sm = (size_t)2 * c->tile_obs * 48 * sizeof(double);
-            switch (c->schur_NB) {
-                case 1: k_schur_mma<1><<<grid, kSchurWarps * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, c->zsign.p, c->Spart.p); break;
-                case 3: k_schur_mma<3><<<grid, kSchurWarps * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, c->zsign.p, c->Spart.p); break;
-                case 5: k_schur_mma<5><<<grid, kSchurWarps * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, c->zsign.p, c->Spart.p); break;
-                default: k_schur_mma<9><<<grid, kSchurWarps * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, c->zsign.p, c->Spart.p); break;
+            const size_t sm = (size_t)2 * ((size_t)c->tile_obs * 384 + (size_t)kTilePts * c->rank_mp) + 64;
+#define SCHUR_LAUNCH(NB_, NW_) k_schur_mma<NB_, NW_><<<grid, NW_ * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, \
+                                                                                       c->zsign.p, c->pt_rank.p, c->rank_mp, c->Spart.p)
+            switch (c->schur_NB * 100 + c->schur_NW) {
+                case 108: SCHUR_LAUNCH(1, 8); break;
+                case 308: SCHUR_LAUNCH(3, 8); break;
+                case 508: SCHUR_LAUNCH(5, 8); break;
+                case 612: SCHUR_LAUNCH(6, 12); break;
+                default: SCHUR_LAUNCH(9, 8); break;
             }
+#undef SCHUR_LAUNCH
         }
     } else {
         {
@@ -324,10 +329,15 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
     if (const char *e = getenv("ARGUS_BA_GEN")) c->gen = atoi(e);
-    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 384));
-    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 384));
-    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 384));
-    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 256 * 384));
+    {
+        const int smx = 2 * (256 * 384 + 32 * 64) + 64;
+        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<9, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<6, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+    }
+    if (const char *e = getenv("ARGUS_SCHUR_NW")) c->schur_nw_pref = atoi(e);
     *out = c;
     return ARGUS_OK;
 }
@@ -342,7 +352,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
                               &c->vstate, &c->Vinv, &c->cvec, &c->dbuf, &c->Upart, &c->scpart, &c->red1, &c->max2, &c->Epart, &c->Spart,
                               &c->red2, &c->S, &c->E, &c->da_free, &c->da_full, &c->part3, &c->red3, &c->cam2, &c->scal, &c->att, &c->respart};
     for (auto *b : bufs) b->release();
-    c->obs_lpt.release(); c->corder.release(); c->cstart.release(); c->Upart2.release(); c->Edirect.release();
+    c->obs_lpt.release(); c->corder.release(); c->pt_rank.release(); c->cstart.release(); c->Upart2.release(); c->Edirect.release();
     c->flags.release(); c->tile_pt.release(); c->blk_jk.release(); c->blk_pair.release(); c->zsign.release(); c->Z.release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -414,10 +424,11 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     }
     {
         const int cand[4] = {1, 3, 5, 9};
-        int NB = 9;
+        int NB = 9, NW = 8;
         for (int q = 0; q < 4; ++q) if (kSchurWarps * cand[q] >= c->npairs) { NB = cand[q]; break; }
-        c->schur_NB = NB;
-        c->schur_G = (c->npairs + kSchurWarps * NB - 1) / (kSchurWarps * NB);
+        if (NB == 9 && c->schur_nw_pref == 12) { NB = 6; NW = 12; }
+        c->schur_NB = NB; c->schur_NW = NW;
+        c->schur_G = (c->npairs + NW * NB - 1) / (NW * NB);
         int nch = c->sms / c->schur_G; if (nch < 1) nch = 1;
         if (nch > c->ntiles) nch = c->ntiles > 0 ? c->ntiles : 1;
         c->schur_nchunk = nch;
@@ -438,20 +449,26 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
             for (int32_t k = o0; k < o1; ++k) hcord[o0 + cnt[ocam[k]]++] = (uint8_t)(k - o0);
         }
     }
+    c->rank_mp = (m + 15) & ~15;
+    std::vector<uint8_t> hrank((size_t)n * c->rank_mp, 0xFF);
+    for (int64_t i = ncon; i < n; ++i) {
+        uint8_t *rr = hrank.data() + (size_t)i * c->rank_mp;
+        for (int32_t k = optr[i]; k < optr[i + 1]; ++k) rr[ocam[k]] = (uint8_t)(k - optr[i]);
+    }
     c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)m * kUfrag * sizeof(double) + (size_t)c->tile_obs * (kGa + 8) * sizeof(double) +
                   (size_t)kTilePts * kPs * sizeof(double);
     {
         int occ = (int)((220 * 1024) / (c->lin_smem + 1024)); if (occ < 1) occ = 1; if (occ > 4) occ = 4;
         c->grid_lin = std::min(c->ntiles > 0 ? c->ntiles : 1, c->sms * occ);
     }
-    std::vector<uint16_t> hjk((size_t)c->schur_G * kSchurWarps * c->schur_NB, 0xFFFF);
-    std::vector<int32_t> hpair((size_t)c->schur_G * kSchurWarps * c->schur_NB, -1);
+    std::vector<uint16_t> hjk((size_t)c->schur_G * c->schur_NW * c->schur_NB, 0xFFFF);
+    std::vector<int32_t> hpair((size_t)c->schur_G * c->schur_NW * c->schur_NB, -1);
     {
         int pidx = 0;
         for (int a = 0; a < mf; ++a)
             for (int b = a; b < mf; ++b, ++pidx) {
-                const int grp = pidx % c->schur_G, q = pidx / c->schur_G, w = q % kSchurWarps, slot = q / kSchurWarps;
-                const size_t at = ((size_t)grp * kSchurWarps + w) * c->schur_NB + slot;
+                const int grp = pidx % c->schur_G, q = pidx / c->schur_G, w = q % c->schur_NW, slot = q / c->schur_NW;
+                const size_t at = ((size_t)grp * c->schur_NW + w) * c->schur_NB + slot;
                 hjk[at] = (uint16_t)((mcon + a) | ((mcon + b) << 8));
                 hpair[at] = pidx;
             }
@@ -461,6 +478,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(c->zsign.ensure((size_t)n)); if (c->gen >= 2) { ENS(c->Z, 48 * nobs); }
     ARGUS_CUDA_CHECK(c->obs_lpt.ensure((size_t)nobs)); ARGUS_CUDA_CHECK(c->corder.ensure((size_t)nobs)); ARGUS_CUDA_CHECK(c->cstart.ensure(hcst.size()));
     ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag);
+    ARGUS_CUDA_CHECK(c->pt_rank.ensure(hrank.size()));
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_lin_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lin_smem));
     ENS(c->obs_ptr, n + 1); ENS(c->obs_cam, nobs); ENS(c->obs_uv, nobs); ENS(c->pt_mask, n);
     ENS(c->rot0, 4 * m); ENS(c->cam, 16 * m); ENS(c->cam_new, 16 * m); ENS(c->cam0, 16 * m);
@@ -475,6 +493,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(c->flags.ensure(2));
 #undef ENS
     cudaStream_t s = c->stream;
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pt_rank.p, hrank.data(), hrank.size(), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_lpt.p, hlpt.data(), hlpt.size(), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->corder.p, hcord.data(), hcord.size(), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cstart.p, hcst.data(), hcst.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
