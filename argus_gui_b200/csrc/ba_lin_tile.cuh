@@ -38,22 +38,27 @@ struct LinTileOut {
     int *flag;
 };
 
-__global__ void __launch_bounds__(256) k_lin_tile(BaProblem pb, TilePlan tp, LinTilePlan lp, const double *__restrict__ cam,
+template <int MC>
+__global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem pb, TilePlan tp, LinTilePlan lp, const double *__restrict__ cam,
                                                   const double *__restrict__ pts, int mode, double mu, int use_state, int write_state,
                                                   LinTileOut out)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);
-    double *Us = reinterpret_cast<double *>(smem_raw + (((size_t)pb.m * sizeof(CamConst) + 15) & ~(size_t)15));   // m x 320 (16-byte aligned)
-    double *Ga = Us + (size_t)pb.m * kUfrag;                        // TO x 36
+    double *Ga = reinterpret_cast<double *>(smem_raw + (((size_t)pb.m * sizeof(CamConst) + 15) & ~(size_t)15));   // TO x 36 (16-byte aligned)
     double *Bs = Ga + (size_t)tp.tile_obs * kGa;                    // TO x 8
     double *Ps = Bs + (size_t)tp.tile_obs * 8;                      // 32 x 16
     __shared__ double red[32];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g8 = lane >> 2, kk = lane & 3;
-    for (int t = tid; t < pb.m * kUfrag; t += blockDim.x) Us[t] = 0.0;
     load_cameras(sc, cam, pb.rot0, pb.m);
+    // Gram accumulators of the cameras this warp owns (mcon + warp + 8 q), kept in registers across all tiles of the CTA
+    double uacc[MC][10];
+#pragma unroll
+    for (int q = 0; q < MC; ++q)
+#pragma unroll
+        for (int t = 0; t < 10; ++t) uacc[q][t] = 0.0;
 
     double cost = 0.0, ebmax = 0.0, vdmax = -1.79769313486231570e308, ptsq = 0.0;
 
@@ -187,34 +192,44 @@ __global__ void __launch_bounds__(256) k_lin_tile(BaProblem pb, TilePlan tp, Lin
         {
             const uint16_t *cs = lp.cstart + (size_t)tile * (pb.m + 1);
             const uint8_t *co = lp.corder + o0;
-            for (int j = pb.mcon + warp; j < pb.m; j += 8) {
-                const int c0 = cs[j], nj = cs[j + 1] - c0;
-                if (nj == 0) continue;
-                double a00[2] = {0, 0}, a01[2] = {0, 0}, a11[2] = {0, 0}, a02[2] = {0, 0}, a12[2] = {0, 0};
-                for (int s = 0; s < nj; s += 2) {
-                    const int idx = s + (kk >> 1);
-                    const bool valid = idx < nj;
-                    const int o = co[c0 + (valid ? idx : 0)];
-                    const int comp = kk & 1;
-                    const double *g = Ga + (size_t)o * kGa;
-                    double2 a = *reinterpret_cast<const double2 *>(g + comp * 16 + g8 * 2);
-                    double ax = (g8 < 2) ? g[32 + comp * 2 + g8] : 0.0;
-                    if (!valid) { a.x = 0.0; a.y = 0.0; ax = 0.0; }
-                    dmma884(a00[0], a00[1], a.x, a.x);
-                    dmma884(a01[0], a01[1], a.x, a.y);
-                    dmma884(a11[0], a11[1], a.y, a.y);
-                    dmma884(a02[0], a02[1], a.x, ax);
-                    dmma884(a12[0], a12[1], a.y, ax);
+#pragma unroll
+            for (int q = 0; q < MC; ++q) {
+                const int j = pb.mcon + warp + 8 * q;
+                if (j < pb.m) {
+                    const int c0 = cs[j], nj = cs[j + 1] - c0;
+                    for (int s = 0; s < nj; s += 2) {
+                        const int idx = s + (kk >> 1);
+                        const bool valid = idx < nj;
+                        const int o = co[c0 + (valid ? idx : 0)];
+                        const int comp = kk & 1;
+                        const double *g = Ga + (size_t)o * kGa;
+                        double2 a = *reinterpret_cast<const double2 *>(g + comp * 16 + g8 * 2);
+                        double ax = (g8 < 2) ? g[32 + comp * 2 + g8] : 0.0;
+                        if (!valid) { a.x = 0.0; a.y = 0.0; ax = 0.0; }
+                        dmma884(uacc[q][0], uacc[q][1], a.x, a.x);
+                        dmma884(uacc[q][2], uacc[q][3], a.x, a.y);
+                        dmma884(uacc[q][4], uacc[q][5], a.y, a.y);
+                        dmma884(uacc[q][6], uacc[q][7], a.x, ax);
+                        dmma884(uacc[q][8], uacc[q][9], a.y, ax);
+                    }
                 }
-                double *u = Us + (size_t)j * kUfrag + lane * 10;
-                u[0] += a00[0]; u[1] += a00[1]; u[2] += a01[0]; u[3] += a01[1]; u[4] += a11[0]; u[5] += a11[1];
-                u[6] += a02[0]; u[7] += a02[1]; u[8] += a12[0]; u[9] += a12[1];
             }
         }
         __syncthreads();
     }
 
-    for (int t = tid; t < pb.m * kUfrag; t += blockDim.x) out.Upart[(size_t)blockIdx.x * pb.m * kUfrag + t] = Us[t];
+    {   // per-CTA Gram fragments; cameras nobody owns (fixed ones) are written as zeros
+        double *up = out.Upart + (size_t)blockIdx.x * pb.m * kUfrag;
+        for (int t = tid; t < pb.mcon * kUfrag; t += blockDim.x) up[t] = 0.0;
+#pragma unroll
+        for (int q = 0; q < MC; ++q) {
+            const int j = pb.mcon + warp + 8 * q;
+            if (j < pb.m) {
+#pragma unroll
+                for (int t = 0; t < 10; ++t) up[(size_t)j * kUfrag + lane * 10 + t] = uacc[q][t];
+            }
+        }
+    }
     const double s0 = block_sum(cost, red), s1 = block_max(ebmax, red), s2 = block_max(vdmax, red), s3 = block_sum(ptsq, red);
     if (tid == 0) {
         out.scpart[4 * blockIdx.x + 0] = s0; out.scpart[4 * blockIdx.x + 1] = s1;

@@ -60,7 +60,7 @@ struct argus_ba_ctx {
     DevBuf<int> flags;     // [0] singular V*, [1] chol status
     // generation-2 (tile / MMA) plan
     int gen = 3;
-    int schur_nw_pref = 8;
+    int schur_nw_pref = 12;
     DevBuf<int32_t> tile_pt; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
     DevBuf<uint8_t> obs_lpt, corder, pt_rank; int rank_mp = 16; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect;
     int grid_lin = 1; size_t lin_smem = 0;
@@ -181,8 +181,11 @@ int run_lin_tile(argus_ba_ctx *c, int mode, double mu, int use_state, int write_
     if (mode != 0) ARGUS_CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, sizeof(int), c->stream));
     {
         ProfScope ps(c, P_LINEARIZE);
-        k_lin_tile<<<c->grid_lin, 256, c->lin_smem, c->stream>>>(c->problem(), c->tile_plan(), c->lin_plan(), c->cam.p, c->pts.p, mode, mu,
-                                                                use_state, write_state, c->lin_out());
+#define LIN_LAUNCH(MC_) k_lin_tile<MC_><<<c->grid_lin, 256, c->lin_smem, c->stream>>>(c->problem(), c->tile_plan(), c->lin_plan(), c->cam.p, \
+                                                                                    c->pts.p, mode, mu, use_state, write_state, c->lin_out())
+        const int mc = (m - c->mcon + 7) / 8;
+        if (mc <= 2) LIN_LAUNCH(2); else if (mc <= 4) LIN_LAUNCH(4); else LIN_LAUNCH(8);
+#undef LIN_LAUNCH
     }
     const int64_t slen = (int64_t)c->npairs * 256;
     {
@@ -409,7 +412,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     }
     // ---- generation-2 plans: point tiles (<= 32 points, <= tile_obs observations) and the block -> (group, warp, slot) map ----
     std::vector<int32_t> tiles;
-    c->tile_obs = (m > 36) ? 128 : 256;
+    c->tile_obs = 256;
     {
         int64_t i = 0;
         while (i < n) {
@@ -455,10 +458,10 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         uint8_t *rr = hrank.data() + (size_t)i * c->rank_mp;
         for (int32_t k = optr[i]; k < optr[i + 1]; ++k) rr[ocam[k]] = (uint8_t)(k - optr[i]);
     }
-    c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)m * kUfrag * sizeof(double) + (size_t)c->tile_obs * (kGa + 8) * sizeof(double) +
+    c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)c->tile_obs * (kGa + 8) * sizeof(double) +
                   (size_t)kTilePts * kPs * sizeof(double);
     {
-        int occ = (int)((220 * 1024) / (c->lin_smem + 1024)); if (occ < 1) occ = 1; if (occ > 4) occ = 4;
+        int occ = (int)((220 * 1024) / (c->lin_smem + 1024)); if (occ < 1) occ = 1; if (occ > 2) occ = 2;
         c->grid_lin = std::min(c->ntiles > 0 ? c->ntiles : 1, c->sms * occ);
     }
     std::vector<uint16_t> hjk((size_t)c->schur_G * c->schur_NW * c->schur_NB, 0xFFFF);
@@ -479,7 +482,9 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(c->obs_lpt.ensure((size_t)nobs)); ARGUS_CUDA_CHECK(c->corder.ensure((size_t)nobs)); ARGUS_CUDA_CHECK(c->cstart.ensure(hcst.size()));
     ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag);
     ARGUS_CUDA_CHECK(c->pt_rank.ensure(hrank.size()));
-    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_lin_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lin_smem));
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_lin_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lin_smem));
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_lin_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lin_smem));
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_lin_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lin_smem));
     ENS(c->obs_ptr, n + 1); ENS(c->obs_cam, nobs); ENS(c->obs_uv, nobs); ENS(c->pt_mask, n);
     ENS(c->rot0, 4 * m); ENS(c->cam, 16 * m); ENS(c->cam_new, 16 * m); ENS(c->cam0, 16 * m);
     ENS(c->pts, 3 * n); ENS(c->pts_new, 3 * n); ENS(c->pts0, 3 * n);

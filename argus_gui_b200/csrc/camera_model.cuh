@@ -163,9 +163,14 @@ ARGUS_HD void cam_project_jac(const CamConst &c, const double M0, const double M
         B[b_]     = G00 * c.R[b_] + G01 * c.R[3 + b_] + G02 * c.R[6 + b_];
         B[3 + b_] = G10 * c.R[b_] + G11 * c.R[3 + b_] + G12 * c.R[6 + b_];
     }
-    // fixed parameters
-    for (int k = 5 - nfix_k; k < 5; ++k) { A[k] = 0.0; A[16 + k] = 0.0; }
-    for (int k = 5 - nfix_d; k < 5; ++k) { A[5 + k] = 0.0; A[21 + k] = 0.0; }
+    // fixed parameters (static indices + predicates: a run-time loop bound would push A into local memory)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 5; ++k) {
+        if (k >= 5 - nfix_k) { A[k] = 0.0; A[16 + k] = 0.0; }
+        if (k >= 5 - nfix_d) { A[5 + k] = 0.0; A[21 + k] = 0.0; }
+    }
 }
 
 // Symmetric 3x3 factorisation V = L D L^T (unit lower L, no pivoting) of the damped point block.
