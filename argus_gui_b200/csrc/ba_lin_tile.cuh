@@ -36,7 +36,14 @@ struct LinTileOut {
     double *Upart;               // grid x m x 320
     double *scpart;              // grid x 4: cost, max|eb|, max diag V, sum pts^2
     int *flag;
+    unsigned long long *dbg;     // optional per-phase clock counters (nullptr in production)
 };
+
+// 32-byte global store (sm_100: st.global.v4.f64): one full sector per store instruction
+__device__ __forceinline__ void st_global_v4(double *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 
 template <int MC>
 __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem pb, TilePlan tp, LinTilePlan lp, const double *__restrict__ cam,
@@ -49,6 +56,10 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
     double *Bs = Ga + (size_t)tp.tile_obs * kGa;                    // TO x 8
     double *Ps = Bs + (size_t)tp.tile_obs * 8;                      // 32 x 16
     __shared__ double red[32];
+    __shared__ double s_M[kTilePts * 3];          // the tile's points
+    __shared__ int s_pofs[kTilePts + 1];          // local observation offset of each point
+    __shared__ uint16_t s_cst[ARGUS_BA_MAX_CAMS + 2];   // start of each camera's run in s_cord
+    __shared__ uint8_t s_cord[256];               // local observation indices sorted by camera
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g8 = lane >> 2, kk = lane & 3;
@@ -62,38 +73,77 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
 
     double cost = 0.0, ebmax = 0.0, vdmax = -1.79769313486231570e308, ptsq = 0.0;
 
+    // ---- software pipeline: everything a tile needs from HBM is fetched into registers one tile ahead ----
+    int h_p0 = 0, h_o0 = 0, h_nobs = 0, h_npts = 0;                 // header of the tile being prefetched / about to run
+    double2 n_uv = make_double2(0.0, 0.0); int n_cam = 0, n_lpt = 0, n_cord = 0, n_pofs = 0, n_cst = 0;
+    double n_M0 = 0.0, n_M1 = 0.0, n_M2 = 0.0;
+    auto load_header = [&](int tile) {
+        if (tile < tp.ntiles) {
+            h_p0 = tp.tile_pt[tile]; const int p1 = tp.tile_pt[tile + 1];
+            h_o0 = tp.tile_o[tile]; h_nobs = tp.tile_o[tile + 1] - h_o0; h_npts = p1 - h_p0;
+        } else { h_nobs = 0; h_npts = 0; }
+    };
+    auto prefetch = [&](int tile) {                                 // uses the header loaded by load_header(tile)
+        if (tile >= tp.ntiles) return;
+        if (tid < h_nobs) {
+            const int k = h_o0 + tid;
+            n_uv = pb.obs_uv[k]; n_cam = pb.obs_cam[k]; n_lpt = lp.obs_lpt[k]; n_cord = lp.corder[k];
+        }
+        if (tid <= h_npts) n_pofs = pb.obs_ptr[h_p0 + tid] - h_o0;
+        if (tid < h_npts) { const int64_t i = h_p0 + tid; n_M0 = pts[3 * i]; n_M1 = pts[3 * i + 1]; n_M2 = pts[3 * i + 2]; }
+        if (tid <= pb.m) n_cst = lp.cstart[(size_t)tile * (pb.m + 1) + tid];
+    };
+    load_header(blockIdx.x);
+    prefetch(blockIdx.x);
+
+    long long tk = clock64();
+#define LIN_TICK(ph) do { if (out.dbg && tid == 0) { const long long t1_ = clock64(); atomicAdd(out.dbg + (ph), (unsigned long long)(t1_ - tk)); tk = t1_; } } while (0)
     for (int tile = blockIdx.x; tile < tp.ntiles; tile += gridDim.x) {
-        const int p0 = tp.tile_pt[tile], p1 = tp.tile_pt[tile + 1];
-        const int o0 = pb.obs_ptr[p0], nobs_t = pb.obs_ptr[p1] - o0, npts = p1 - p0;
+        const int p0 = h_p0, o0 = h_o0, nobs_t = h_nobs, npts = h_npts;
+        // hand the prefetched index data to shared memory (the previous tile ended with a barrier)
+        if (tid < nobs_t) s_cord[tid] = (uint8_t)n_cord;
+        if (tid <= npts) s_pofs[tid] = n_pofs;
+        if (tid < npts) { s_M[3 * tid] = n_M0; s_M[3 * tid + 1] = n_M1; s_M[3 * tid + 2] = n_M2; }
+        if (tid <= pb.m) s_cst[tid] = (uint16_t)n_cst;
+        const double2 z = n_uv; const int my_cam = n_cam, my_lp = n_lpt;
+        load_header(tile + gridDim.x);                              // header of the next tile: in flight during P1
+        __syncthreads();
+        LIN_TICK(0);
 
         // ---- P1: one thread per observation ----
-        int my_lp = 0, my_cam = 0;
         if (tid < nobs_t) {
-            const int k = o0 + tid;
-            my_cam = pb.obs_cam[k];
-            my_lp = lp.obs_lpt[k];
             const int64_t i = p0 + my_lp;
-            const double M0 = pts[3 * i], M1 = pts[3 * i + 1], M2 = pts[3 * i + 2];
+            const double M0 = s_M[3 * my_lp], M1 = s_M[3 * my_lp + 1], M2 = s_M[3 * my_lp + 2];
             double u, v, A[32], B[6];
             cam_project_jac(sc[my_cam], M0, M1, M2, pb.nfix_k, pb.nfix_d, u, v, A, B);
-            const double2 z = pb.obs_uv[k];
             const double e0 = z.x - u, e1 = z.y - v;
             cost += e0 * e0 + e1 * e1;
             double *g = Ga + (size_t)tid * kGa;
-            const bool cfree = my_cam >= pb.mcon;
+            if (my_cam >= pb.mcon) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                *reinterpret_cast<double2 *>(g + r * 2) = cfree ? make_double2(A[r], A[r + 8]) : make_double2(0.0, 0.0);
-                *reinterpret_cast<double2 *>(g + 16 + r * 2) = cfree ? make_double2(A[16 + r], A[24 + r]) : make_double2(0.0, 0.0);
+                for (int r = 0; r < 8; ++r) {
+                    *reinterpret_cast<double2 *>(g + r * 2) = make_double2(A[r], A[r + 8]);
+                    *reinterpret_cast<double2 *>(g + 16 + r * 2) = make_double2(A[16 + r], A[24 + r]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; ++r) *reinterpret_cast<double2 *>(g + r * 2) = make_double2(0.0, 0.0);
             }
-            g[32] = e0; g[33] = 0.0; g[34] = e1; g[35] = 0.0;        // [comp][{e, e'}]
+            *reinterpret_cast<double2 *>(g + 32) = make_double2(e0, 0.0);      // [comp][{e, e'}]
+            *reinterpret_cast<double2 *>(g + 34) = make_double2(e1, 0.0);
             double *b = Bs + (size_t)tid * 8;
-            const bool pfree = i >= pb.ncon;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) b[q] = pfree ? B[q] : 0.0;
-            b[6] = e0; b[7] = e1;
+            if (i >= pb.ncon) {
+                *reinterpret_cast<double2 *>(b) = make_double2(B[0], B[1]); *reinterpret_cast<double2 *>(b + 2) = make_double2(B[2], B[3]);
+                *reinterpret_cast<double2 *>(b + 4) = make_double2(B[4], B[5]);
+            } else {
+                *reinterpret_cast<double2 *>(b) = make_double2(0.0, 0.0); *reinterpret_cast<double2 *>(b + 2) = make_double2(0.0, 0.0);
+                *reinterpret_cast<double2 *>(b + 4) = make_double2(0.0, 0.0);
+            }
+            *reinterpret_cast<double2 *>(b + 6) = make_double2(e0, e1);
         }
+        prefetch(tile + gridDim.x);                                 // next tile's data: in flight during P2..P4
         __syncthreads();
+        LIN_TICK(1);
 
         // ---- P2: 8 threads per point ----
         {
@@ -102,10 +152,12 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             const bool have = lpt < npts;
             const int64_t i = p0 + (have ? lpt : 0);
             if (have) {
-                const int ob = pb.obs_ptr[i] - o0, oe = pb.obs_ptr[i + 1] - o0;
+                const int ob = s_pofs[lpt], oe = s_pofs[lpt + 1];
                 for (int o = ob + q; o < oe; o += 8) {
                     const double *b = Bs + (size_t)o * 8;
-                    const double B0 = b[0], B1 = b[1], B2 = b[2], B3 = b[3], B4 = b[4], B5 = b[5], e0 = b[6], e1 = b[7];
+                    const double2 t0 = *reinterpret_cast<const double2 *>(b), t1 = *reinterpret_cast<const double2 *>(b + 2),
+                                  t2 = *reinterpret_cast<const double2 *>(b + 4), t3 = *reinterpret_cast<const double2 *>(b + 6);
+                    const double B0 = t0.x, B1 = t0.y, B2 = t1.x, B3 = t1.y, B4 = t2.x, B5 = t2.y, e0 = t3.x, e1 = t3.y;
                     v00 += B0 * B0 + B3 * B3; v01 += B0 * B1 + B3 * B4; v02 += B0 * B2 + B3 * B5;
                     v11 += B1 * B1 + B4 * B4; v12 += B1 * B2 + B4 * B5; v22 += B2 * B2 + B5 * B5;
                     b0 += B0 * e0 + B3 * e1; b1 += B1 * e0 + B4 * e1; b2 += B2 * e0 + B5 * e1;
@@ -121,7 +173,7 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             }
             if (have && q == 0) {
                 const bool pfree = i >= pb.ncon;
-                const double M0 = pts[3 * i], M1 = pts[3 * i + 1], M2 = pts[3 * i + 2];
+                const double M0 = s_M[3 * lpt], M1 = s_M[3 * lpt + 1], M2 = s_M[3 * lpt + 2];
                 ptsq += M0 * M0 + M1 * M1 + M2 * M2;
                 double *Vi = out.V + 6 * i;
                 Vi[0] = v00; Vi[1] = v01; Vi[2] = v02; Vi[3] = v11; Vi[4] = v12; Vi[5] = v22;
@@ -162,61 +214,73 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             }
         }
         __syncthreads();
+        LIN_TICK(2);
 
         // ---- P3: per observation: e' and Z ----
         if (mode != 0 && tid < nobs_t) {
             const double *P = Ps + my_lp * kPs;
             const double *b = Bs + (size_t)tid * 8;
-            const double B0 = b[0], B1 = b[1], B2 = b[2], B3 = b[3], B4 = b[4], B5 = b[5];
+            const double2 t0 = *reinterpret_cast<const double2 *>(b), t1 = *reinterpret_cast<const double2 *>(b + 2),
+                          t2 = *reinterpret_cast<const double2 *>(b + 4), t3 = *reinterpret_cast<const double2 *>(b + 6);
+            const double B0 = t0.x, B1 = t0.y, B2 = t1.x, B3 = t1.y, B4 = t2.x, B5 = t2.y;
             double *g = Ga + (size_t)tid * kGa;
             const double c0 = P[6], c1 = P[7], c2 = P[8];
-            g[33] = b[6] - (B0 * c0 + B1 * c1 + B2 * c2);
-            g[35] = b[7] - (B3 * c0 + B4 * c1 + B5 * c2);
+            g[33] = t3.x - (B0 * c0 + B1 * c1 + B2 * c2);
+            g[35] = t3.y - (B3 * c0 + B4 * c1 + B5 * c2);
             const double l0 = P[0], l1 = P[1], l2 = P[2], s0 = P[3], s1 = P[4], s2 = P[5];
             double *Zk = out.Z + 48 * (int64_t)(o0 + tid);
+            // two rows (r, r+1) x three components x (lo, hi) = 12 doubles = three 32-byte stores (full sectors)
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const double2 a0 = *reinterpret_cast<const double2 *>(g + r * 2);          // du/da_r, du/da_{r+8}
-                const double2 a1 = *reinterpret_cast<const double2 *>(g + 16 + r * 2);     // dv/da_r, dv/da_{r+8}
-                const double wl0 = a0.x * B0 + a1.x * B3, wl1 = a0.x * B1 + a1.x * B4, wl2 = a0.x * B2 + a1.x * B5;   // row r
-                const double wh0 = a0.y * B0 + a1.y * B3, wh1 = a0.y * B1 + a1.y * B4, wh2 = a0.y * B2 + a1.y * B5;   // row r + 8
-                // layout ((r%8)*3 + c)*2 + r/8: the (r, r+8) pair of one component is one 16-byte store
-                *reinterpret_cast<double2 *>(Zk + (r * 3 + 0) * 2) = make_double2(wl0 * s0, wh0 * s0);
-                *reinterpret_cast<double2 *>(Zk + (r * 3 + 1) * 2) = make_double2((l0 * wl0 + wl1) * s1, (l0 * wh0 + wh1) * s1);
-                *reinterpret_cast<double2 *>(Zk + (r * 3 + 2) * 2) = make_double2((l1 * wl0 + l2 * wl1 + wl2) * s2, (l1 * wh0 + l2 * wh1 + wh2) * s2);
+            for (int r = 0; r < 8; r += 2) {
+                double zz[12];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const double2 a0 = *reinterpret_cast<const double2 *>(g + (r + rr) * 2);          // du/da_r, du/da_{r+8}
+                    const double2 a1 = *reinterpret_cast<const double2 *>(g + 16 + (r + rr) * 2);     // dv/da_r, dv/da_{r+8}
+                    const double wl0 = a0.x * B0 + a1.x * B3, wl1 = a0.x * B1 + a1.x * B4, wl2 = a0.x * B2 + a1.x * B5;   // row r
+                    const double wh0 = a0.y * B0 + a1.y * B3, wh1 = a0.y * B1 + a1.y * B4, wh2 = a0.y * B2 + a1.y * B5;   // row r + 8
+                    // layout ((r%8)*3 + c)*2 + r/8
+                    zz[rr * 6 + 0] = wl0 * s0; zz[rr * 6 + 1] = wh0 * s0;
+                    zz[rr * 6 + 2] = (l0 * wl0 + wl1) * s1; zz[rr * 6 + 3] = (l0 * wh0 + wh1) * s1;
+                    zz[rr * 6 + 4] = (l1 * wl0 + l2 * wl1 + wl2) * s2; zz[rr * 6 + 5] = (l1 * wh0 + l2 * wh1 + wh2) * s2;
+                }
+                double *zp = Zk + r * 6;
+                st_global_v4(zp, zz[0], zz[1], zz[2], zz[3]);
+                st_global_v4(zp + 4, zz[4], zz[5], zz[6], zz[7]);
+                st_global_v4(zp + 8, zz[8], zz[9], zz[10], zz[11]);
             }
         }
         __syncthreads();
+        LIN_TICK(3);
 
         // ---- P4: Gram per camera on the tensor pipe ----
-        {
-            const uint16_t *cs = lp.cstart + (size_t)tile * (pb.m + 1);
-            const uint8_t *co = lp.corder + o0;
 #pragma unroll
-            for (int q = 0; q < MC; ++q) {
-                const int j = pb.mcon + warp + 8 * q;
-                if (j < pb.m) {
-                    const int c0 = cs[j], nj = cs[j + 1] - c0;
-                    for (int s = 0; s < nj; s += 2) {
-                        const int idx = s + (kk >> 1);
-                        const bool valid = idx < nj;
-                        const int o = co[c0 + (valid ? idx : 0)];
-                        const int comp = kk & 1;
-                        const double *g = Ga + (size_t)o * kGa;
-                        double2 a = *reinterpret_cast<const double2 *>(g + comp * 16 + g8 * 2);
-                        double ax = (g8 < 2) ? g[32 + comp * 2 + g8] : 0.0;
-                        if (!valid) { a.x = 0.0; a.y = 0.0; ax = 0.0; }
-                        dmma884(uacc[q][0], uacc[q][1], a.x, a.x);
-                        dmma884(uacc[q][2], uacc[q][3], a.x, a.y);
-                        dmma884(uacc[q][4], uacc[q][5], a.y, a.y);
-                        dmma884(uacc[q][6], uacc[q][7], a.x, ax);
-                        dmma884(uacc[q][8], uacc[q][9], a.y, ax);
-                    }
+        for (int q = 0; q < MC; ++q) {
+            const int j = pb.mcon + warp + 8 * q;
+            if (j < pb.m) {
+                const int c0 = s_cst[j], nj = s_cst[j + 1] - c0;
+#pragma unroll 2
+                for (int s = 0; s < nj; s += 2) {
+                    const int idx = s + (kk >> 1);
+                    const bool valid = idx < nj;
+                    const int o = s_cord[c0 + (valid ? idx : 0)];
+                    const int comp = kk & 1;
+                    const double *g = Ga + (size_t)o * kGa;
+                    double2 a = *reinterpret_cast<const double2 *>(g + comp * 16 + g8 * 2);
+                    double ax = (g8 < 2) ? g[32 + comp * 2 + g8] : 0.0;
+                    if (!valid) { a.x = 0.0; a.y = 0.0; ax = 0.0; }
+                    dmma884(uacc[q][0], uacc[q][1], a.x, a.x);
+                    dmma884(uacc[q][2], uacc[q][3], a.x, a.y);
+                    dmma884(uacc[q][4], uacc[q][5], a.y, a.y);
+                    dmma884(uacc[q][6], uacc[q][7], a.x, ax);
+                    dmma884(uacc[q][8], uacc[q][9], a.y, ax);
                 }
             }
         }
         __syncthreads();
+        LIN_TICK(4);
     }
+#undef LIN_TICK
 
     {   // per-CTA Gram fragments; cameras nobody owns (fixed ones) are written as zeros
         double *up = out.Upart + (size_t)blockIdx.x * pb.m * kUfrag;

@@ -28,6 +28,7 @@ struct TilePlan {
     int ntiles;
     int tile_obs;                   // TO: max observations per tile
     const int32_t *tile_pt;         // ntiles + 1: first point of each tile
+    const int32_t *tile_o;          // ntiles + 1: first observation of each tile
 };
 
 struct SchurPlan {

@@ -61,9 +61,10 @@ struct argus_ba_ctx {
     // generation-2 (tile / MMA) plan
     int gen = 3;
     int schur_nw_pref = 12;
-    DevBuf<int32_t> tile_pt; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
+    DevBuf<int32_t> tile_pt, tile_o; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
     DevBuf<uint8_t> obs_lpt, corder, pt_rank; int rank_mp = 16; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect;
     int grid_lin = 1; size_t lin_smem = 0;
+    unsigned long long *lin_dbg = nullptr;
     int ntiles = 0, tile_obs = 256, schur_G = 1, schur_NB = 1, schur_NW = 8, schur_nchunk = 1;
     double *h_pinned = nullptr;   // 16 doubles
     int grid_pts128 = 1, grid_pts256 = 1, nchunks = 1, npairs = 1;
@@ -76,7 +77,7 @@ struct argus_ba_ctx {
     double prof_ms[P_COUNT]; int64_t prof_n[P_COUNT];
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0, n_allreduce = 0;
 
-    TilePlan tile_plan() const { TilePlan tp; tp.ntiles = ntiles; tp.tile_obs = tile_obs; tp.tile_pt = tile_pt.p; return tp; }
+    TilePlan tile_plan() const { TilePlan tp; tp.ntiles = ntiles; tp.tile_obs = tile_obs; tp.tile_pt = tile_pt.p; tp.tile_o = tile_o.p; return tp; }
     SchurPlan schur_plan() const {
         SchurPlan sp; sp.G = schur_G; sp.nchunk = schur_nchunk; sp.npairs = npairs; sp.blk_jk = blk_jk.p; sp.blk_pair = blk_pair.p;
         return sp;
@@ -84,7 +85,7 @@ struct argus_ba_ctx {
     LinTilePlan lin_plan() const { LinTilePlan lp; lp.obs_lpt = obs_lpt.p; lp.corder = corder.p; lp.cstart = cstart.p; return lp; }
     LinTileOut lin_out() {
         LinTileOut o; o.Z = Z.p; o.zsign = zsign.p; o.Vinv = Vinv.p; o.V = V.p; o.eb = eb.p; o.vstate = vstate.p; o.Upart = Upart2.p;
-        o.scpart = scpart.p; o.flag = flags.p; return o;
+        o.scpart = scpart.p; o.flag = flags.p; o.dbg = lin_dbg; return o;
     }
     BaProblem problem() const {
         BaProblem pb;
@@ -341,6 +342,7 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
         ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<6, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
     }
     if (const char *e = getenv("ARGUS_SCHUR_NW")) c->schur_nw_pref = atoi(e);
+    if (getenv("ARGUS_LIN_DEBUG")) { ARGUS_CUDA_CHECK(cudaMalloc(&c->lin_dbg, 8 * sizeof(unsigned long long))); ARGUS_CUDA_CHECK(cudaMemset(c->lin_dbg, 0, 8 * sizeof(unsigned long long))); }
     *out = c;
     return ARGUS_OK;
 }
@@ -350,13 +352,18 @@ void argus_ba_destroy(argus_ba_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->lin_dbg) {
+        unsigned long long h[8]; cudaMemcpy(h, c->lin_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "argus_b200 lin-tile phase clocks (sum over CTAs): top/fill %llu  P1 %llu  P2 %llu  P3 %llu  P4 %llu\n", h[0], h[1], h[2], h[3], h[4]);
+        cudaFree(c->lin_dbg);
+    }
     c->obs_ptr.release(); c->obs_cam.release(); c->obs_uv.release(); c->pt_mask.release();
     DevBuf<double> *bufs[] = {&c->rot0, &c->cam, &c->pts, &c->cam_new, &c->pts_new, &c->cam0, &c->pts0, &c->W, &c->Y, &c->V, &c->eb,
                               &c->vstate, &c->Vinv, &c->cvec, &c->dbuf, &c->Upart, &c->scpart, &c->red1, &c->max2, &c->Epart, &c->Spart,
                               &c->red2, &c->S, &c->E, &c->da_free, &c->da_full, &c->part3, &c->red3, &c->cam2, &c->scal, &c->att, &c->respart};
     for (auto *b : bufs) b->release();
     c->obs_lpt.release(); c->corder.release(); c->pt_rank.release(); c->cstart.release(); c->Upart2.release(); c->Edirect.release();
-    c->flags.release(); c->tile_pt.release(); c->blk_jk.release(); c->blk_pair.release(); c->zsign.release(); c->Z.release();
+    c->flags.release(); c->tile_pt.release(); c->tile_o.release(); c->blk_jk.release(); c->blk_pair.release(); c->zsign.release(); c->Z.release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -425,6 +432,8 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         tiles.push_back((int32_t)n);
         c->ntiles = (int)tiles.size() - 1;
     }
+    std::vector<int32_t> tile_o(tiles.size());
+    for (size_t q = 0; q < tiles.size(); ++q) tile_o[q] = optr[tiles[q]];
     {
         const int cand[4] = {1, 3, 5, 9};
         int NB = 9, NW = 8;
@@ -477,7 +486,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
             }
     }
 #define ENS(buf, cnt) ARGUS_CUDA_CHECK((buf).ensure((size_t)(cnt)))
-    ARGUS_CUDA_CHECK(c->tile_pt.ensure(tiles.size())); ARGUS_CUDA_CHECK(c->blk_jk.ensure(hjk.size())); ARGUS_CUDA_CHECK(c->blk_pair.ensure(hpair.size()));
+    ARGUS_CUDA_CHECK(c->tile_pt.ensure(tiles.size())); ARGUS_CUDA_CHECK(c->tile_o.ensure(tiles.size())); ARGUS_CUDA_CHECK(c->blk_jk.ensure(hjk.size())); ARGUS_CUDA_CHECK(c->blk_pair.ensure(hpair.size()));
     ARGUS_CUDA_CHECK(c->zsign.ensure((size_t)n)); if (c->gen >= 2) { ENS(c->Z, 48 * nobs); }
     ARGUS_CUDA_CHECK(c->obs_lpt.ensure((size_t)nobs)); ARGUS_CUDA_CHECK(c->corder.ensure((size_t)nobs)); ARGUS_CUDA_CHECK(c->cstart.ensure(hcst.size()));
     ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag);
@@ -503,6 +512,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->corder.p, hcord.data(), hcord.size(), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cstart.p, hcst.data(), hcst.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_pt.p, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_o.p, tile_o.data(), tile_o.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_jk.p, hjk.data(), hjk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_pair.p, hpair.data(), hpair.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_ptr.p, optr.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
