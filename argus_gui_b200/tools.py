@@ -1,0 +1,135 @@
+"""Drop-in for the DLT functions of /root/reference/argus_gui/tools.py (same names, arguments, return shapes, errors);
+the per-frame Python loops of the reference are replaced by the batched CUDA kernels behind the C ABI.
+
+    uv_to_xyz(pts, profs, dlt)            tools.py:296-337   -> argus_dlt_triangulate
+    get_repo_errors(xyzs, pts, prof, dlt) tools.py:360-423   -> argus_dlt_reproj_error
+    undistort_pts(pts, prof)              tools.py:129-148   -> argus_undistort_points   (pinhole profiles)
+    reconstruct_uv(L, xyz), dlt_inverse(L, xyz), normalize(pts, prof), solve_dlt(xyz, uv)   (host numpy, not hot)
+
+Only pinhole profiles (list / ndarray) are supported; the omnidirectional model objects of the external ``argus.ocam``
+package are out of scope."""
+import numpy as np
+
+from . import dlt as _dlt
+
+__all__ = ["ArgusError", "dlt_inverse", "reconstruct_uv", "undistort_pts", "normalize", "solve_dlt", "uv_to_xyz",
+           "get_repo_errors", "uv_to_xyz_and_errors"]
+
+
+class Error(Exception):
+    pass
+
+
+class ArgusError(Error):
+    """Exception raised for errors in the input (tools.py:17-29)."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def __str__(self):
+        return repr(self.value)
+
+
+def _is_pinhole(prof):
+    return isinstance(prof, (list, tuple, np.ndarray))
+
+
+def dlt_inverse(L, xyz):
+    if not hasattr(L, "__iter__"):
+        raise ArgusError("DLT coefficients must be iterable")
+    L = np.asarray(L, dtype=np.float64)
+    if L.ndim != 1 or L.shape[0] != 11:
+        raise ArgusError("There must be exaclty 11 DLT coefficients in a 1d iterable")
+    if type(xyz) != np.ndarray or xyz.ndim != 2 or xyz.shape[1] != 3:
+        raise ArgusError("XYZ must be an Nx3 numpy array")
+    den = xyz @ L[8:11] + 1.0
+    return np.stack([(xyz @ L[0:3] + L[3]) / den, (xyz @ L[4:7] + L[7]) / den], axis=1)
+
+
+def reconstruct_uv(L, xyz):
+    if not hasattr(L, "__iter__"):
+        raise ArgusError("DLT coefficients must be iterable")
+    if type(xyz) != np.ndarray:
+        raise ArgusError("XYZ must be a numpy array")
+    L = np.asarray(L, dtype=np.float64)
+    den = np.dot(L[-3:], xyz) + 1.0
+    return np.array([(np.dot(L[:3], xyz) + L[3]) / den, (np.dot(L[4:7], xyz) + L[7]) / den])
+
+
+def undistort_pts(pts, prof):
+    """Nx2 pixel coordinates -> Nx2 undistorted pixel coordinates (float32, as cv2.undistortPoints returns them)."""
+    if not _is_pinhole(prof):
+        raise ArgusError("only pinhole distortion profiles are supported by the B200 backend")
+    pts = np.asarray(pts, dtype=np.float64)
+    if pts.ndim == 1:          # the reference broadcasts a (2,) pair into two identical rows (tools.py:138-139)
+        pts = np.tile(pts.reshape(1, 2), (pts.shape[0], 1))
+    return _dlt.undistort(pts, np.asarray(prof, dtype=np.float64))
+
+
+def normalize(pts, prof):
+    if type(pts) != np.ndarray:
+        raise ArgusError("pts must be a numpy array")
+    if pts.ndim != 2 or pts.shape[1] != 2:
+        raise ArgusError("pts must be an Nx2 array")
+    pts[:, 0] = (pts[:, 0] - prof[1]) / prof[0]       # in place, as the reference
+    pts[:, 1] = (pts[:, 1] - prof[2]) / prof[0]
+    return pts
+
+
+def solve_dlt(xyz, uv):
+    """11-parameter DLT fit (tools.py:220-280): returns (L (11 x 1), mean reprojection distance)."""
+    if type(xyz) != np.ndarray or type(uv) != np.ndarray:
+        raise ArgusError("uv and xyz must be numpy arrays")
+    if xyz.ndim != 2 or uv.ndim != 2:
+        raise ArgusError("xyz and uv must be 2-d arrays")
+    if xyz.shape[0] != uv.shape[0]:
+        raise ArgusError("xyz and uv must have the same number of rows")
+    if xyz.shape[1] != 3:
+        raise ArgusError("xyz must be an Nx3 array")
+    if uv.shape[1] != 2:
+        raise ArgusError("uv must be an Nx2 array")
+    keep = ~np.isnan(uv).any(axis=1)
+    xyz, uv = xyz[keep], uv[keep]
+    n = xyz.shape[0]
+    A = np.zeros((2 * n, 11)); B = np.zeros((2 * n, 1))
+    A[0::2, 0:3] = xyz; A[0::2, 3] = 1.0; A[0::2, 8:11] = -xyz * uv[:, 0:1]
+    A[1::2, 4:7] = xyz; A[1::2, 7] = 1.0; A[1::2, 8:11] = -xyz * uv[:, 1:2]
+    B[0::2, 0] = uv[:, 0]; B[1::2, 0] = uv[:, 1]
+    L = np.linalg.lstsq(A, B, rcond=None)[0]
+    rec = dlt_inverse(L[:, 0], xyz)
+    rmse = float(np.sqrt(((rec - uv) ** 2).sum(axis=1)).sum() / float(n)) if n else float("nan")
+    return L, rmse
+
+
+def _check_cams(pts, profs, dlt):
+    if (int(pts.shape[1] / 2) != len(profs)) or (int(pts.shape[1] / 2) != len(dlt)):
+        raise ArgusError("the length of the profile list and DLT coefficients should match the number of cameras present")
+    for p in profs:
+        if not _is_pinhole(p):
+            raise ArgusError("only pinhole distortion profiles are supported by the B200 backend")
+
+
+def uv_to_xyz(pts, profs, dlt):
+    """pts: N x (2 * cameras) pixel coordinates of ONE track (NaN = not seen) -> N x 3."""
+    pts = np.asarray(pts, dtype=np.float64)
+    _check_cams(pts, profs, dlt)
+    return _dlt.triangulate(pts, profs, np.asarray(dlt, dtype=np.float64))
+
+
+def get_repo_errors(xyzs, pts, prof, dlt):
+    """xyzs: N x 3k, pts: N x (2 * cameras * k) -> k x N reprojection errors."""
+    if (not hasattr(prof, "__iter__")) or (not hasattr(dlt, "__iter__")):
+        raise ArgusError("camera profile and dlt coefficients must be iterables")
+    if type(xyzs) != np.ndarray or xyzs.ndim != 2 or (xyzs.shape[1] % 3) != 0:
+        raise ArgusError("xyz values must be an N*(3*k) array, where k is the number of tracks")
+    for p in prof:
+        if not _is_pinhole(p):
+            raise ArgusError("only pinhole distortion profiles are supported by the B200 backend")
+    return _dlt.reproj_error(xyzs, np.asarray(pts, dtype=np.float64), prof, np.asarray(dlt, dtype=np.float64))
+
+
+def uv_to_xyz_and_errors(pts, profs, dlt):
+    """All tracks at once (extension): pts N x (2 * cameras * k) -> (xyz N x 3k, errors k x N); equals calling uv_to_xyz on
+    every track slice and get_repo_errors on the result, with one host<->device round trip."""
+    pts = np.asarray(pts, dtype=np.float64)
+    return _dlt.reconstruct(pts, profs, np.asarray(dlt, dtype=np.float64))
