@@ -149,6 +149,34 @@ def solve_motstr(vmask, p, rot0, x, nccalib=0, ncdist=0, itmax=DEFAULT_ITMAX, op
     return p, info, ret
 
 
+def host_allreduce_hook(group=None):
+    """Same contract as ``torch_allreduce_hook`` for HOST buffers (gloo): used by the CPU tests of the multi-rank
+    plumbing; the pointer is wrapped without a copy."""
+    import torch
+    import torch.distributed as dist
+
+    def hook(ptr, count, op, stream):
+        buf = (ctypes.c_double * int(count)).from_address(int(ptr))
+        t = torch.from_numpy(np.frombuffer(buf, dtype=np.float64))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX, group=group)
+        return 0
+    return hook
+
+
+def shard_problem(vmask, p, x, m, world, rank, balance_observations=False):
+    """This rank's block of points with all their observations and ALL cameras:
+    -> (vmask_local, p_local = [16 m | 3 n_local], x_local, (lo, hi))."""
+    vmask = np.asarray(vmask)
+    n = vmask.shape[0]
+    per_pt = (vmask != 0).sum(axis=1).astype(np.int64)
+    lo, hi = shard_points(n, world, rank, per_pt if balance_observations else None)
+    rowptr = np.concatenate([[0], np.cumsum(per_pt)])
+    p = np.asarray(p, dtype=np.float64).ravel()
+    x = np.asarray(x, dtype=np.float64).reshape(-1, 2)
+    p_loc = np.concatenate([p[:16 * m], p[16 * m + 3 * lo:16 * m + 3 * hi]])
+    return vmask[lo:hi], p_loc, x[rowptr[lo]:rowptr[hi]], (lo, hi)
+
+
 def torch_allreduce_hook(group=None):
     """All-reduce hook backed by ``torch.distributed`` (NCCL on GPUs).  The C solver hands a device pointer; it is
     wrapped without a copy and reduced on the solver's stream."""

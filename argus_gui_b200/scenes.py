@@ -199,3 +199,27 @@ def make_dlt_scene(nframes, m=4, ntracks=10, seed=2, nan_frac=0.1, noise=0.5, ra
             pts[:, t * 2 * m + 2 * j: t * 2 * m + 2 * j + 2] = uv
     return {"pts": pts, "prof": prof, "dlt": dlt, "xyz_true": xyz_true.reshape(nframes, 3 * ntracks),
             "cams": cams, "m": m, "ntracks": ntracks}
+
+
+def make_wand_scene(nframes=2000, nbackground=100, m=3, seed=1, wand=0.5, noise=0.5, dropout=0.05, radius=5.0):
+    """Config C1: m cameras on a 120-degree arc looking at the origin, ``nframes`` frames of a ``wand`` m
+    wand (random centre in a 2 m cube, random orientation) -> paired points (nframes x 4m: [end-1 uv per camera | end-2 uv
+    per camera]), ``nbackground`` points in a 3 m cube -> unpaired (nbackground x 2m), pinhole + r2 = -0.05 cameras
+    (m x 10: f, cx, cy, AR, s, r2, r4, t1, t2, r6), pixel noise, random drop-outs."""
+    rng = np.random.default_rng(seed)
+    cams = make_ring_cameras(m, radius=radius, height_amp=0.3, dist=(-0.05, 0.0, 0.0, 0.0, 0.0), arc=2 * np.pi / 3)
+    centre = rng.uniform(-1.0, 1.0, size=(nframes, 3))
+    d = rng.normal(size=(nframes, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    e1, e2 = centre - 0.5 * wand * d, centre + 0.5 * wand * d
+    bg = rng.uniform(-1.5, 1.5, size=(nbackground, 3))
+
+    def proj(X):
+        out = np.empty((X.shape[0], 2 * m))
+        for j in range(m):
+            uv = project_points(cams, X, np.full(X.shape[0], j)) + rng.normal(0, noise, size=(X.shape[0], 2))
+            uv[rng.random(X.shape[0]) < dropout] = np.nan
+            out[:, 2 * j:2 * j + 2] = uv
+        return out
+    ppts = np.hstack([proj(e1), proj(e2)])
+    uppts = proj(bg)
+    return {"ppts": ppts, "uppts": uppts, "cams": cams[:, :10].copy(), "cams_true": cams, "wand": wand, "e1": e1, "e2": e2, "bg": bg}
