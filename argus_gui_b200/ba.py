@@ -19,6 +19,14 @@ def _ptr(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _as_mask(vmask):
+    """n x m visibility mask as C-contiguous int8 without copying uint8 / bool inputs."""
+    vmask = np.asarray(vmask)
+    if vmask.dtype in (np.uint8, np.bool_) and vmask.flags.c_contiguous:
+        return vmask.view(np.int8)
+    return np.ascontiguousarray(vmask, dtype=np.int8)
+
+
 def shard_points(n, world, rank, nobs_per_point=None):
     """Contiguous block of points [lo, hi) owned by ``rank``.  With ``nobs_per_point`` the cut points balance
     observations instead of points."""
@@ -69,7 +77,7 @@ class BundleAdjuster:
         _lib.check(self.lib.argus_ba_set_comm(self.h, int(rank), int(world), self._cb, None), "argus_ba_set_comm")
 
     def upload(self, vmask, p, rot0, x, nccalib=0, ncdist=0, ncon=0, mcon=0):
-        vmask = np.ascontiguousarray(vmask, dtype=np.int8)
+        vmask = _as_mask(vmask)
         n, m = vmask.shape
         p = np.ascontiguousarray(p, dtype=np.float64).ravel()
         rot0 = np.ascontiguousarray(rot0, dtype=np.float64).ravel()
@@ -135,7 +143,7 @@ def solve_motstr(vmask, p, rot0, x, nccalib=0, ncdist=0, itmax=DEFAULT_ITMAX, op
                  verbose=0, compat=True):
     """One-shot host-pointer call ``argus_ba_motstr_kdrts``.  Returns (p_new, info[10], retval)."""
     lib = _lib.load()
-    vmask = np.ascontiguousarray(vmask, dtype=np.int8)
+    vmask = _as_mask(vmask)
     n, m = vmask.shape
     p = np.array(p, dtype=np.float64, copy=True).ravel()
     rot0 = np.ascontiguousarray(rot0, dtype=np.float64).ravel()

@@ -11,6 +11,9 @@
 #include <float.h>
 #include <vector>
 #include <algorithm>
+#include <chrono>
+#include <thread>
+#include <functional>
 #include "../../include/argus_b200.h"
 #include "ba_kernels.cuh"
 #include "ba_schur_mma.cuh"
@@ -25,18 +28,47 @@ enum ProfId { P_RESIDUAL = 0, P_LINEARIZE, P_LIN_REDUCE, P_PREPARE, P_SCHUR, P_S
 const char *kProfNames[P_COUNT] = {"residual", "linearize", "lin_reduce", "prepare", "schur", "schur_reduce", "assemble",
                                    "chol_solve", "backsub_eval", "allreduce"};
 
+// One device allocation per uploaded problem: every buffer is carved out of it (two passes: measure, then assign).
+struct Arena {
+    char *base = nullptr; size_t size = 0, used = 0; bool measuring = false;
+    void *take(size_t bytes) {
+        const size_t off = (used + 255) & ~(size_t)255;
+        used = off + bytes;
+        return (measuring || !base) ? nullptr : base + off;
+    }
+};
+thread_local Arena *g_arena = nullptr;     // set only inside argus_ba_upload (per calling thread)
+
 template <typename T> struct DevBuf {
-    T *p = nullptr; size_t cap = 0;
+    T *p = nullptr; size_t cap = 0; bool owned = false;
     cudaError_t ensure(size_t n) {
-        if (n <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (g_arena) {                       // arena mode: pointers are (re)assigned on every upload
+            if (owned && p) cudaFree(p);
+            owned = false;
+            p = static_cast<T *>(g_arena->take((n ? n : 1) * sizeof(T)));
+            cap = n;
+            return cudaSuccess;
+        }
+        if (n <= cap && p) return cudaSuccess;
+        if (owned && p) cudaFree(p);
         p = nullptr; cap = 0;
         cudaError_t e = cudaMalloc(&p, (n ? n : 1) * sizeof(T));
-        if (e == cudaSuccess) cap = n;
+        if (e == cudaSuccess) { cap = n; owned = true; }
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (owned && p) cudaFree(p); p = nullptr; cap = 0; owned = false; }
 };
+
+// host-side helper: split [0, n) over the host cores (the index build at upload is a pure host streaming job)
+void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)> &fn)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    int T = (int)std::min<int64_t>(std::min<unsigned>(hw ? hw : 4, 16), (n + 65535) / 65536);
+    if (T <= 1) { fn(0, n); return; }
+    std::vector<std::thread> th;
+    for (int q = 0; q < T; ++q) th.emplace_back([&, q] { fn(n * q / T, n * (q + 1) / T); });
+    for (auto &x : th) x.join();
+}
 
 }  // namespace
 
@@ -67,6 +99,7 @@ struct argus_ba_ctx {
     unsigned long long *lin_dbg = nullptr;
     int ntiles = 0, tile_obs = 256, schur_G = 1, schur_NB = 1, schur_NW = 8, schur_nchunk = 1;
     double *h_pinned = nullptr;   // 16 doubles
+    Arena arena;
     int grid_pts128 = 1, grid_pts256 = 1, nchunks = 1, npairs = 1;
     int64_t chunk_pts = 1;
     // profile
@@ -365,6 +398,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
     c->obs_lpt.release(); c->corder.release(); c->pt_rank.release(); c->cstart.release(); c->Upart2.release(); c->Edirect.release();
     c->flags.release(); c->tile_pt.release(); c->tile_o.release(); c->blk_jk.release(); c->blk_pair.release(); c->zsign.release(); c->Z.release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->arena.base) cudaFree(c->arena.base);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -386,24 +420,30 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     if (m < 1 || m > ARGUS_BA_MAX_CAMS || n < 0 || ncon < 0 || ncon > n || mcon < 0 || mcon >= m) return ARGUS_E_ARG;
     if (nccalib < 0 || nccalib > 5 || ncdist < 0 || ncdist > 5) return ARGUS_E_ARG;
     ARGUS_CUDA_CHECK(cudaSetDevice(c->device));
+    const bool timing = getenv("ARGUS_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = tnow();
     // visibility index (sba_levmar.c:639-650 builds the same CRS; here: point-major CSR + per-point camera bit mask)
     std::vector<int32_t> optr((size_t)n + 1);
     std::vector<uint64_t> mask((size_t)n);
+    parallel_for(n, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const char *row = vmask + i * m;
+            uint64_t mk = 0;
+            for (int j = 0; j < m; ++j) if (row[j]) mk |= 1ull << j;
+            mask[i] = mk;
+        }
+    });
     int64_t nobs = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        const char *row = vmask + i * m;
-        uint64_t mk = 0;
-        for (int j = 0; j < m; ++j) if (row[j]) mk |= 1ull << j;
-        optr[i] = (int32_t)nobs; mask[i] = mk;
-        nobs += __builtin_popcountll(mk);
-        if (nobs > 0x7fffffffLL) return ARGUS_E_ARG;
-    }
+    for (int64_t i = 0; i < n; ++i) { optr[i] = (int32_t)nobs; nobs += __builtin_popcountll(mask[i]); if (nobs > 0x7fffffffLL) return ARGUS_E_ARG; }
     optr[n] = (int32_t)nobs;
     std::vector<uint8_t> ocam((size_t)nobs);
-    for (int64_t i = 0; i < n; ++i) {
-        uint64_t mk = mask[i]; int32_t k = optr[i];
-        while (mk) { ocam[k++] = (uint8_t)__builtin_ctzll(mk); mk &= mk - 1; }
-    }
+    parallel_for(n, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            uint64_t mk = mask[i]; int32_t k = optr[i];
+            while (mk) { ocam[k++] = (uint8_t)__builtin_ctzll(mk); mk &= mk - 1; }
+        }
+    });
     c->n = n; c->ncon = ncon; c->m = m; c->mcon = mcon; c->nobs = nobs; c->nfix_k = nccalib; c->nfix_d = ncdist;
     const int mf = m - mcon, N = 16 * mf;
     c->npairs = mf * (mf + 1) / 2;
@@ -448,9 +488,9 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     // per-observation local point index, per-tile camera-sorted observation order (static: visibility never changes)
     std::vector<uint8_t> hlpt((size_t)nobs), hcord((size_t)nobs);
     std::vector<uint16_t> hcst((size_t)c->ntiles * (m + 1));
-    {
+    parallel_for(c->ntiles, [&](int64_t tlo, int64_t thi) {
         std::vector<int> cnt(m + 1);
-        for (int tl = 0; tl < c->ntiles; ++tl) {
+        for (int64_t tl = tlo; tl < thi; ++tl) {
             const int32_t p0 = tiles[tl], p1 = tiles[tl + 1], o0 = optr[p0], o1 = optr[p1];
             std::fill(cnt.begin(), cnt.end(), 0);
             for (int32_t p = p0; p < p1; ++p)
@@ -460,13 +500,17 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
             for (int j = 0; j <= m; ++j) cs[j] = (uint16_t)cnt[j];
             for (int32_t k = o0; k < o1; ++k) hcord[o0 + cnt[ocam[k]]++] = (uint8_t)(k - o0);
         }
-    }
+    });
     c->rank_mp = (m + 15) & ~15;
-    std::vector<uint8_t> hrank((size_t)n * c->rank_mp, 0xFF);
-    for (int64_t i = ncon; i < n; ++i) {
-        uint8_t *rr = hrank.data() + (size_t)i * c->rank_mp;
-        for (int32_t k = optr[i]; k < optr[i + 1]; ++k) rr[ocam[k]] = (uint8_t)(k - optr[i]);
-    }
+    std::vector<uint8_t> hrank((size_t)n * c->rank_mp);
+    parallel_for(n, [&](int64_t lo, int64_t hi) {
+        const int mp = c->rank_mp;
+        memset(hrank.data() + (size_t)lo * mp, 0xFF, (size_t)(hi - lo) * mp);
+        for (int64_t i = std::max<int64_t>(lo, ncon); i < hi; ++i) {
+            uint8_t *rr = hrank.data() + (size_t)i * mp;
+            for (int32_t k = optr[i]; k < optr[i + 1]; ++k) rr[ocam[k]] = (uint8_t)(k - optr[i]);
+        }
+    });
     c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)c->tile_obs * (kGa + 8) * sizeof(double) +
                   (size_t)kTilePts * kPs * sizeof(double);
     {
@@ -485,27 +529,51 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
                 hpair[at] = pidx;
             }
     }
-#define ENS(buf, cnt) ARGUS_CUDA_CHECK((buf).ensure((size_t)(cnt)))
-    ARGUS_CUDA_CHECK(c->tile_pt.ensure(tiles.size())); ARGUS_CUDA_CHECK(c->tile_o.ensure(tiles.size())); ARGUS_CUDA_CHECK(c->blk_jk.ensure(hjk.size())); ARGUS_CUDA_CHECK(c->blk_pair.ensure(hpair.size()));
-    ARGUS_CUDA_CHECK(c->zsign.ensure((size_t)n)); if (c->gen >= 2) { ENS(c->Z, 48 * nobs); }
-    ARGUS_CUDA_CHECK(c->obs_lpt.ensure((size_t)nobs)); ARGUS_CUDA_CHECK(c->corder.ensure((size_t)nobs)); ARGUS_CUDA_CHECK(c->cstart.ensure(hcst.size()));
-    ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag);
-    ARGUS_CUDA_CHECK(c->pt_rank.ensure(hrank.size()));
+    const double t_index = tnow();
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_lin_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lin_smem));
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_lin_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lin_smem));
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_lin_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->lin_smem));
-    ENS(c->obs_ptr, n + 1); ENS(c->obs_cam, nobs); ENS(c->obs_uv, nobs); ENS(c->pt_mask, n);
-    ENS(c->rot0, 4 * m); ENS(c->cam, 16 * m); ENS(c->cam_new, 16 * m); ENS(c->cam0, 16 * m);
-    ENS(c->pts, 3 * n); ENS(c->pts_new, 3 * n); ENS(c->pts0, 3 * n);
-    if (c->gen < 3) { ENS(c->W, 48 * nobs); }
-    if (c->gen < 2) { ENS(c->Y, 48 * nobs); } ENS(c->V, 6 * n); ENS(c->eb, 3 * n); ENS(c->vstate, 3 * n); ENS(c->Vinv, 6 * n);
-    ENS(c->cvec, 3 * n); ENS(c->dbuf, 3 * n);
-    ENS(c->Upart, (int64_t)c->grid_pts128 * m * kU); ENS(c->scpart, 4 * std::max(c->grid_pts128, c->grid_lin)); ENS(c->red1, m * kU + 2); ENS(c->max2, 2);
-    ENS(c->Epart, (int64_t)c->grid_pts128 * m * 16); ENS(c->Spart, (int64_t)std::max(c->nchunks, c->schur_nchunk) * c->npairs * 256);
-    ENS(c->red2, (int64_t)c->npairs * 256 + m * 16); ENS(c->S, (int64_t)N * N); ENS(c->E, N); ENS(c->da_free, N); ENS(c->da_full, 16 * m);
-    ENS(c->part3, 3 * c->grid_pts128); ENS(c->red3, 3); ENS(c->cam2, 2); ENS(c->scal, 8); ENS(c->att, 8); ENS(c->respart, c->grid_pts256);
-    ARGUS_CUDA_CHECK(c->flags.ensure(2));
-#undef ENS
+    // every device buffer of the problem comes out of ONE allocation: measure, allocate, assign
+    auto plan = [&]() -> cudaError_t {
+#define PLAN_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
+#define PLAN_ENS(buf, cnt) PLAN_CHECK((buf).ensure((size_t)(cnt)))
+    PLAN_CHECK(c->tile_pt.ensure(tiles.size())); PLAN_CHECK(c->tile_o.ensure(tiles.size())); PLAN_CHECK(c->blk_jk.ensure(hjk.size())); PLAN_CHECK(c->blk_pair.ensure(hpair.size()));
+    PLAN_CHECK(c->zsign.ensure((size_t)n)); if (c->gen >= 2) { PLAN_ENS(c->Z, 48 * nobs); }
+    PLAN_CHECK(c->obs_lpt.ensure((size_t)nobs)); PLAN_CHECK(c->corder.ensure((size_t)nobs)); PLAN_CHECK(c->cstart.ensure(hcst.size()));
+    PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag);
+    PLAN_CHECK(c->pt_rank.ensure(hrank.size()));
+    PLAN_ENS(c->obs_ptr, n + 1); PLAN_ENS(c->obs_cam, nobs); PLAN_ENS(c->obs_uv, nobs); PLAN_ENS(c->pt_mask, n);
+    PLAN_ENS(c->rot0, 4 * m); PLAN_ENS(c->cam, 16 * m); PLAN_ENS(c->cam_new, 16 * m); PLAN_ENS(c->cam0, 16 * m);
+    PLAN_ENS(c->pts, 3 * n); PLAN_ENS(c->pts_new, 3 * n); PLAN_ENS(c->pts0, 3 * n);
+    if (c->gen < 3) { PLAN_ENS(c->W, 48 * nobs); }
+    if (c->gen < 2) { PLAN_ENS(c->Y, 48 * nobs); } PLAN_ENS(c->V, 6 * n); PLAN_ENS(c->eb, 3 * n); PLAN_ENS(c->vstate, 3 * n); PLAN_ENS(c->Vinv, 6 * n);
+    PLAN_ENS(c->cvec, 3 * n); PLAN_ENS(c->dbuf, 3 * n);
+    PLAN_ENS(c->Upart, (int64_t)c->grid_pts128 * m * kU); PLAN_ENS(c->scpart, 4 * std::max(c->grid_pts128, c->grid_lin)); PLAN_ENS(c->red1, m * kU + 2); PLAN_ENS(c->max2, 2);
+    PLAN_ENS(c->Epart, (int64_t)c->grid_pts128 * m * 16); PLAN_ENS(c->Spart, (int64_t)std::max(c->nchunks, c->schur_nchunk) * c->npairs * 256);
+    PLAN_ENS(c->red2, (int64_t)c->npairs * 256 + m * 16); PLAN_ENS(c->S, (int64_t)N * N); PLAN_ENS(c->E, N); PLAN_ENS(c->da_free, N); PLAN_ENS(c->da_full, 16 * m);
+    PLAN_ENS(c->part3, 3 * c->grid_pts128); PLAN_ENS(c->red3, 3); PLAN_ENS(c->cam2, 2); PLAN_ENS(c->scal, 8); PLAN_ENS(c->att, 8); PLAN_ENS(c->respart, c->grid_pts256);
+    PLAN_CHECK(c->flags.ensure(2));
+#undef PLAN_ENS
+#undef PLAN_CHECK
+        return cudaSuccess;
+    };
+    {
+        Arena &ar = c->arena;
+        ar.measuring = true; ar.used = 0;
+        g_arena = &ar;
+        cudaError_t pe = plan();
+        const size_t need = ar.used + 256;
+        if (pe == cudaSuccess && need > ar.size) {
+            if (ar.base) cudaFree(ar.base);
+            ar.base = nullptr; ar.size = 0;
+            pe = cudaMalloc(&ar.base, need);
+            if (pe == cudaSuccess) ar.size = need;
+        }
+        if (pe == cudaSuccess) { ar.measuring = false; ar.used = 0; pe = plan(); }
+        g_arena = nullptr;
+        ARGUS_CUDA_CHECK(pe);
+    }
+    const double t_alloc = tnow();
     cudaStream_t s = c->stream;
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pt_rank.p, hrank.data(), hrank.size(), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_lpt.p, hlpt.data(), hlpt.size(), cudaMemcpyHostToDevice, s));
@@ -524,6 +592,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pts0.p, p + 16 * m, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));      // host staging vectors go out of scope
     c->h2d_bytes += (n + 1) * sizeof(int32_t) + nobs * (sizeof(uint8_t) + sizeof(double2)) + n * sizeof(uint64_t) + (4 + 16) * m * sizeof(double) + 3 * n * sizeof(double);
+    if (timing) fprintf(stderr, "argus_b200 upload: host index build %.1f ms, device alloc %.1f ms, H2D %.1f ms\n", 1e3 * (t_index - t_start), 1e3 * (t_alloc - t_index), 1e3 * (tnow() - t_alloc));
     return argus_ba_reset(c);
 }
 
