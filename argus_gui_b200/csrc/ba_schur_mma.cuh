@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(128) k_make_z(BaProblem pb, double mu, int use
 }
 
 // The Schur kernel.  grid = (nchunk, G); NW warps, each owning NB blocks; lane 0 of warp 0 doubles as the copy producer.
-// Dynamic shared memory: 2 x [Z tile: TO x 48 doubles | rank tile: 32 x mp bytes], then a 64-byte block of zeros.
+// Dynamic shared memory: 2 x [Z tile: TO x 48 doubles | rank tile: 32 x mp bytes], then one Z row (384 B) of zeros.
 // Spart[chunk][pair][256]: per-chunk partial sums in fragment order (lane * 8 + q), q = (ri*2 + ci)*2 + e for the
 // 8x8 sub-tile (ri, ci) of the block: element (row = ri*8 + lane>>2, col = ci*8 + 2*(lane&3) + e).
 //
@@ -164,14 +164,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(BaProblem pb, TilePlan
     const uint32_t stage = zbytes + (uint32_t)kTilePts * (uint32_t)mp;          // multiple of 16
     unsigned char *zero_blk = smem_raw + 2 * stage;
     __shared__ __align__(8) uint64_t mfull[2], mempty[2];
-    __shared__ uint32_t hitlist[NW][kTilePts];
+    __shared__ uint2 hitlist[NW][kTilePts + 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g8 = lane >> 2, kk = lane & 3;
     const int chunk = blockIdx.x, grp = blockIdx.y;
     const int ntl = (tp.ntiles > chunk) ? (tp.ntiles - chunk + sp.nchunk - 1) / sp.nchunk : 0;   // tiles of this chunk
 
-    if (threadIdx.x < 16) reinterpret_cast<uint32_t *>(zero_blk)[threadIdx.x] = 0u;
+    if (threadIdx.x < 96) reinterpret_cast<uint32_t *>(zero_blk)[threadIdx.x] = 0u;        // a whole Z row of zeros (384 B)
     if (threadIdx.x == 0) { mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1); mbar_init(&mempty[0], NW); mbar_init(&mempty[1], NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -211,8 +211,14 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(BaProblem pb, TilePlan
         for (int q = 0; q < 8; ++q) acc[b][q] = 0.0;
 
     const uint32_t smem_base = smem_u32(smem_raw);
-    const uint32_t zero_ent = (2u * stage) >> 4;            // 16-byte units from smem_base
-    uint32_t *hl = hitlist[warp];
+    uint2 *hl = hitlist[warp];
+    const uint32_t zero_addr = smem_base + 2u * stage;
+    const uint32_t lane_off = (uint32_t)g8 * 48u + (uint32_t)kk * 16u;
+    // (hit-in-group, component) of this k-lane in the three steps of a full 4-hit group
+    const int gh0 = (kk == 3) ? 1 : 0, gh1 = (kk == 0 || kk == 1) ? 1 : 2, gh2 = (kk == 0) ? 2 : 3;
+    const int gc0 = (kk == 3) ? 0 : kk, gc1 = (kk == 0) ? 1 : (kk == 1) ? 2 : (kk == 2) ? 0 : 1, gc2 = (kk == 0) ? 2 : kk - 1;
+    const uint32_t goff0 = (uint32_t)g8 * 48u + (uint32_t)gc0 * 16u, goff1 = (uint32_t)g8 * 48u + (uint32_t)gc1 * 16u,
+                   goff2 = (uint32_t)g8 * 48u + (uint32_t)gc2 * 16u;
 
     // per-lane metadata of the point this lane represents in a tile: local observation base and the sign bits of D
     auto load_meta = [&](int it, int &ob, uint32_t &sg, bool &have) {
@@ -234,6 +240,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(BaProblem pb, TilePlan
         const int sb = it & 1;
         mbar_wait(&mfull[sb], (uint32_t)((it >> 1) & 1));
         const uint32_t zoff = (uint32_t)sb * stage;                           // byte offset of this stage from smem_base
+        const uint32_t zbase = smem_base + zoff;
         const unsigned char *rk = smem_raw + zoff + zbytes + (size_t)lane * mp;
         const bool anyneg = __any_sync(0xffffffffu, sg != 0);
 
@@ -248,34 +255,60 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(BaProblem pb, TilePlan
             if (nh == 0) continue;
             if (hit) {
                 const int pos = __popc(bal & ((1u << lane) - 1u));
-                // 16-byte units from smem_base: (stage offset + observation * 384) / 16
-                const uint32_t ej = (zoff >> 4) + (uint32_t)(ob + (int)rj) * 24u, ek = (zoff >> 4) + (uint32_t)(ob + (int)rkk) * 24u;
-                hl[pos] = ej | (ek << 14) | (sg << 28);
+                // shared-memory byte addresses of the two Z rows of this hit; bits 28..30 of .x carry the sign bits of D
+                const uint32_t aj = zbase + (uint32_t)(ob + (int)rj) * 384u, ak = zbase + (uint32_t)(ob + (int)rkk) * 384u;
+                hl[pos] = make_uint2(aj | (sg << 28), ak);
             }
             __syncwarp();
-            // One hit per DMMA step: k-lanes 0..2 carry the three components of the hit, k-lane 3 carries zeros.  All lanes of a
-            // step read the same observation(s), 16 bytes each at consecutive addresses: no shared-memory bank conflicts.
-            const uint32_t lane_off = (uint32_t)g8 * 48u + (uint32_t)kk * 16u;
+            // K packing.  Full groups of 4 hits fill 3 DMMA steps completely (12 K-slots): k-lane kk handles the (hit, component)
+            // pairs  kk0: (0,0)(1,1)(2,2)  kk1: (0,1)(1,2)(3,0)  kk2: (0,2)(2,0)(3,1)  kk3: (1,0)(2,1)(3,2)  of the group in steps
+            // 0,1,2.  The remaining 1..3 hits take one step each (k-lanes 0..2 = the three components, k-lane 3 reads zeros).
+            const int nfull = nh & ~3;
             if (j == k) {
-#pragma unroll 2
-                for (int h = 0; h < nh; ++h) {
-                    const uint32_t ent = hl[h];
-                    double2 a = make_double2(0.0, 0.0);
-                    if (kk < 3) a = lds_f64x2(smem_base + ((ent & 0x3FFFu) << 4) + lane_off);
+                for (int q = 0; q < nfull; q += 4) {
+                    const uint2 e0 = hl[q + gh0], e1 = hl[q + gh1], e2 = hl[q + gh2];
+                    const double2 a0 = lds_f64x2((e0.x & 0x0FFFFFFFu) + goff0), a1 = lds_f64x2((e1.x & 0x0FFFFFFFu) + goff1),
+                                  a2 = lds_f64x2((e2.x & 0x0FFFFFFFu) + goff2);
+                    double2 s0 = a0, s1 = a1, s2 = a2;
+                    if (anyneg) {
+                        const uint32_t b0 = ((e0.x >> 28) >> gc0) & 1u, b1 = ((e1.x >> 28) >> gc1) & 1u, b2 = ((e2.x >> 28) >> gc2) & 1u;
+                        s0.x = flip_sign(s0.x, b0); s0.y = flip_sign(s0.y, b0); s1.x = flip_sign(s1.x, b1); s1.y = flip_sign(s1.y, b1);
+                        s2.x = flip_sign(s2.x, b2); s2.y = flip_sign(s2.y, b2);
+                    }
+                    dmma884(acc[b][0], acc[b][1], s0.x, a0.x); dmma884(acc[b][2], acc[b][3], s0.x, a0.y); dmma884(acc[b][6], acc[b][7], s0.y, a0.y);
+                    dmma884(acc[b][0], acc[b][1], s1.x, a1.x); dmma884(acc[b][2], acc[b][3], s1.x, a1.y); dmma884(acc[b][6], acc[b][7], s1.y, a1.y);
+                    dmma884(acc[b][0], acc[b][1], s2.x, a2.x); dmma884(acc[b][2], acc[b][3], s2.x, a2.y); dmma884(acc[b][6], acc[b][7], s2.y, a2.y);
+                }
+                for (int h = nfull; h < nh; ++h) {
+                    const uint2 ent = hl[h];
+                    const double2 a = lds_f64x2(kk < 3 ? (ent.x & 0x0FFFFFFFu) + lane_off : zero_addr);
                     double2 sa = a;
-                    if (anyneg) { const uint32_t bit = ((ent >> 28) >> kk) & 1u; sa.x = flip_sign(sa.x, bit); sa.y = flip_sign(sa.y, bit); }
+                    if (anyneg) { const uint32_t bit = ((ent.x >> 28) >> kk) & 1u; sa.x = flip_sign(sa.x, bit); sa.y = flip_sign(sa.y, bit); }
                     dmma884(acc[b][0], acc[b][1], sa.x, a.x); dmma884(acc[b][2], acc[b][3], sa.x, a.y); dmma884(acc[b][6], acc[b][7], sa.y, a.y);
                 }
             } else {
-#pragma unroll 2
-                for (int h = 0; h < nh; ++h) {
-                    const uint32_t ent = hl[h];
-                    double2 a = make_double2(0.0, 0.0), bb = make_double2(0.0, 0.0);
-                    if (kk < 3) {
-                        a = lds_f64x2(smem_base + ((ent & 0x3FFFu) << 4) + lane_off);
-                        bb = lds_f64x2(smem_base + (((ent >> 14) & 0x3FFFu) << 4) + lane_off);
+                for (int q = 0; q < nfull; q += 4) {
+                    const uint2 e0 = hl[q + gh0], e1 = hl[q + gh1], e2 = hl[q + gh2];
+                    double2 a0 = lds_f64x2((e0.x & 0x0FFFFFFFu) + goff0), a1 = lds_f64x2((e1.x & 0x0FFFFFFFu) + goff1),
+                            a2 = lds_f64x2((e2.x & 0x0FFFFFFFu) + goff2);
+                    const double2 b0 = lds_f64x2(e0.y + goff0), b1 = lds_f64x2(e1.y + goff1), b2 = lds_f64x2(e2.y + goff2);
+                    if (anyneg) {
+                        const uint32_t t0 = ((e0.x >> 28) >> gc0) & 1u, t1 = ((e1.x >> 28) >> gc1) & 1u, t2 = ((e2.x >> 28) >> gc2) & 1u;
+                        a0.x = flip_sign(a0.x, t0); a0.y = flip_sign(a0.y, t0); a1.x = flip_sign(a1.x, t1); a1.y = flip_sign(a1.y, t1);
+                        a2.x = flip_sign(a2.x, t2); a2.y = flip_sign(a2.y, t2);
                     }
-                    if (anyneg) { const uint32_t bit = ((ent >> 28) >> kk) & 1u; a.x = flip_sign(a.x, bit); a.y = flip_sign(a.y, bit); }
+                    dmma884(acc[b][0], acc[b][1], a0.x, b0.x); dmma884(acc[b][2], acc[b][3], a0.x, b0.y);
+                    dmma884(acc[b][4], acc[b][5], a0.y, b0.x); dmma884(acc[b][6], acc[b][7], a0.y, b0.y);
+                    dmma884(acc[b][0], acc[b][1], a1.x, b1.x); dmma884(acc[b][2], acc[b][3], a1.x, b1.y);
+                    dmma884(acc[b][4], acc[b][5], a1.y, b1.x); dmma884(acc[b][6], acc[b][7], a1.y, b1.y);
+                    dmma884(acc[b][0], acc[b][1], a2.x, b2.x); dmma884(acc[b][2], acc[b][3], a2.x, b2.y);
+                    dmma884(acc[b][4], acc[b][5], a2.y, b2.x); dmma884(acc[b][6], acc[b][7], a2.y, b2.y);
+                }
+                for (int h = nfull; h < nh; ++h) {
+                    const uint2 ent = hl[h];
+                    double2 a = lds_f64x2(kk < 3 ? (ent.x & 0x0FFFFFFFu) + lane_off : zero_addr);
+                    const double2 bb = lds_f64x2(kk < 3 ? ent.y + lane_off : zero_addr);
+                    if (anyneg) { const uint32_t bit = ((ent.x >> 28) >> kk) & 1u; a.x = flip_sign(a.x, bit); a.y = flip_sign(a.y, bit); }
                     dmma884(acc[b][0], acc[b][1], a.x, bb.x); dmma884(acc[b][2], acc[b][3], a.x, bb.y);
                     dmma884(acc[b][4], acc[b][5], a.y, bb.x); dmma884(acc[b][6], acc[b][7], a.y, bb.y);
                 }

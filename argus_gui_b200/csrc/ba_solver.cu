@@ -257,7 +257,7 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
         {
             ProfScope ps(c, P_SCHUR);
             dim3 grid(c->schur_nchunk, c->schur_G);
-            const size_t sm = (size_t)2 * ((size_t)c->tile_obs * 384 + (size_t)kTilePts * c->rank_mp) + 64;
+            const size_t sm = (size_t)2 * ((size_t)c->tile_obs * 384 + (size_t)kTilePts * c->rank_mp) + 384;
 #define SCHUR_LAUNCH(NB_, NW_) k_schur_mma<NB_, NW_><<<grid, NW_ * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, \
                                                                                        c->zsign.p, c->pt_rank.p, c->rank_mp, c->Spart.p)
             switch (c->schur_NB * 100 + c->schur_NW) {
@@ -367,7 +367,7 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
     if (const char *e = getenv("ARGUS_BA_GEN")) c->gen = atoi(e);
     {
-        const int smx = 2 * (256 * 384 + 32 * 64) + 64;
+        const int smx = 2 * (256 * 384 + 32 * 64) + 384;
         ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
         ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
         ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
