@@ -418,6 +418,182 @@ __global__ void __launch_bounds__(kCholThreads) k_chol_solve(double *__restrict_
     if (tid == 0) status[0] = 1;
 }
 
+// K5, second generation: same contract as k_chol_solve (one CTA, S overwritten by its lower Cholesky factor, status[0] = 1 / 0),
+// restructured so that no long dependent chain touches global memory:
+//   * the 32x32 diagonal block is factored in shared memory by the whole CTA;
+//   * its inverse (lower triangular) is formed by all warps (one column per warp pass, shuffle broadcast) and kept in
+//     work[kb/32][32][32]: the panel solve L = A D^-T becomes a small matrix product with full instruction-level
+//     parallelism, and both substitutions become per-block triangular matrix-vector products + parallel updates.
+// work: (ceil(N/32)) x 1024 doubles of scratch.
+__global__ void __launch_bounds__(kCholThreads) k_chol_solve2(double *__restrict__ S, const double *__restrict__ E, double *__restrict__ x, int N,
+                                                              double *__restrict__ work, int *__restrict__ status)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *P = reinterpret_cast<double *>(smem_raw);          // rows below the panel x 33 (also the running rhs later)
+    __shared__ double D[kCholNB][kCholNB + 1];
+    __shared__ double Di[kCholNB][kCholNB + 1];
+    __shared__ double ys[kCholNB];
+    __shared__ int fail;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    if (tid == 0) fail = 0;
+    __syncthreads();
+    for (int kb = 0; kb < N; kb += kCholNB) {
+        const int nb = min(kCholNB, N - kb);
+        for (int t = tid; t < kCholNB * kCholNB; t += blockDim.x) {
+            const int r = t >> 5, c = t & 31;
+            D[r][c] = (r < nb && c <= r) ? S[(int64_t)(kb + r) * N + kb + c] : ((r == c) ? 1.0 : 0.0);   // identity padding
+            Di[r][c] = 0.0;
+        }
+        __syncthreads();
+        // (1) factor the diagonal block with the whole CTA.  The step loop runs the square-root-free recurrence
+        //     (D[r][c] -= D[r][j] D[c][j] / d_j, one barrier and one division on the critical path per step; every thread
+        //     reads the pivot itself, so the positive-definiteness test is uniform); the columns are scaled by
+        //     1/sqrt(d_j) afterwards, which gives exactly the Cholesky factor.
+        bool bad = false;
+        for (int j = 0; j < nb; ++j) {
+            const double d = D[j][j];
+            if (!(d > 0.0)) { bad = true; break; }
+            const double id = 1.0 / d;
+            const int w = nb - 1 - j;
+            for (int t = tid; t < w * w; t += blockDim.x) {
+                const int r = j + 1 + t / w, c = j + 1 + t % w;
+                if (c <= r) D[r][c] -= D[r][j] * D[c][j] * id;
+            }
+            __syncthreads();
+        }
+        if (bad) { if (tid == 0) fail = 1; }
+        __syncthreads();
+        if (fail) break;
+        if (tid < kCholNB) ys[tid] = D[tid][tid];            // pivots d_j
+        __syncthreads();
+        for (int t = tid; t < kCholNB * kCholNB; t += blockDim.x) {
+            const int r = t >> 5, c = t & 31;
+            if (c < r) D[r][c] *= rsqrt(ys[c]); else if (c == r) D[r][c] = sqrt(ys[c]);
+        }
+        __syncthreads();
+        // (2) inverse of the factor: column jj by warp (jj mod nwarp); lane = row
+        for (int jj = warp; jj < kCholNB; jj += nwarp) {
+            double xi = 0.0, acc = 0.0;
+            const double rdii = 1.0 / D[lane][lane];        // one division per lane, none on the 31-step dependent chain
+            if (lane == jj) xi = rdii;
+            for (int k = jj; k < kCholNB - 1; ++k) {
+                const double xk = __shfl_sync(0xffffffffu, xi, k);
+                if (lane > k) acc += D[lane][k] * xk;
+                if (lane == k + 1) xi = -acc * rdii;
+            }
+            Di[lane][jj] = (lane >= jj) ? xi : 0.0;
+        }
+        __syncthreads();
+        for (int t = tid; t < kCholNB * kCholNB; t += blockDim.x) {
+            const int r = t >> 5, c = t & 31;
+            work[(int64_t)(kb / kCholNB) * 1024 + t] = Di[r][c];
+            if (r < nb && c <= r) S[(int64_t)(kb + r) * N + kb + c] = D[r][c];
+        }
+        // (3) panel: L_i = A_i D^-T, i.e. L[i][c] = sum_{q <= c} A[i][q] Di[c][q]
+        const int r0 = kb + nb, R = N - r0;
+        for (int i = tid; i < R; i += blockDim.x) {
+            double *row = S + (int64_t)(r0 + i) * N + kb;
+            double a[kCholNB];
+#pragma unroll
+            for (int q = 0; q < kCholNB; ++q) a[q] = (q < nb) ? row[q] : 0.0;
+            double *pr = P + i * 33;
+#pragma unroll 4
+            for (int c = 0; c < kCholNB; ++c) {
+                double sacc = 0.0;
+#pragma unroll
+                for (int q = 0; q < kCholNB; ++q) sacc += a[q] * Di[c][q];       // Di is lower triangular: zeros for q > c
+                pr[c] = sacc;
+                if (c < nb) row[c] = sacc;
+            }
+        }
+        __syncthreads();
+        // (4) trailing update of the lower triangle: 4x4 register tiles
+        const int T = (R + 3) >> 2;
+        for (int t = tid; t < T * T; t += blockDim.x) {
+            const int ti = t / T, tj = t % T;
+            if (tj > ti) continue;
+            double acc[4][4];
+#pragma unroll
+            for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                for (int b_ = 0; b_ < 4; ++b_) acc[a_][b_] = 0.0;
+            const int i0 = 4 * ti, j0 = 4 * tj;
+            for (int c = 0; c < kCholNB; ++c) {
+                double pi[4], pj[4];
+#pragma unroll
+                for (int a_ = 0; a_ < 4; ++a_) { pi[a_] = (i0 + a_ < R) ? P[(i0 + a_) * 33 + c] : 0.0; pj[a_] = (j0 + a_ < R) ? P[(j0 + a_) * 33 + c] : 0.0; }
+#pragma unroll
+                for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                    for (int b_ = 0; b_ < 4; ++b_) acc[a_][b_] += pi[a_] * pj[b_];
+            }
+#pragma unroll
+            for (int a_ = 0; a_ < 4; ++a_)
+#pragma unroll
+                for (int b_ = 0; b_ < 4; ++b_) {
+                    const int i = i0 + a_, j = j0 + b_;
+                    if (i < R && j <= i) S[(int64_t)(r0 + i) * N + r0 + j] -= acc[a_][b_];
+                }
+        }
+        __syncthreads();
+    }
+    if (fail) { if (tid == 0) status[0] = 0; return; }
+    // forward substitution L y = E: per block y_b = Di_b rhs_b, then rhs_i -= L[i][b] y_b
+    double *rhs = P;
+    for (int i = tid; i < N; i += blockDim.x) rhs[i] = E[i];
+    __syncthreads();
+    for (int kb = 0; kb < N; kb += kCholNB) {
+        const int nb = min(kCholNB, N - kb);
+        for (int t = tid; t < kCholNB * kCholNB; t += blockDim.x) Di[t >> 5][t & 31] = work[(int64_t)(kb / kCholNB) * 1024 + t];
+        __syncthreads();
+        if (tid < kCholNB) {            // Di is zero above the diagonal and identity-padded: the full 32-term dot product is exact
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < kCholNB; q += 2) { s0 += Di[tid][q] * ((q < nb) ? rhs[kb + q] : 0.0); s1 += Di[tid][q + 1] * ((q + 1 < nb) ? rhs[kb + q + 1] : 0.0); }
+            ys[tid] = (tid < nb) ? s0 + s1 : 0.0;
+        }
+        __syncthreads();
+        if (tid < nb) rhs[kb + tid] = ys[tid];
+        for (int i = kb + nb + tid; i < N; i += blockDim.x) {
+            const double *row = S + (int64_t)i * N + kb;
+            double rv[kCholNB];
+#pragma unroll
+            for (int c = 0; c < kCholNB; ++c) rv[c] = (c < nb) ? row[c] : 0.0;        // all loads in flight together
+            double s0 = rhs[i], s1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < kCholNB; c += 2) { s0 -= rv[c] * ys[c]; s1 -= rv[c + 1] * ys[c + 1]; }
+            rhs[i] = s0 + s1;
+        }
+        __syncthreads();
+    }
+    // backward substitution L^T x = y: x_b = Di_b^T rhs_b, then rhs_i -= L[b][i]^T x_b for i above the block
+    for (int kb = ((N - 1) / kCholNB) * kCholNB; kb >= 0; kb -= kCholNB) {
+        const int nb = min(kCholNB, N - kb);
+        for (int t = tid; t < kCholNB * kCholNB; t += blockDim.x) Di[t >> 5][t & 31] = work[(int64_t)(kb / kCholNB) * 1024 + t];
+        __syncthreads();
+        if (tid < kCholNB) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < kCholNB; q += 2) { s0 += Di[q][tid] * ((q < nb) ? rhs[kb + q] : 0.0); s1 += Di[q + 1][tid] * ((q + 1 < nb) ? rhs[kb + q + 1] : 0.0); }
+            ys[tid] = (tid < nb) ? s0 + s1 : 0.0;
+        }
+        __syncthreads();
+        if (tid < nb) rhs[kb + tid] = ys[tid];
+        for (int i = tid; i < kb; i += blockDim.x) {
+            double rv[kCholNB];
+#pragma unroll
+            for (int c = 0; c < kCholNB; ++c) rv[c] = (c < nb) ? S[(int64_t)(kb + c) * N + i] : 0.0;
+            double s0 = rhs[i], s1 = 0.0;
+#pragma unroll
+            for (int c = 0; c < kCholNB; c += 2) { s0 -= rv[c] * ys[c]; s1 -= rv[c + 1] * ys[c + 1]; }
+            rhs[i] = s0 + s1;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < N; i += blockDim.x) x[i] = rhs[i];
+    if (tid == 0) status[0] = 1;
+}
+
 // camera update: cam_new = cam + da (da = 0 for the mcon fixed cameras, sba_levmar.c:1211), and the camera part of
 // ||dp||^2 and dL = sum dp (mu dp + J^T e) (sba_levmar.c:1261-1264, 1297-1298).  out = {da^2, dL_cam}.  One block.
 __global__ void k_cam_update(int m, int mcon, const double *__restrict__ cam, const double *__restrict__ da_free,

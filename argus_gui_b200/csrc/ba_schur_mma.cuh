@@ -220,23 +220,28 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(BaProblem pb, TilePlan
     const uint32_t goff0 = (uint32_t)g8 * 48u + (uint32_t)gc0 * 16u, goff1 = (uint32_t)g8 * 48u + (uint32_t)gc1 * 16u,
                    goff2 = (uint32_t)g8 * 48u + (uint32_t)gc2 * 16u;
 
-    // per-lane metadata of the point this lane represents in a tile: local observation base and the sign bits of D
-    auto load_meta = [&](int it, int &ob, uint32_t &sg, bool &have) {
-        ob = 0; sg = 0; have = false;
-        if (it < ntl) {
-            const int t = chunk + it * sp.nchunk;
-            const int p0 = tp.tile_pt[t], p1 = tp.tile_pt[t + 1];
-            const int p = p0 + lane;
-            if (p < p1) { ob = pb.obs_ptr[p] - pb.obs_ptr[p0]; sg = zsign[p]; have = true; }
-        }
+    // per-lane metadata of the point this lane represents in a tile: local observation base and the sign bits of D.
+    // Two-level prefetch so no load waits on another: tile bounds two tiles ahead, per-point data one tile ahead.
+    auto load_bounds = [&](int it, int &p0, int &p1, int &o0) {
+        p0 = 0; p1 = 0; o0 = 0;
+        if (it < ntl) { const int t = chunk + it * sp.nchunk; p0 = tp.tile_pt[t]; p1 = tp.tile_pt[t + 1]; o0 = tp.tile_o[t]; }
     };
+    auto load_meta = [&](int p0, int p1, int o0, int &ob, uint32_t &sg, bool &have) {
+        ob = 0; sg = 0; have = false;
+        const int p = p0 + lane;
+        if (p < p1) { ob = pb.obs_ptr[p] - o0; sg = zsign[p]; have = true; }
+    };
+    int bp0, bp1, bo0;                       // bounds of tile it + 1 (then it + 2)
     int ob_n; uint32_t sg_n; bool hv_n;
-    load_meta(0, ob_n, sg_n, hv_n);
+    load_bounds(0, bp0, bp1, bo0);
+    load_meta(bp0, bp1, bo0, ob_n, sg_n, hv_n);
+    load_bounds(1, bp0, bp1, bo0);
 
     for (int it = 0; it < ntl; ++it) {
         const int ob = ob_n; const uint32_t sg = sg_n; const bool have = hv_n;
         if (it + 1 < ntl) produce(it + 1);
-        load_meta(it + 1, ob_n, sg_n, hv_n);
+        load_meta(bp0, bp1, bo0, ob_n, sg_n, hv_n);          // tile it + 1 (bounds arrived during the previous tile)
+        load_bounds(it + 2, bp0, bp1, bo0);
         const int sb = it & 1;
         mbar_wait(&mfull[sb], (uint32_t)((it >> 1) & 1));
         const uint32_t zoff = (uint32_t)sb * stage;                           // byte offset of this stage from smem_base

@@ -94,7 +94,7 @@ struct argus_ba_ctx {
     int gen = 3;
     int schur_nw_pref = 12;
     DevBuf<int32_t> tile_pt, tile_o; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
-    DevBuf<uint8_t> obs_lpt, corder, pt_rank; int rank_mp = 16; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect;
+    DevBuf<uint8_t> obs_lpt, corder, pt_rank; int rank_mp = 16; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect, cholwork;
     int grid_lin = 1; size_t lin_smem = 0;
     unsigned long long *lin_dbg = nullptr;
     int ntiles = 0, tile_obs = 256, schur_G = 1, schur_NB = 1, schur_NW = 8, schur_nchunk = 1;
@@ -304,7 +304,8 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
         size_t rows = (size_t)(N > 32 ? N - 32 : 1);
         size_t sm = rows * 33 * sizeof(double);
         if (sm < (size_t)N * sizeof(double)) sm = (size_t)N * sizeof(double);
-        k_chol_solve<<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->flags.p + 1);
+        if (c->gen >= 3 && N <= 832) k_chol_solve2<<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->cholwork.p, c->flags.p + 1);
+        else k_chol_solve<<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->flags.p + 1);
     }
     {
         ProfScope ps(c, P_BACKSUB);
@@ -365,6 +366,7 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
     // opt in to large dynamic shared memory where needed
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, 214000));
     if (const char *e = getenv("ARGUS_BA_GEN")) c->gen = atoi(e);
     {
         const int smx = 2 * (256 * 384 + 32 * 64) + 384;
@@ -395,7 +397,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
                               &c->vstate, &c->Vinv, &c->cvec, &c->dbuf, &c->Upart, &c->scpart, &c->red1, &c->max2, &c->Epart, &c->Spart,
                               &c->red2, &c->S, &c->E, &c->da_free, &c->da_full, &c->part3, &c->red3, &c->cam2, &c->scal, &c->att, &c->respart};
     for (auto *b : bufs) b->release();
-    c->obs_lpt.release(); c->corder.release(); c->pt_rank.release(); c->cstart.release(); c->Upart2.release(); c->Edirect.release();
+    c->obs_lpt.release(); c->corder.release(); c->pt_rank.release(); c->cstart.release(); c->Upart2.release(); c->Edirect.release(); c->cholwork.release();
     c->flags.release(); c->tile_pt.release(); c->tile_o.release(); c->blk_jk.release(); c->blk_pair.release(); c->zsign.release(); c->Z.release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->arena.base) cudaFree(c->arena.base);
@@ -540,7 +542,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     PLAN_CHECK(c->tile_pt.ensure(tiles.size())); PLAN_CHECK(c->tile_o.ensure(tiles.size())); PLAN_CHECK(c->blk_jk.ensure(hjk.size())); PLAN_CHECK(c->blk_pair.ensure(hpair.size()));
     PLAN_CHECK(c->zsign.ensure((size_t)n)); if (c->gen >= 2) { PLAN_ENS(c->Z, 48 * nobs); }
     PLAN_CHECK(c->obs_lpt.ensure((size_t)nobs)); PLAN_CHECK(c->corder.ensure((size_t)nobs)); PLAN_CHECK(c->cstart.ensure(hcst.size()));
-    PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag);
+    PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1024);
     PLAN_CHECK(c->pt_rank.ensure(hrank.size()));
     PLAN_ENS(c->obs_ptr, n + 1); PLAN_ENS(c->obs_cam, nobs); PLAN_ENS(c->obs_uv, nobs); PLAN_ENS(c->pt_mask, n);
     PLAN_ENS(c->rot0, 4 * m); PLAN_ENS(c->cam, 16 * m); PLAN_ENS(c->cam_new, 16 * m); PLAN_ENS(c->cam0, 16 * m);
