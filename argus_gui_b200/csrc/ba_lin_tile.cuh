@@ -16,7 +16,9 @@
 
 namespace argus {
 
-constexpr int kGa = 36;          // doubles per observation in the Gram operand tile: 32 (A rows, (g, g+8) pairs) + 4 (e, e')
+constexpr int kGa = 38;          // doubles per observation in the Gram operand tile: 32 (A rows, (g, g+8) pairs) + 4 (e, e') + 2 pad:
+                                 // 19 16-byte units per row (odd) -> consecutive threads hit distinct shared-memory banks
+constexpr int kBs = 10;          // doubles per observation in the B/e tile: 6 + 2 + 2 pad (5 16-byte units, odd)
 constexpr int kUfrag = 320;      // per camera: 5 DMMA tiles x 64 fragment elements (lane * 10 + q)
 constexpr int kPs = 16;          // per point scratch: li[3], sq[3], c[3], sign, free
 
@@ -53,8 +55,8 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);
     double *Ga = reinterpret_cast<double *>(smem_raw + (((size_t)pb.m * sizeof(CamConst) + 15) & ~(size_t)15));   // TO x 36 (16-byte aligned)
-    double *Bs = Ga + (size_t)tp.tile_obs * kGa;                    // TO x 8
-    double *Ps = Bs + (size_t)tp.tile_obs * 8;                      // 32 x 16
+    double *Bs = Ga + (size_t)tp.tile_obs * kGa;                    // TO x kBs
+    double *Ps = Bs + (size_t)tp.tile_obs * kBs;                    // 32 x 16
     __shared__ double red[32];
     __shared__ double s_M[kTilePts * 3];          // the tile's points
     __shared__ int s_pofs[kTilePts + 1];          // local observation offset of each point
@@ -73,40 +75,21 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
 
     double cost = 0.0, ebmax = 0.0, vdmax = -1.79769313486231570e308, ptsq = 0.0;
 
-    // ---- software pipeline: everything a tile needs from HBM is fetched into registers one tile ahead ----
-    int h_p0 = 0, h_o0 = 0, h_nobs = 0, h_npts = 0;                 // header of the tile being prefetched / about to run
-    double2 n_uv = make_double2(0.0, 0.0); int n_cam = 0, n_lpt = 0, n_cord = 0, n_pofs = 0, n_cst = 0;
-    double n_M0 = 0.0, n_M1 = 0.0, n_M2 = 0.0;
-    auto load_header = [&](int tile) {
-        if (tile < tp.ntiles) {
-            h_p0 = tp.tile_pt[tile]; const int p1 = tp.tile_pt[tile + 1];
-            h_o0 = tp.tile_o[tile]; h_nobs = tp.tile_o[tile + 1] - h_o0; h_npts = p1 - h_p0;
-        } else { h_nobs = 0; h_npts = 0; }
-    };
-    auto prefetch = [&](int tile) {                                 // uses the header loaded by load_header(tile)
-        if (tile >= tp.ntiles) return;
-        if (tid < h_nobs) {
-            const int k = h_o0 + tid;
-            n_uv = pb.obs_uv[k]; n_cam = pb.obs_cam[k]; n_lpt = lp.obs_lpt[k]; n_cord = lp.corder[k];
-        }
-        if (tid <= h_npts) n_pofs = pb.obs_ptr[h_p0 + tid] - h_o0;
-        if (tid < h_npts) { const int64_t i = h_p0 + tid; n_M0 = pts[3 * i]; n_M1 = pts[3 * i + 1]; n_M2 = pts[3 * i + 2]; }
-        if (tid <= pb.m) n_cst = lp.cstart[(size_t)tile * (pb.m + 1) + tid];
-    };
-    load_header(blockIdx.x);
-    prefetch(blockIdx.x);
-
     long long tk = clock64();
 #define LIN_TICK(ph) do { if (out.dbg && tid == 0) { const long long t1_ = clock64(); atomicAdd(out.dbg + (ph), (unsigned long long)(t1_ - tk)); tk = t1_; } } while (0)
     for (int tile = blockIdx.x; tile < tp.ntiles; tile += gridDim.x) {
-        const int p0 = h_p0, o0 = h_o0, nobs_t = h_nobs, npts = h_npts;
-        // hand the prefetched index data to shared memory (the previous tile ended with a barrier)
-        if (tid < nobs_t) s_cord[tid] = (uint8_t)n_cord;
-        if (tid <= npts) s_pofs[tid] = n_pofs;
-        if (tid < npts) { s_M[3 * tid] = n_M0; s_M[3 * tid + 1] = n_M1; s_M[3 * tid + 2] = n_M2; }
-        if (tid <= pb.m) s_cst[tid] = (uint16_t)n_cst;
-        const double2 z = n_uv; const int my_cam = n_cam, my_lp = n_lpt;
-        load_header(tile + gridDim.x);                              // header of the next tile: in flight during P1
+        const int p0 = tp.tile_pt[tile], npts = tp.tile_pt[tile + 1] - p0;
+        const int o0 = tp.tile_o[tile], nobs_t = tp.tile_o[tile + 1] - o0;
+        // the tile's index data and points -> shared memory (the previous tile ended with a barrier)
+        double2 z = make_double2(0.0, 0.0); int my_cam = 0, my_lp = 0;
+        if (tid < nobs_t) {
+            const int k = o0 + tid;
+            z = pb.obs_uv[k]; my_cam = pb.obs_cam[k]; my_lp = lp.obs_lpt[k];
+            s_cord[tid] = lp.corder[k];
+        }
+        if (tid <= npts) s_pofs[tid] = pb.obs_ptr[p0 + tid] - o0;
+        if (tid < npts) { const int64_t i = p0 + tid; s_M[3 * tid] = pts[3 * i]; s_M[3 * tid + 1] = pts[3 * i + 1]; s_M[3 * tid + 2] = pts[3 * i + 2]; }
+        if (tid <= pb.m) s_cst[tid] = lp.cstart[(size_t)tile * (pb.m + 1) + tid];
         __syncthreads();
         LIN_TICK(0);
 
@@ -131,7 +114,7 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             }
             *reinterpret_cast<double2 *>(g + 32) = make_double2(e0, 0.0);      // [comp][{e, e'}]
             *reinterpret_cast<double2 *>(g + 34) = make_double2(e1, 0.0);
-            double *b = Bs + (size_t)tid * 8;
+            double *b = Bs + (size_t)tid * kBs;
             if (i >= pb.ncon) {
                 *reinterpret_cast<double2 *>(b) = make_double2(B[0], B[1]); *reinterpret_cast<double2 *>(b + 2) = make_double2(B[2], B[3]);
                 *reinterpret_cast<double2 *>(b + 4) = make_double2(B[4], B[5]);
@@ -141,7 +124,6 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             }
             *reinterpret_cast<double2 *>(b + 6) = make_double2(e0, e1);
         }
-        prefetch(tile + gridDim.x);                                 // next tile's data: in flight during P2..P4
         __syncthreads();
         LIN_TICK(1);
 
@@ -154,7 +136,7 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             if (have) {
                 const int ob = s_pofs[lpt], oe = s_pofs[lpt + 1];
                 for (int o = ob + q; o < oe; o += 8) {
-                    const double *b = Bs + (size_t)o * 8;
+                    const double *b = Bs + (size_t)o * kBs;
                     const double2 t0 = *reinterpret_cast<const double2 *>(b), t1 = *reinterpret_cast<const double2 *>(b + 2),
                                   t2 = *reinterpret_cast<const double2 *>(b + 4), t3 = *reinterpret_cast<const double2 *>(b + 6);
                     const double B0 = t0.x, B1 = t0.y, B2 = t1.x, B3 = t1.y, B4 = t2.x, B5 = t2.y, e0 = t3.x, e1 = t3.y;
@@ -219,7 +201,7 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
         // ---- P3: per observation: e' and Z ----
         if (mode != 0 && tid < nobs_t) {
             const double *P = Ps + my_lp * kPs;
-            const double *b = Bs + (size_t)tid * 8;
+            const double *b = Bs + (size_t)tid * kBs;
             const double2 t0 = *reinterpret_cast<const double2 *>(b), t1 = *reinterpret_cast<const double2 *>(b + 2),
                           t2 = *reinterpret_cast<const double2 *>(b + 4), t3 = *reinterpret_cast<const double2 *>(b + 6);
             const double B0 = t0.x, B1 = t0.y, B2 = t1.x, B3 = t1.y, B4 = t2.x, B5 = t2.y;

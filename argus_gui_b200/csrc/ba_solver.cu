@@ -513,7 +513,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
             for (int32_t k = optr[i]; k < optr[i + 1]; ++k) rr[ocam[k]] = (uint8_t)(k - optr[i]);
         }
     });
-    c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)c->tile_obs * (kGa + 8) * sizeof(double) +
+    c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)c->tile_obs * (kGa + kBs) * sizeof(double) +
                   (size_t)kTilePts * kPs * sizeof(double);
     {
         int occ = (int)((220 * 1024) / (c->lin_smem + 1024)); if (occ < 1) occ = 1; if (occ > 2) occ = 2;
