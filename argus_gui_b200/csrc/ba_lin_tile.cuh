@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                         double vv[6] = {v00, v01, v02, v11, v12, v22};
                         if (use_state) { vv[0] = out.vstate[3 * i]; vv[3] = out.vstate[3 * i + 1]; vv[5] = out.vstate[3 * i + 2]; }
                         vv[0] += mu; vv[3] += mu; vv[5] += mu;
-                        double li[3], di[3];
-                        if (!sym3_ldl_inv(vv, li, di)) {
+                        double li[3], di[3], rs[3];
+                        if (!sym3_ldl_inv_rs(vv, li, di, rs)) {
                             atomicOr(out.flag, 1);
                             out.zsign[i] = 0;
                         } else {
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                             Ni[0] = n00; Ni[1] = n01; Ni[2] = n02; Ni[3] = n11; Ni[4] = n12; Ni[5] = n22;
                             if (write_state) { out.vstate[3 * i] = n00; out.vstate[3 * i + 1] = n11; out.vstate[3 * i + 2] = n22; }
                             P[0] = li[0]; P[1] = li[1]; P[2] = li[2];
-                            P[3] = sqrt(fabs(di[0])); P[4] = sqrt(fabs(di[1])); P[5] = sqrt(fabs(di[2]));
+                            P[3] = rs[0]; P[4] = rs[1]; P[5] = rs[2];
                             P[6] = n00 * b0 + n01 * b1 + n02 * b2; P[7] = n01 * b0 + n11 * b1 + n12 * b2; P[8] = n02 * b0 + n12 * b1 + n22 * b2;
                             out.zsign[i] = (uint8_t)((di[0] < 0.0 ? 1 : 0) | (di[1] < 0.0 ? 2 : 0) | (di[2] < 0.0 ? 4 : 0));
                         }

@@ -129,7 +129,8 @@ __global__ void __launch_bounds__(128) k_make_z(BaProblem pb, double mu, int use
     for (int t = threadIdx.x; t < pb.m * 16; t += blockDim.x) Epart[(int64_t)blockIdx.x * pb.m * 16 + t] = Es[t];
 }
 
-// The Schur kernel.  grid = (nchunk, G); NW warps, each owning NB blocks; lane 0 of warp 0 doubles as the copy producer.
+// The Schur kernel.  grid = (nchunk, G); NW consumer warps, each owning NB blocks; the copy producer is lane 0 of warp 0
+// (PROD = 0) or a dedicated extra warp (PROD = 1).
 // Dynamic shared memory: 2 x [Z tile: TO x 48 doubles | rank tile: 32 x mp bytes], then one Z row (384 B) of zeros.
 // Spart[chunk][pair][256]: per-chunk partial sums in fragment order (lane * 8 + q), q = (ri*2 + ci)*2 + e for the
 // 8x8 sub-tile (ri, ci) of the block: element (row = ri*8 + lane>>2, col = ci*8 + 2*(lane&3) + e).
@@ -154,8 +155,8 @@ __device__ __forceinline__ double flip_sign(double v, uint32_t bit)      // bit 
     return __hiloint2double(__double2hiint(v) ^ (int)(bit << 31), __double2loint(v));
 }
 
-template <int NB, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(BaProblem pb, TilePlan tp, SchurPlan sp, const double *__restrict__ Z,
+template <int NB, int NW, int PROD>
+__global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb, TilePlan tp, SchurPlan sp, const double *__restrict__ Z,
                                                                  const uint8_t *__restrict__ zsign, const uint8_t *__restrict__ pt_rank,
                                                                  int mp, double *__restrict__ Spart)
 {
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(BaProblem pb, TilePlan
     // producer duty (warp 0, lane 0): bulk-async copies of the Z rows and the rank rows of local tile `it` into stage it & 1,
     // after every warp has released that stage (mempty)
     auto produce = [&](int it) {
-        if (warp == 0 && lane == 0) {
+        if (warp == (PROD ? NW : 0) && lane == 0) {
             const int b = it & 1;
             if (it >= 2) mbar_wait(&mempty[b], (uint32_t)(((it >> 1) - 1) & 1));
             const int t = chunk + it * sp.nchunk;
@@ -194,7 +195,9 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(BaProblem pb, TilePlan
         }
         __syncwarp();
     };
-    if (ntl > 0) produce(0);
+    if (PROD) {                      // dedicated producer warp: runs ahead of the consumers by up to two stages
+        if (warp == NW) { for (int it = 0; it < ntl; ++it) produce(it); return; }
+    } else if (ntl > 0) produce(0);
 
     // ---------------- consumer warps ----------------
     int bj[NB], bk[NB];
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(BaProblem pb, TilePlan
 
     for (int it = 0; it < ntl; ++it) {
         const int ob = ob_n; const uint32_t sg = sg_n; const bool have = hv_n;
-        if (it + 1 < ntl) produce(it + 1);
+        if (!PROD && it + 1 < ntl) produce(it + 1);
         load_meta(bp0, bp1, bo0, ob_n, sg_n, hv_n);          // tile it + 1 (bounds arrived during the previous tile)
         load_bounds(it + 2, bp0, bp1, bo0);
         const int sb = it & 1;

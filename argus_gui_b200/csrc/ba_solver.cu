@@ -258,14 +258,15 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
             ProfScope ps(c, P_SCHUR);
             dim3 grid(c->schur_nchunk, c->schur_G);
             const size_t sm = (size_t)2 * ((size_t)c->tile_obs * 384 + (size_t)kTilePts * c->rank_mp) + 384;
-#define SCHUR_LAUNCH(NB_, NW_) k_schur_mma<NB_, NW_><<<grid, NW_ * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, \
+#define SCHUR_LAUNCH(NB_, NW_, PR_) k_schur_mma<NB_, NW_, PR_><<<grid, (NW_ + PR_) * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, \
                                                                                        c->zsign.p, c->pt_rank.p, c->rank_mp, c->Spart.p)
             switch (c->schur_NB * 100 + c->schur_NW) {
-                case 108: SCHUR_LAUNCH(1, 8); break;
-                case 308: SCHUR_LAUNCH(3, 8); break;
-                case 508: SCHUR_LAUNCH(5, 8); break;
-                case 612: SCHUR_LAUNCH(6, 12); break;
-                default: SCHUR_LAUNCH(9, 8); break;
+                case 108: SCHUR_LAUNCH(1, 8, 0); break;
+                case 308: SCHUR_LAUNCH(3, 8, 0); break;
+                case 508: SCHUR_LAUNCH(5, 8, 0); break;
+                case 612: SCHUR_LAUNCH(6, 12, 0); break;
+                case 711: SCHUR_LAUNCH(7, 11, 1); break;
+                default: SCHUR_LAUNCH(9, 8, 0); break;
             }
 #undef SCHUR_LAUNCH
         }
@@ -370,11 +371,12 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
     if (const char *e = getenv("ARGUS_BA_GEN")) c->gen = atoi(e);
     {
         const int smx = 2 * (256 * 384 + 32 * 64) + 384;
-        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
-        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
-        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
-        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<9, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
-        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<6, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<3, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<5, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<9, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<6, 12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<7, 11, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
     }
     if (const char *e = getenv("ARGUS_SCHUR_NW")) c->schur_nw_pref = atoi(e);
     if (getenv("ARGUS_LIN_DEBUG")) { ARGUS_CUDA_CHECK(cudaMalloc(&c->lin_dbg, 8 * sizeof(unsigned long long))); ARGUS_CUDA_CHECK(cudaMemset(c->lin_dbg, 0, 8 * sizeof(unsigned long long))); }
@@ -481,6 +483,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         int NB = 9, NW = 8;
         for (int q = 0; q < 4; ++q) if (kSchurWarps * cand[q] >= c->npairs) { NB = cand[q]; break; }
         if (NB == 9 && c->schur_nw_pref == 12) { NB = 6; NW = 12; }
+        if (NB == 9 && c->schur_nw_pref == 11) { NB = 7; NW = 11; }
         c->schur_NB = NB; c->schur_NW = NW;
         c->schur_G = (c->npairs + NW * NB - 1) / (NW * NB);
         int nch = c->sms / c->schur_G; if (nch < 1) nch = 1;

@@ -198,4 +198,42 @@ ARGUS_HD bool sym3_ldl_inv(const double *v, double *li, double *di)
     return true;
 }
 
+// Same factorisation with one reciprocal square root per pivot instead of a division and a square root:
+// rs[k] = 1/sqrt(|d_k|), di[k] = sign(d_k) rs[k]^2 (= 1/d_k to a few ulp).  Three dependent rsqrt chains are the whole
+// critical path of the per-point phase of the tile kernel.
+ARGUS_HD bool sym3_ldl_inv_rs(const double *v, double *li, double *di, double *rs)
+{
+    const double d0 = v[0];
+    if (d0 == 0.0) return false;
+#if defined(__CUDA_ARCH__)
+    const double r0 = rsqrt(fabs(d0));
+#else
+    const double r0 = 1.0 / sqrt(fabs(d0));
+#endif
+    const double i0 = (d0 < 0.0) ? -(r0 * r0) : r0 * r0;
+    const double l10 = v[1] * i0, l20 = v[2] * i0;
+    const double d1 = v[3] - l10 * v[1];
+    if (d1 == 0.0) return false;
+#if defined(__CUDA_ARCH__)
+    const double r1 = rsqrt(fabs(d1));
+#else
+    const double r1 = 1.0 / sqrt(fabs(d1));
+#endif
+    const double i1 = (d1 < 0.0) ? -(r1 * r1) : r1 * r1;
+    const double l21 = (v[4] - l20 * v[1]) * i1;
+    const double d2 = v[5] - l20 * v[2] - l21 * l21 * d1;
+    if (d2 == 0.0) return false;
+#if defined(__CUDA_ARCH__)
+    const double r2 = rsqrt(fabs(d2));
+#else
+    const double r2 = 1.0 / sqrt(fabs(d2));
+#endif
+    di[0] = i0; di[1] = i1; di[2] = (d2 < 0.0) ? -(r2 * r2) : r2 * r2;
+    rs[0] = r0; rs[1] = r1; rs[2] = r2;
+    li[0] = -l10;
+    li[1] = l10 * l21 - l20;
+    li[2] = -l21;
+    return true;
+}
+
 }  // namespace argus
