@@ -171,6 +171,90 @@ __global__ void __launch_bounds__(256) k_dlt_reproj(const double *__restrict__ x
     err[(int64_t)track * N + frame] = reproj_one(pts + t * 2 * m, X, m, cams);
 }
 
+// Fused triangulation + reprojection error (argus_dlt_reconstruct): every pixel is undistorted once instead of twice.
+// Identical results to k_dlt_triangulate followed by k_dlt_reproj (same per-camera arithmetic in the same order).
+template <int MMAX>
+__global__ void __launch_bounds__(256) k_dlt_fused(const double *__restrict__ pts, int64_t N, int m, int k, DltCams cams,
+                                                   double *__restrict__ xyz, double *__restrict__ err, int flags)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * k) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const double *row = pts + t * 2 * m;
+    float fu[MMAX], fv[MMAX];
+    unsigned long long seen_u = 0ull, seen_uv = 0ull;
+    double M[6] = {0, 0, 0, 0, 0, 0}, r[3] = {0, 0, 0};
+    int nvis = 0, lj = -1;
+#pragma unroll
+    for (int j = 0; j < MMAX; ++j) {
+        if (j < m) {
+            const double2 uv = *reinterpret_cast<const double2 *>(row + 2 * j);
+            fu[j] = 0.f; fv[j] = 0.f;
+            if (!isnan(uv.x)) {
+                seen_u |= 1ull << j;
+                undistort_f32(uv.x, uv.y, cams.prof + 8 * j, fu[j], fv[j]);
+                if (!isnan(uv.y)) {
+                    seen_uv |= 1ull << j;
+                    const double *L = cams.dlt + 11 * j;
+                    const double du = (double)fu[j];
+                    ne_add(du * L[8] - L[0], du * L[9] - L[1], du * L[10] - L[2], L[3] - du, M, r);
+                    if (flags & 1) {
+                        const double dv = (double)fv[j];
+                        ne_add(dv * L[8] - L[4], dv * L[9] - L[5], dv * L[10] - L[6], L[7] - dv, M, r);
+                    }
+                    lj = j; ++nvis;
+                }
+            }
+        }
+    }
+    double X[3] = {nan, nan, nan};
+    if (nvis >= 2) {
+        if (!(flags & 1)) {
+            float lv = 0.f;
+#pragma unroll
+            for (int j = 0; j < MMAX; ++j) if (j == lj) lv = fv[j];
+            const double *L = cams.dlt + 11 * lj;
+            const double dv = (double)lv;
+            ne_add(dv * L[8] - L[4], dv * L[9] - L[5], dv * L[10] - L[6], L[7] - dv, M, r);
+        }
+        const double l00 = sqrt(M[0]);
+        const double l10 = M[1] / l00, l20 = M[2] / l00;
+        const double l11 = sqrt(M[3] - l10 * l10);
+        const double l21 = (M[4] - l20 * l10) / l11;
+        const double l22 = sqrt(M[5] - l20 * l20 - l21 * l21);
+        const double y0 = r[0] / l00;
+        const double y1 = (r[1] - l10 * y0) / l11;
+        const double y2 = (r[2] - l20 * y0 - l21 * y1) / l22;
+        X[2] = y2 / l22;
+        X[1] = (y1 - l21 * X[2]) / l11;
+        X[0] = (y0 - l10 * X[1] - l20 * X[2]) / l00;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) if (X[q] == 0.0) X[q] = nan;
+    }
+    double *o = xyz + 3 * t;
+    o[0] = X[0]; o[1] = X[1]; o[2] = X[2];
+    double e = nan;
+    if (!(isnan(X[0]) || isnan(X[1]) || isnan(X[2]))) {
+        double eps = 0.0; int nc = 0;
+#pragma unroll
+        for (int j = 0; j < MMAX; ++j) {
+            if (j < m && ((seen_u >> j) & 1ull)) {
+                const double *L = cams.dlt + 11 * j;
+                const double den = L[8] * X[0] + L[9] * X[1] + L[10] * X[2] + 1.0;
+                const double ru = (L[0] * X[0] + L[1] * X[1] + L[2] * X[2] + L[3]) / den;
+                const double rv = (L[4] * X[0] + L[5] * X[1] + L[6] * X[2] + L[7]) / den;
+                const double d0 = (double)fu[j] - ru, d1 = (double)fv[j] - rv;
+                eps += d0 * d0 + d1 * d1;
+                ++nc;
+            }
+        }
+        e = (nc == 2) ? sqrt(eps / 2.0) : sqrt(eps / (double)(2 * nc - 3));
+        if (e == 0.0) e = nan;
+    }
+    const int64_t frame = t / k; const int track = (int)(t % k);
+    err[(int64_t)track * N + frame] = e;
+}
+
 int launch_tri(const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt, double *d_xyz, int flags, cudaStream_t s)
 {
     const int64_t T = N * k;
@@ -186,6 +270,25 @@ int launch_err(const double *d_xyz, const double *d_pts, int64_t N, int m, int k
     if (T == 0) return ARGUS_OK;
     DltCams cams{d_prof, d_dlt};
     k_dlt_reproj<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(d_xyz, d_pts, N, m, k, cams, d_err);
+    DLT_CUDA_CHECK(cudaGetLastError());
+    return ARGUS_OK;
+}
+
+int launch_fused(const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt, double *d_xyz, double *d_err,
+                 int flags, cudaStream_t s)
+{
+    const int64_t T = N * k;
+    if (T == 0) return ARGUS_OK;
+    DltCams cams{d_prof, d_dlt};
+    const unsigned grid = (unsigned)((T + 255) / 256);
+    if (m <= 4) k_dlt_fused<4><<<grid, 256, 0, s>>>(d_pts, N, m, k, cams, d_xyz, d_err, flags);
+    else if (m <= 8) k_dlt_fused<8><<<grid, 256, 0, s>>>(d_pts, N, m, k, cams, d_xyz, d_err, flags);
+    else if (m <= 16) k_dlt_fused<16><<<grid, 256, 0, s>>>(d_pts, N, m, k, cams, d_xyz, d_err, flags);
+    else {      // many cameras: the two-kernel path (no per-thread camera arrays)
+        int rc = launch_tri(d_pts, N, m, k, d_prof, d_dlt, d_xyz, flags, s);
+        if (rc) return rc;
+        return launch_err(d_xyz, d_pts, N, m, k, d_prof, d_dlt, d_err, s);
+    }
     DLT_CUDA_CHECK(cudaGetLastError());
     return ARGUS_OK;
 }
@@ -222,6 +325,13 @@ int argus_dlt_reproj_error_dev(const double *d_xyz, const double *d_pts, int64_t
 {
     if (!d_xyz || !d_pts || !d_prof || !d_dlt || !d_err || m < 1 || m > kMaxCams || k < 1 || N < 0) return ARGUS_E_ARG;
     return launch_err(d_xyz, d_pts, N, m, k, d_prof, d_dlt, d_err, (cudaStream_t)stream);
+}
+
+int argus_dlt_reconstruct_dev(const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt, double *d_xyz,
+                              double *d_err, int flags, void *stream)
+{
+    if (!d_pts || !d_prof || !d_dlt || !d_xyz || !d_err || m < 1 || m > kMaxCams || k < 1 || N < 0) return ARGUS_E_ARG;
+    return launch_fused(d_pts, N, m, k, d_prof, d_dlt, d_xyz, d_err, flags, (cudaStream_t)stream);
 }
 
 int argus_dlt_triangulate(const double *pts, int64_t N, int m, int k, const double *prof, const double *dlt, double *xyz, int flags)
@@ -269,9 +379,7 @@ int argus_dlt_reconstruct(const double *pts, int64_t N, int m, int k, const doub
     DLT_CUDA_CHECK(cudaMemcpy(d_pts, pts, (size_t)N * 2 * m * k * sizeof(double), cudaMemcpyHostToDevice));
     DLT_CUDA_CHECK(cudaMemcpy(d_prof, prof, (size_t)m * 8 * sizeof(double), cudaMemcpyHostToDevice));
     DLT_CUDA_CHECK(cudaMemcpy(d_dlt, dlt, (size_t)m * 11 * sizeof(double), cudaMemcpyHostToDevice));
-    int rc = launch_tri(d_pts, N, m, k, d_prof, d_dlt, d_xyz, flags, 0);
-    if (rc) return rc;
-    rc = launch_err(d_xyz, d_pts, N, m, k, d_prof, d_dlt, d_err, 0);
+    int rc = launch_fused(d_pts, N, m, k, d_prof, d_dlt, d_xyz, d_err, flags, 0);
     if (rc) return rc;
     DLT_CUDA_CHECK(cudaMemcpy(xyz, d_xyz, (size_t)N * 3 * k * sizeof(double), cudaMemcpyDeviceToHost));
     DLT_CUDA_CHECK(cudaMemcpy(err, d_err, (size_t)N * k * sizeof(double), cudaMemcpyDeviceToHost));

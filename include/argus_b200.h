@@ -118,6 +118,8 @@ int  argus_undistort_points(const double *pts, int64_t N, const double *prof8, f
 /* device-pointer variants (inputs already resident in HBM; used for the kernel-only timings) */
 int  argus_dlt_triangulate_dev(const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt,
                                double *d_xyz, int flags, void *stream);
+int  argus_dlt_reconstruct_dev(const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt,
+                               double *d_xyz, double *d_err, int flags, void *stream);
 int  argus_dlt_reproj_error_dev(const double *d_xyz, const double *d_pts, int64_t N, int m, int k,
                                 const double *d_prof, const double *d_dlt, double *d_err, void *stream);
 

@@ -43,8 +43,9 @@ def test_d1_d2_golden(golden_dlt, case, m, k):
     for t in range(k):
         one = dlt.triangulate(np.ascontiguousarray(pts[:, t * 2 * m:(t + 1) * 2 * m]), prof, L)
         assert np.array_equal(one, xyz[:, 3 * t:3 * t + 3], equal_nan=True)
-    x2, e2 = dlt.reconstruct(pts, prof, L)
+    x2, e2 = dlt.reconstruct(pts, prof, L)          # fused kernel: identical to the two separate calls, bit for bit
     assert np.array_equal(x2, xyz, equal_nan=True)
+    assert np.array_equal(e2, dlt.reproj_error(xyz, pts, prof, L), equal_nan=True)
 
 
 def test_textbook_flag_matches_oracle(golden_dlt):
