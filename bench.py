@@ -344,6 +344,12 @@ def main():
         rl = {"kernel": dom, "bound": "hbm", "achieved": per / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src}
     rl["frac"] = rl["achieved"] / rl["peak"]
     rl["traffic"] = None
+    try:        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of the same command
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tr.get("workload") == args.workload and dom in tr:
+            rl["traffic"] = tr[dom]; rl["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+    except Exception:
+        pass
     rl["ms_per_launch"] = dom_ms
     rl["share_of_kernel_time"] = kern[dom][0] / sum_ms
     t_iter = ms_total * 1e-3 / (ITERS_PER_STEP * args.steps)
