@@ -34,6 +34,7 @@ SIGNATURES = {
     "argus_ba_set_comm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ALLREDUCE_FN, ctypes.c_void_p]),
     "argus_ba_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "argus_ba_set_camera_fix": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "argus_ba_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "argus_ba_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "argus_ba_download": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

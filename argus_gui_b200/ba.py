@@ -90,6 +90,17 @@ class BundleAdjuster:
         _lib.check(rc, "argus_ba_upload")
         return self
 
+    def set_camera_fix(self, nccalib, ncdist):
+        """Per-camera numbers of fixed trailing intrinsics / distortion coefficients (extension; ``None, None`` resets)."""
+        if nccalib is None or ncdist is None:
+            rc = self.lib.argus_ba_set_camera_fix(self.h, None, None)
+        else:
+            a = np.ascontiguousarray(nccalib, dtype=np.int32); b = np.ascontiguousarray(ncdist, dtype=np.int32)
+            if a.size != self.m or b.size != self.m:
+                raise ValueError("one entry per camera expected")
+            rc = self.lib.argus_ba_set_camera_fix(self.h, _ptr(a), _ptr(b))
+        _lib.check(rc, "argus_ba_set_camera_fix")
+
     def reset(self):
         _lib.check(self.lib.argus_ba_reset(self.h), "argus_ba_reset")
 

@@ -15,7 +15,8 @@ struct BaProblem {
     int     m;        // cameras (all ranks)
     int     mcon;     // leading fixed cameras
     int64_t nobs;     // visible projections on this rank
-    int     nfix_k, nfix_d;   // nccalib / ncdist
+    int     nfix_k, nfix_d;   // nccalib / ncdist (all cameras)
+    const uint8_t *cam_fix;   // optional per-camera override: [2j] = nccalib_j, [2j+1] = ncdist_j (extension; nullptr = global)
 
     const int32_t  *obs_ptr;  // n+1: first observation of each point
     const uint8_t  *obs_cam;  // nobs: camera of each observation

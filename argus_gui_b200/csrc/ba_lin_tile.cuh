@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             const int64_t i = p0 + my_lp;
             const double M0 = s_M[3 * my_lp], M1 = s_M[3 * my_lp + 1], M2 = s_M[3 * my_lp + 2];
             double u, v, A[32], B[6];
-            cam_project_jac(sc[my_cam], M0, M1, M2, pb.nfix_k, pb.nfix_d, u, v, A, B);
+            const int nfk = pb.cam_fix ? pb.cam_fix[2 * my_cam] : pb.nfix_k, nfd = pb.cam_fix ? pb.cam_fix[2 * my_cam + 1] : pb.nfix_d;
+            cam_project_jac(sc[my_cam], M0, M1, M2, nfk, nfd, u, v, A, B);
             const double e0 = z.x - u, e1 = z.y - v;
             cost += e0 * e0 + e1 * e1;
             double *g = Ga + (size_t)tid * kGa;
@@ -351,7 +352,8 @@ __global__ void __launch_bounds__(128) k_backsub_recompute(BaProblem pb, double 
                 const int j = pb.obs_cam[k];
                 if (j < pb.mcon) continue;
                 double u, v, A[32], B[6];
-                cam_project_jac(sc[j], M0, M1, M2, pb.nfix_k, pb.nfix_d, u, v, A, B);
+                const int nfk = pb.cam_fix ? pb.cam_fix[2 * j] : pb.nfix_k, nfd = pb.cam_fix ? pb.cam_fix[2 * j + 1] : pb.nfix_d;
+                cam_project_jac(sc[j], M0, M1, M2, nfk, nfd, u, v, A, B);
                 const double *dj = das + 16 * j;
                 double s0 = 0.0, s1 = 0.0;
 #pragma unroll

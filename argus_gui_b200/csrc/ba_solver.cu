@@ -94,7 +94,8 @@ struct argus_ba_ctx {
     int gen = 3;
     int schur_nw_pref = 12;
     DevBuf<int32_t> tile_pt, tile_o; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
-    DevBuf<uint8_t> obs_lpt, corder, pt_rank; int rank_mp = 16; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect, cholwork;
+    DevBuf<uint8_t> obs_lpt, corder, pt_rank; int rank_mp = 16;
+    DevBuf<uint8_t> cam_fix; bool cam_fix_on = false; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect, cholwork;
     int grid_lin = 1; size_t lin_smem = 0;
     unsigned long long *lin_dbg = nullptr;
     int ntiles = 0, tile_obs = 256, schur_G = 1, schur_NB = 1, schur_NW = 8, schur_nchunk = 1;
@@ -122,7 +123,7 @@ struct argus_ba_ctx {
     }
     BaProblem problem() const {
         BaProblem pb;
-        pb.n = n; pb.ncon = ncon; pb.m = m; pb.mcon = mcon; pb.nobs = nobs; pb.nfix_k = nfix_k; pb.nfix_d = nfix_d;
+        pb.n = n; pb.ncon = ncon; pb.m = m; pb.mcon = mcon; pb.nobs = nobs; pb.nfix_k = nfix_k; pb.nfix_d = nfix_d; pb.cam_fix = cam_fix_on ? cam_fix.p : nullptr;
         pb.obs_ptr = obs_ptr.p; pb.obs_cam = obs_cam.p; pb.obs_uv = obs_uv.p; pb.pt_mask = pt_mask.p; pb.rot0 = rot0.p;
         return pb;
     }
@@ -399,7 +400,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
                               &c->vstate, &c->Vinv, &c->cvec, &c->dbuf, &c->Upart, &c->scpart, &c->red1, &c->max2, &c->Epart, &c->Spart,
                               &c->red2, &c->S, &c->E, &c->da_free, &c->da_full, &c->part3, &c->red3, &c->cam2, &c->scal, &c->att, &c->respart};
     for (auto *b : bufs) b->release();
-    c->obs_lpt.release(); c->corder.release(); c->pt_rank.release(); c->cstart.release(); c->Upart2.release(); c->Edirect.release(); c->cholwork.release();
+    c->obs_lpt.release(); c->corder.release(); c->pt_rank.release(); c->cam_fix.release(); c->cstart.release(); c->Upart2.release(); c->Edirect.release(); c->cholwork.release();
     c->flags.release(); c->tile_pt.release(); c->tile_o.release(); c->blk_jk.release(); c->blk_pair.release(); c->zsign.release(); c->Z.release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->arena.base) cudaFree(c->arena.base);
@@ -448,7 +449,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
             while (mk) { ocam[k++] = (uint8_t)__builtin_ctzll(mk); mk &= mk - 1; }
         }
     });
-    c->n = n; c->ncon = ncon; c->m = m; c->mcon = mcon; c->nobs = nobs; c->nfix_k = nccalib; c->nfix_d = ncdist;
+    c->n = n; c->ncon = ncon; c->m = m; c->mcon = mcon; c->nobs = nobs; c->nfix_k = nccalib; c->nfix_d = ncdist; c->cam_fix_on = false;
     const int mf = m - mcon, N = 16 * mf;
     c->npairs = mf * (mf + 1) / 2;
     c->grid_pts128 = (int)std::min<int64_t>((n + 127) / 128, (int64_t)c->sms * 8); if (c->grid_pts128 < 1) c->grid_pts128 = 1;
@@ -599,6 +600,23 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     c->h2d_bytes += (n + 1) * sizeof(int32_t) + nobs * (sizeof(uint8_t) + sizeof(double2)) + n * sizeof(uint64_t) + (4 + 16) * m * sizeof(double) + 3 * n * sizeof(double);
     if (timing) fprintf(stderr, "argus_b200 upload: host index build %.1f ms, device alloc %.1f ms, H2D %.1f ms\n", 1e3 * (t_index - t_start), 1e3 * (t_alloc - t_index), 1e3 * (tnow() - t_alloc));
     return argus_ba_reset(c);
+}
+
+int argus_ba_set_camera_fix(argus_ba_ctx *c, const int *nccalib, const int *ncdist)
+{
+    if (!c || c->m == 0) return ARGUS_E_ARG;
+    ARGUS_CUDA_CHECK(cudaSetDevice(c->device));
+    if (!nccalib || !ncdist) { c->cam_fix_on = false; return ARGUS_OK; }
+    if (c->gen < 3) return ARGUS_E_ARG;            // only the tile kernels implement the per-camera extension
+    std::vector<uint8_t> h(2 * (size_t)c->m);
+    for (int j = 0; j < c->m; ++j) {
+        if (nccalib[j] < 0 || nccalib[j] > 5 || ncdist[j] < 0 || ncdist[j] > 5) return ARGUS_E_ARG;
+        h[2 * j] = (uint8_t)nccalib[j]; h[2 * j + 1] = (uint8_t)ncdist[j];
+    }
+    ARGUS_CUDA_CHECK(c->cam_fix.ensure(h.size()));
+    ARGUS_CUDA_CHECK(cudaMemcpy(c->cam_fix.p, h.data(), h.size(), cudaMemcpyHostToDevice));
+    c->cam_fix_on = true;
+    return ARGUS_OK;
 }
 
 int argus_ba_reset(argus_ba_ctx *c)

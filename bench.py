@@ -35,6 +35,8 @@ WORKLOADS = {
     "c4": (16, 2_000_000, 10, 0, 0),
     "c3": (8, 200_000, 6, 0, 0),
     "small": (8, 20_000, 6, 0, 0),
+    # config 5: 32 cameras, 5M points x 12 views, 10 % outlier tracks, cameras 0-15 fixed intrinsics / 16-31 free (extension)
+    "c5": (32, 5_000_000, 12, 0, 0),
 }
 OPTS_FIXED_WORK = [1e-3, 0.0, 0.0, 0.0, 0.0]
 
@@ -99,7 +101,8 @@ class ClockSampler:
 def make_scene(workload, rank):
     from argus_gui_b200 import scenes
     m, n, views, nk, nd = WORKLOADS[workload]
-    s = scenes.make_ba_scene(m, n, views, seed=4 + 1000 * rank, cam_seed=4)
+    s = scenes.make_ba_scene(m, n, views, seed=4 + 1000 * rank, cam_seed=4, outlier_frac=0.1 if workload == "c5" else 0.0,
+                             radius=9.0 if workload == "c5" else 8.0)
     p0, rot0 = scenes.pack_ba_problem(s["cams0"], s["pts0"])
     return s, p0, rot0, (m, n, views, nk, nd)
 
@@ -275,6 +278,8 @@ def main():
         if world > 1:
             B.set_comm(rank, world, ba.torch_allreduce_hook())
         B.upload(s["vmask"], p0, rot0, s["x"], nk, nd)
+        if args.workload == "c5":
+            B.set_camera_fix([5] * 16 + [0] * 16, [5] * 16 + [0] * 16)
         for _ in range(args.warmup):
             B.reset(); ret, info = B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
             assert ret == ITERS_PER_STEP, (ret, info)

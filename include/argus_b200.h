@@ -75,6 +75,10 @@ int  argus_ba_set_comm(argus_ba_ctx *ctx, int rank, int world, argus_allreduce_f
 /* copy a problem (or this rank's shard of the points, with all cameras) to the device and build the indices */
 int  argus_ba_upload(argus_ba_ctx *ctx, int64_t n, int64_t ncon, int m, int mcon, const char *vmask,
                      const double *p, const double *rot0, const double *x, int nccalib, int ncdist);
+/* EXTENSION (no counterpart in the reference, whose nccalib / ncdist are global, sbaprojs.c:1229-1247): per-camera numbers
+ * of fixed trailing intrinsics / distortion coefficients, m entries each, after argus_ba_upload; NULL, NULL restores the global
+ * values.  BASELINE config 5 ("mixed fixed/free intrinsics") needs it. */
+int  argus_ba_set_camera_fix(argus_ba_ctx *ctx, const int *nccalib, const int *ncdist);
 /* restore the parameter vector uploaded last (device-side copy), e.g. between timed repetitions */
 int  argus_ba_reset(argus_ba_ctx *ctx);
 int  argus_ba_solve(argus_ba_ctx *ctx, int itmax, int verbose, const double opts[5], double info[10], int flags);

@@ -229,6 +229,11 @@ static double eval_cost(const vis_t *vs, const double *p, const double *rot0, co
     return sum;
 }
 
+/* per-camera fixed-parameter counts (EXTENSION used by BASELINE config 5; the reference's are global): when non-NULL,
+ * cam_nk[j] / cam_nd[j] replace nccalib / ncdist for camera j */
+static const int *g_cam_nk = NULL, *g_cam_nd = NULL;
+void orc_set_camera_fix(const int *nk, const int *nd) { g_cam_nk = nk; g_cam_nd = nd; }
+
 int orc_motstr(int64_t n, int64_t ncon, int m, int mcon, const char *vmask, double *p, const double *rot0, const double *x,
                int nccalib, int ncdist, int itmax, int verbose, const double opts[5], double info[10], int compat)
 {
@@ -270,7 +275,8 @@ int orc_motstr(int64_t n, int64_t ncon, int m, int mcon, const char *vmask, doub
         pb = p + CNP * m;
         for (int64_t i = 0; i < n; ++i)
             for (int64_t k = vs.ptr[i]; k < vs.ptr[i + 1]; ++k)
-                jac_one(p + CNP * vs.cam[k], rot0 + 4 * vs.cam[k], pb + PNP * i, nccalib, ncdist, A + 32 * k, B + 6 * k, NULL);
+                jac_one(p + CNP * vs.cam[k], rot0 + 4 * vs.cam[k], pb + PNP * i, g_cam_nk ? g_cam_nk[vs.cam[k]] : nccalib,
+                        g_cam_nd ? g_cam_nd[vs.cam[k]] : ncdist, A + 32 * k, B + 6 * k, NULL);
         ++njev;
         memset(U, 0, (size_t)m * 256 * sizeof(double)); memset(ea, 0, (size_t)m * CNP * sizeof(double));
         memset(V, 0, (size_t)n * 9 * sizeof(double)); memset(eb, 0, (size_t)n * PNP * sizeof(double));

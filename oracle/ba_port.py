@@ -52,7 +52,7 @@ def port_jacobian(p, vmask, rot0, nccalib=0, ncdist=0):
     return A, B
 
 
-def port_motstr(p, x, vmask, rot0, nccalib, ncdist, itmax=150, opts=None, ncon=0, mcon=0, verbose=0, compat=True):
+def port_motstr(p, x, vmask, rot0, nccalib, ncdist, itmax=150, opts=None, ncon=0, mcon=0, verbose=0, compat=True, cam_fix=None):
     """Same contract as oracle.sba_ref.ref_motstr: returns (p_new, info[10], retval)."""
     lib = load()
     vmask = np.ascontiguousarray(vmask, dtype=np.int8); n, m = vmask.shape
@@ -62,7 +62,12 @@ def port_motstr(p, x, vmask, rot0, nccalib, ncdist, itmax=150, opts=None, ncon=0
         opts = [1e-3, 1e-12, 1e-12, 1e-12, 0.0]
     opts = np.ascontiguousarray(opts, dtype=np.float64)
     info = np.zeros(10)
+    if cam_fix is not None:      # per-camera (nccalib_j, ncdist_j) extension
+        nk = np.ascontiguousarray(cam_fix[0], dtype=np.int32); nd = np.ascontiguousarray(cam_fix[1], dtype=np.int32)
+        lib.orc_set_camera_fix(_p(nk), _p(nd))
     ret = lib.orc_motstr(ctypes.c_int64(n), ctypes.c_int64(ncon), ctypes.c_int(m), ctypes.c_int(mcon), _p(vmask), _p(p), _p(rot0), _p(x),
                          ctypes.c_int(nccalib), ctypes.c_int(ncdist), ctypes.c_int(itmax), ctypes.c_int(verbose), _p(opts), _p(info),
                          ctypes.c_int(1 if compat else 0))
+    if cam_fix is not None:
+        lib.orc_set_camera_fix(None, None)
     return p, info, ret

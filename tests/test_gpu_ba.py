@@ -244,3 +244,25 @@ def test_m0_two_shards_equal_single(golden_ba):
         p_sh[:16 * m] = p_loc[:16 * m]
         p_sh[16 * m + 3 * lo:16 * m + 3 * hi] = p_loc[16 * m:]
     assert rel_blocks(p_sh, p_ref, m) < 1e-9
+
+
+def test_config5_shape_per_camera_fixed_intrinsics_and_outliers():
+    """BASELINE config 5 at reduced size: 32 cameras, 12 views per point, 10 % outlier tracks, cameras 0-15 with fixed
+    intrinsics + distortion, cameras 16-31 fully free (per-camera extension, argus_ba_set_camera_fix) - against the oracle
+    port with the same per-camera counts."""
+    m, n, views = 32, 6000, 12
+    s = scenes.make_ba_scene(m, n, views, seed=5, outlier_frac=0.1, radius=9.0)
+    p0, rot0 = scenes.pack_ba_problem(s["cams0"], s["pts0"])
+    nk = np.array([5] * 16 + [0] * 16); nd = np.array([5] * 16 + [0] * 16)
+    B = ba.BundleAdjuster().upload(s["vmask"], p0, rot0, s["x"], 0, 0)
+    B.set_camera_fix(nk, nd)
+    ret, info = B.solve(itmax=6)
+    pg = B.download()
+    B.close()
+    po, io, ro = ba_port.port_motstr(p0, s["x"], s["vmask"], rot0, 0, 0, itmax=6, cam_fix=(nk, nd))
+    assert ret == ro and list(info[5:]) == list(io[5:])
+    assert abs(info[1] - io[1]) <= 1e-8 * io[1]
+    assert rel_blocks(pg, po, m) < 1e-6
+    cg = pg[:16 * m].reshape(m, 16); c0 = p0[:16 * m].reshape(m, 16)
+    assert np.array_equal(cg[:16, :10], c0[:16, :10])         # fixed cameras: intrinsics and distortion untouched
+    assert np.abs(cg[16:, 0] - c0[16:, 0]).min() > 0            # free cameras: refined
