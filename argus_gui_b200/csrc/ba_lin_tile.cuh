@@ -41,6 +41,51 @@ struct LinTileOut {
     unsigned long long *dbg;     // optional per-phase clock counters (nullptr in production)
 };
 
+// ---- static index construction (once per upload; visibility never changes during a solve) ----
+// pt_rank[i][cam] = position of cam in point i's observation list (rows pre-filled with 0xFF; fixed points stay 0xFF)
+__global__ void k_build_point_index(int64_t n, int64_t ncon, int mp, const int32_t *__restrict__ obs_ptr, const uint8_t *__restrict__ obs_cam,
+                                    uint8_t *__restrict__ pt_rank)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || i < ncon) return;
+    const int k0 = obs_ptr[i], k1 = obs_ptr[i + 1];
+    uint8_t *rr = pt_rank + (size_t)i * mp;
+    for (int k = k0; k < k1; ++k) rr[obs_cam[k]] = (uint8_t)(k - k0);
+}
+
+// per tile: local point index of every observation, camera-sorted (stable) observation order and the camera run starts
+__global__ void __launch_bounds__(256) k_build_tile_index(int m, const int32_t *__restrict__ tile_pt, const int32_t *__restrict__ tile_o,
+                                                          const int32_t *__restrict__ obs_ptr, const uint8_t *__restrict__ obs_cam,
+                                                          uint8_t *__restrict__ obs_lpt, uint8_t *__restrict__ corder, uint16_t *__restrict__ cstart)
+{
+    __shared__ int s_pofs[kTilePts + 1];
+    __shared__ uint8_t s_cam[256];
+    __shared__ int s_cnt[ARGUS_BA_MAX_CAMS + 1];
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int p0 = tile_pt[tile], npts = tile_pt[tile + 1] - p0;
+    const int o0 = tile_o[tile], nobs_t = tile_o[tile + 1] - o0;
+    if (tid <= npts) s_pofs[tid] = obs_ptr[p0 + tid] - o0;
+    if (tid <= m) s_cnt[tid] = 0;
+    if (tid < nobs_t) s_cam[tid] = obs_cam[o0 + tid];
+    __syncthreads();
+    if (tid < nobs_t) {
+        int lp = 0;
+        while (lp + 1 < npts && tid >= s_pofs[lp + 1]) ++lp;
+        obs_lpt[o0 + tid] = (uint8_t)lp;
+        atomicAdd(&s_cnt[s_cam[tid] + 1], 1);               // integer histogram: order-independent
+    }
+    __syncthreads();
+    if (tid == 0) for (int j = 0; j < m; ++j) s_cnt[j + 1] += s_cnt[j];
+    __syncthreads();
+    if (tid <= m) cstart[(size_t)tile * (m + 1) + tid] = (uint16_t)s_cnt[tid];
+    if (tid < nobs_t) {                                      // stable position inside the camera's run: observations before me with my camera
+        const int cam = s_cam[tid];
+        int before = 0;
+        for (int q = 0; q < tid; ++q) before += (s_cam[q] == cam);
+        corder[o0 + s_cnt[cam] + before] = (uint8_t)tid;
+    }
+}
+
 // 32-byte global store (sm_100: st.global.v4.f64): one full sector per store instruction
 __device__ __forceinline__ void st_global_v4(double *p, double a, double b, double c, double d)
 {

@@ -491,32 +491,8 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         if (nch > c->ntiles) nch = c->ntiles > 0 ? c->ntiles : 1;
         c->schur_nchunk = nch;
     }
-    // per-observation local point index, per-tile camera-sorted observation order (static: visibility never changes)
-    std::vector<uint8_t> hlpt((size_t)nobs), hcord((size_t)nobs);
-    std::vector<uint16_t> hcst((size_t)c->ntiles * (m + 1));
-    parallel_for(c->ntiles, [&](int64_t tlo, int64_t thi) {
-        std::vector<int> cnt(m + 1);
-        for (int64_t tl = tlo; tl < thi; ++tl) {
-            const int32_t p0 = tiles[tl], p1 = tiles[tl + 1], o0 = optr[p0], o1 = optr[p1];
-            std::fill(cnt.begin(), cnt.end(), 0);
-            for (int32_t p = p0; p < p1; ++p)
-                for (int32_t k = optr[p]; k < optr[p + 1]; ++k) { hlpt[k] = (uint8_t)(p - p0); cnt[ocam[k] + 1]++; }
-            for (int j = 0; j < m; ++j) cnt[j + 1] += cnt[j];
-            uint16_t *cs = hcst.data() + (size_t)tl * (m + 1);
-            for (int j = 0; j <= m; ++j) cs[j] = (uint16_t)cnt[j];
-            for (int32_t k = o0; k < o1; ++k) hcord[o0 + cnt[ocam[k]]++] = (uint8_t)(k - o0);
-        }
-    });
     c->rank_mp = (m + 15) & ~15;
-    std::vector<uint8_t> hrank((size_t)n * c->rank_mp);
-    parallel_for(n, [&](int64_t lo, int64_t hi) {
-        const int mp = c->rank_mp;
-        memset(hrank.data() + (size_t)lo * mp, 0xFF, (size_t)(hi - lo) * mp);
-        for (int64_t i = std::max<int64_t>(lo, ncon); i < hi; ++i) {
-            uint8_t *rr = hrank.data() + (size_t)i * mp;
-            for (int32_t k = optr[i]; k < optr[i + 1]; ++k) rr[ocam[k]] = (uint8_t)(k - optr[i]);
-        }
-    });
+    // obs_lpt, corder, cstart and pt_rank are derived on the device from obs_ptr / obs_cam / tile_pt (k_build_*_index)
     c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)c->tile_obs * (kGa + kBs) * sizeof(double) +
                   (size_t)kTilePts * kPs * sizeof(double);
     {
@@ -545,9 +521,9 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
 #define PLAN_ENS(buf, cnt) PLAN_CHECK((buf).ensure((size_t)(cnt)))
     PLAN_CHECK(c->tile_pt.ensure(tiles.size())); PLAN_CHECK(c->tile_o.ensure(tiles.size())); PLAN_CHECK(c->blk_jk.ensure(hjk.size())); PLAN_CHECK(c->blk_pair.ensure(hpair.size()));
     PLAN_CHECK(c->zsign.ensure((size_t)n)); if (c->gen >= 2) { PLAN_ENS(c->Z, 48 * nobs); }
-    PLAN_CHECK(c->obs_lpt.ensure((size_t)nobs)); PLAN_CHECK(c->corder.ensure((size_t)nobs)); PLAN_CHECK(c->cstart.ensure(hcst.size()));
+    PLAN_CHECK(c->obs_lpt.ensure((size_t)nobs)); PLAN_CHECK(c->corder.ensure((size_t)nobs)); PLAN_CHECK(c->cstart.ensure((size_t)c->ntiles * (m + 1)));
     PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1024);
-    PLAN_CHECK(c->pt_rank.ensure(hrank.size()));
+    PLAN_CHECK(c->pt_rank.ensure((size_t)n * c->rank_mp));
     PLAN_ENS(c->obs_ptr, n + 1); PLAN_ENS(c->obs_cam, nobs); PLAN_ENS(c->obs_uv, nobs); PLAN_ENS(c->pt_mask, n);
     PLAN_ENS(c->rot0, 4 * m); PLAN_ENS(c->cam, 16 * m); PLAN_ENS(c->cam_new, 16 * m); PLAN_ENS(c->cam0, 16 * m);
     PLAN_ENS(c->pts, 3 * n); PLAN_ENS(c->pts_new, 3 * n); PLAN_ENS(c->pts0, 3 * n);
@@ -581,10 +557,6 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     }
     const double t_alloc = tnow();
     cudaStream_t s = c->stream;
-    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pt_rank.p, hrank.data(), hrank.size(), cudaMemcpyHostToDevice, s));
-    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_lpt.p, hlpt.data(), hlpt.size(), cudaMemcpyHostToDevice, s));
-    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->corder.p, hcord.data(), hcord.size(), cudaMemcpyHostToDevice, s));
-    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cstart.p, hcst.data(), hcst.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_pt.p, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_o.p, tile_o.data(), tile_o.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_jk.p, hjk.data(), hjk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
@@ -596,8 +568,18 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->rot0.p, rot0, 4 * m * sizeof(double), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cam0.p, p, 16 * m * sizeof(double), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pts0.p, p + 16 * m, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    // derived static indices, built on the device
+    if (n > 0) {
+        ARGUS_CUDA_CHECK(cudaMemsetAsync(c->pt_rank.p, 0xFF, (size_t)n * c->rank_mp, s));
+        k_build_point_index<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, ncon, c->rank_mp, c->obs_ptr.p, c->obs_cam.p, c->pt_rank.p);
+        if (c->ntiles > 0)
+            k_build_tile_index<<<c->ntiles, 256, 0, s>>>(m, c->tile_pt.p, c->tile_o.p, c->obs_ptr.p, c->obs_cam.p, c->obs_lpt.p, c->corder.p,
+                                                         c->cstart.p);
+        ARGUS_CUDA_CHECK(cudaGetLastError());
+    }
     ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));      // host staging vectors go out of scope
-    c->h2d_bytes += (n + 1) * sizeof(int32_t) + nobs * (sizeof(uint8_t) + sizeof(double2)) + n * sizeof(uint64_t) + (4 + 16) * m * sizeof(double) + 3 * n * sizeof(double);
+    c->h2d_bytes += (n + 1) * sizeof(int32_t) + nobs * (sizeof(uint8_t) + sizeof(double2)) + n * sizeof(uint64_t) + (4 + 16) * m * sizeof(double) + 3 * n * sizeof(double) +
+                    2 * tiles.size() * sizeof(int32_t);
     if (timing) fprintf(stderr, "argus_b200 upload: host index build %.1f ms, device alloc %.1f ms, H2D %.1f ms\n", 1e3 * (t_index - t_start), 1e3 * (t_alloc - t_index), 1e3 * (tnow() - t_alloc));
     return argus_ba_reset(c);
 }
