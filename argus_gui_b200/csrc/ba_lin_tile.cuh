@@ -281,27 +281,34 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
         __syncthreads();
         LIN_TICK(3);
 
-        // ---- P4: Gram per camera on the tensor pipe ----
+        // ---- P4: Gram per camera on the tensor pipe (the cameras a warp owns advance together: independent DMMA chains) ----
+        {
+            int c0q[MC], njq[MC], smax = 0;
 #pragma unroll
-        for (int q = 0; q < MC; ++q) {
-            const int j = pb.mcon + warp + 8 * q;
-            if (j < pb.m) {
-                const int c0 = s_cst[j], nj = s_cst[j + 1] - c0;
-#pragma unroll 2
-                for (int s = 0; s < nj; s += 2) {
-                    const int idx = s + (kk >> 1);
-                    const bool valid = idx < nj;
-                    const int o = s_cord[c0 + (valid ? idx : 0)];
-                    const int comp = kk & 1;
-                    const double *g = Ga + (size_t)o * kGa;
-                    double2 a = *reinterpret_cast<const double2 *>(g + comp * 16 + g8 * 2);
-                    double ax = (g8 < 2) ? g[32 + comp * 2 + g8] : 0.0;
-                    if (!valid) { a.x = 0.0; a.y = 0.0; ax = 0.0; }
-                    dmma884(uacc[q][0], uacc[q][1], a.x, a.x);
-                    dmma884(uacc[q][2], uacc[q][3], a.x, a.y);
-                    dmma884(uacc[q][4], uacc[q][5], a.y, a.y);
-                    dmma884(uacc[q][6], uacc[q][7], a.x, ax);
-                    dmma884(uacc[q][8], uacc[q][9], a.y, ax);
+            for (int q = 0; q < MC; ++q) {
+                const int j = pb.mcon + warp + 8 * q;
+                c0q[q] = 0; njq[q] = 0;
+                if (j < pb.m) { c0q[q] = s_cst[j]; njq[q] = s_cst[j + 1] - c0q[q]; }
+                smax = max(smax, njq[q]);
+            }
+            const int comp = kk & 1;
+            for (int s = 0; s < smax; s += 2) {
+#pragma unroll
+                for (int q = 0; q < MC; ++q) {
+                    if (s < njq[q]) {
+                        const int idx = s + (kk >> 1);
+                        const bool valid = idx < njq[q];
+                        const int o = s_cord[c0q[q] + (valid ? idx : 0)];
+                        const double *g = Ga + (size_t)o * kGa;
+                        double2 a = *reinterpret_cast<const double2 *>(g + comp * 16 + g8 * 2);
+                        double ax = (g8 < 2) ? g[32 + comp * 2 + g8] : 0.0;
+                        if (!valid) { a.x = 0.0; a.y = 0.0; ax = 0.0; }
+                        dmma884(uacc[q][0], uacc[q][1], a.x, a.x);
+                        dmma884(uacc[q][2], uacc[q][3], a.x, a.y);
+                        dmma884(uacc[q][4], uacc[q][5], a.y, a.y);
+                        dmma884(uacc[q][6], uacc[q][7], a.x, ax);
+                        dmma884(uacc[q][8], uacc[q][9], a.y, ax);
+                    }
                 }
             }
         }
