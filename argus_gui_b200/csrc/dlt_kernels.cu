@@ -18,6 +18,7 @@
 // HBM-bound: 88 B (triangulate) / 96 B (error) per (frame, track) at m = 4; no shared memory needed, the camera
 // tables (m x 19 doubles) live in constant-cached global loads.
 #include <cuda_runtime.h>
+#include <curand_kernel.h>
 #include <stdio.h>
 #include <math.h>
 #include "../../include/argus_b200.h"
@@ -255,6 +256,79 @@ __global__ void __launch_bounds__(256) k_dlt_fused(const double *__restrict__ pt
     err[(int64_t)track * N + frame] = e;
 }
 
+// Bootstrap confidence intervals of the triangulated points (bootstrapXYZs, /root/reference/argus_gui/tools.py:448-544, the
+// 250-iteration loop at :513-527): every iteration perturbs the pixels of a (frame, track) with N(0, sigma^2),
+// sigma = rmse * sqrt(2) / (finite pixel coordinates / 2), re-triangulates, and the sample standard deviation (ddof = 1,
+// NaN results ignored) over the iterations is returned.  One thread per (frame, track) runs all iterations (Welford).
+// noise != nullptr: explicit standard-normal numbers in the reference's draw order [track][iteration][frame][2m] (exact
+// parity tests); otherwise Philox (curand) seeded per thread.
+__global__ void __launch_bounds__(128) k_dlt_bootstrap(const double *__restrict__ pts, int64_t N, int m, int k, DltCams cams,
+                                                       const double *__restrict__ rmses, int bs_iter, const double *__restrict__ noise,
+                                                       unsigned long long seed, double *__restrict__ sd)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * k) return;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const int64_t frame = t / k; const int track = (int)(t % k);
+    const double *row = pts + t * 2 * m;
+    int nfin = 0;
+    for (int q = 0; q < 2 * m; ++q) nfin += isfinite(row[q]) ? 1 : 0;
+    const double sigma = rmses[frame * k + track] * 1.4142135623730951 / (0.5 * (double)nfin);
+    curandStatePhilox4_32_10_t st;
+    if (!noise) curand_init(seed, (unsigned long long)t, 0ull, &st);
+    double mean[3] = {0, 0, 0}, m2[3] = {0, 0, 0}; int cnt[3] = {0, 0, 0};
+    for (int it = 0; it < bs_iter; ++it) {
+        double M[6] = {0, 0, 0, 0, 0, 0}, r[3] = {0, 0, 0};
+        int nvis = 0, lj = -1; float lv = 0.f;
+        const double *nz = noise ? noise + (((int64_t)track * bs_iter + it) * N + frame) * 2 * m : nullptr;
+        for (int j = 0; j < m; ++j) {
+            double n0, n1;
+            if (nz) { n0 = nz[2 * j]; n1 = nz[2 * j + 1]; }
+            else { const double2 g = curand_normal2_double(&st); n0 = g.x; n1 = g.y; }
+            const double pu = n0 * sigma + row[2 * j], pv = n1 * sigma + row[2 * j + 1];
+            if (isnan(pu) || isnan(pv)) continue;
+            float fu, fv;
+            undistort_f32(pu, pv, cams.prof + 8 * j, fu, fv);
+            const double *L = cams.dlt + 11 * j;
+            const double du = (double)fu;
+            ne_add(du * L[8] - L[0], du * L[9] - L[1], du * L[10] - L[2], L[3] - du, M, r);
+            lv = fv; lj = j; ++nvis;
+        }
+        if (nvis < 2) continue;
+        {
+            const double *L = cams.dlt + 11 * lj;
+            const double dv = (double)lv;
+            ne_add(dv * L[8] - L[4], dv * L[9] - L[5], dv * L[10] - L[6], L[7] - dv, M, r);
+        }
+        const double l00 = sqrt(M[0]);
+        const double l10 = M[1] / l00, l20 = M[2] / l00;
+        const double l11 = sqrt(M[3] - l10 * l10);
+        const double l21 = (M[4] - l20 * l10) / l11;
+        const double l22 = sqrt(M[5] - l20 * l20 - l21 * l21);
+        const double y0 = r[0] / l00;
+        const double y1 = (r[1] - l10 * y0) / l11;
+        const double y2 = (r[2] - l20 * y0 - l21 * y1) / l22;
+        double X[3];
+        X[2] = y2 / l22;
+        X[1] = (y1 - l21 * X[2]) / l11;
+        X[0] = (y0 - l10 * X[1] - l20 * X[2]) / l00;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            if (X[q] == 0.0 || isnan(X[q])) continue;           // zeros are NaN in the reference (tools.py:336) and nanstd skips them
+            cnt[q] += 1;
+            const double d = X[q] - mean[q];
+            mean[q] += d / (double)cnt[q];
+            m2[q] += d * (X[q] - mean[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        double v = (cnt[q] > 1) ? sqrt(m2[q] / (double)(cnt[q] - 1)) : nan;
+        if (v == 0.0) v = nan;
+        sd[3 * t + q] = v;
+    }
+}
+
 int launch_tri(const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt, double *d_xyz, int flags, cudaStream_t s)
 {
     const int64_t T = N * k;
@@ -383,6 +457,32 @@ int argus_dlt_reconstruct(const double *pts, int64_t N, int m, int k, const doub
     if (rc) return rc;
     DLT_CUDA_CHECK(cudaMemcpy(xyz, d_xyz, (size_t)N * 3 * k * sizeof(double), cudaMemcpyDeviceToHost));
     DLT_CUDA_CHECK(cudaMemcpy(err, d_err, (size_t)N * k * sizeof(double), cudaMemcpyDeviceToHost));
+    return ARGUS_OK;
+}
+
+int argus_dlt_bootstrap(const double *pts, int64_t N, int m, int k, const double *prof, const double *dlt, const double *rmses, int bs_iter,
+                        const double *noise, uint64_t seed, double *sd)
+{
+    if (!pts || !prof || !dlt || !rmses || !sd || m < 1 || m > kMaxCams || k < 1 || N < 0 || bs_iter < 1) return ARGUS_E_ARG;
+    if (!have_device()) return ARGUS_E_CUDA;
+    if (N == 0) return ARGUS_OK;
+    Scratch sc; double *d_pts, *d_prof, *d_dlt, *d_rm, *d_sd, *d_noise = nullptr;
+    const size_t npx = (size_t)N * 2 * m * k;
+    DLT_CUDA_CHECK(sc.alloc(&d_pts, npx)); DLT_CUDA_CHECK(sc.alloc(&d_prof, (size_t)m * 8)); DLT_CUDA_CHECK(sc.alloc(&d_dlt, (size_t)m * 11));
+    DLT_CUDA_CHECK(sc.alloc(&d_rm, (size_t)N * k)); DLT_CUDA_CHECK(sc.alloc(&d_sd, (size_t)N * 3 * k));
+    DLT_CUDA_CHECK(cudaMemcpy(d_pts, pts, npx * sizeof(double), cudaMemcpyHostToDevice));
+    DLT_CUDA_CHECK(cudaMemcpy(d_prof, prof, (size_t)m * 8 * sizeof(double), cudaMemcpyHostToDevice));
+    DLT_CUDA_CHECK(cudaMemcpy(d_dlt, dlt, (size_t)m * 11 * sizeof(double), cudaMemcpyHostToDevice));
+    DLT_CUDA_CHECK(cudaMemcpy(d_rm, rmses, (size_t)N * k * sizeof(double), cudaMemcpyHostToDevice));
+    if (noise) {
+        DLT_CUDA_CHECK(sc.alloc(&d_noise, npx * (size_t)bs_iter));
+        DLT_CUDA_CHECK(cudaMemcpy(d_noise, noise, npx * (size_t)bs_iter * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    DltCams cams{d_prof, d_dlt};
+    const int64_t T = N * k;
+    k_dlt_bootstrap<<<(unsigned)((T + 127) / 128), 128>>>(d_pts, N, m, k, cams, d_rm, bs_iter, d_noise, (unsigned long long)seed, d_sd);
+    DLT_CUDA_CHECK(cudaGetLastError());
+    DLT_CUDA_CHECK(cudaMemcpy(sd, d_sd, (size_t)N * 3 * k * sizeof(double), cudaMemcpyDeviceToHost));
     return ARGUS_OK;
 }
 

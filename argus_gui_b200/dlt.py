@@ -71,3 +71,22 @@ def undistort(pts, prof8):
     out = np.empty((pts.shape[0], 2), dtype=np.float32)
     _lib.check(lib.argus_undistort_points(_ptr(pts), pts.shape[0], _ptr(prof8), _ptr(out)), "argus_undistort_points")
     return out
+
+
+def bootstrap_sd(pts, rmses, prof, dlt, bs_iter=250, noise=None, seed=0):
+    """Sample standard deviation (ddof = 1) of ``bs_iter`` perturbed re-triangulations per (frame, track):
+    pts N x 2mk, rmses N x k -> N x 3k (argus_dlt_bootstrap).  ``noise``: optional explicit standard-normal numbers
+    of shape (k, bs_iter, N, 2m)."""
+    lib = _lib.load()
+    pts, prof, dlt, m, k = _prep(pts, prof, dlt)
+    N = pts.shape[0]
+    rmses = np.ascontiguousarray(rmses, dtype=np.float64).reshape(N, k)
+    if noise is not None:
+        noise = np.ascontiguousarray(noise, dtype=np.float64)
+        if noise.shape != (k, bs_iter, N, 2 * m):
+            raise ValueError("noise must have shape (tracks, bs_iter, frames, 2 * cameras)")
+    sd = np.empty((N, 3 * k))
+    rc = lib.argus_dlt_bootstrap(_ptr(pts), N, m, k, _ptr(prof), _ptr(dlt), _ptr(rmses), int(bs_iter),
+                                 _ptr(noise) if noise is not None else None, ctypes.c_uint64(int(seed)), _ptr(sd))
+    _lib.check(rc, "argus_dlt_bootstrap")
+    return sd

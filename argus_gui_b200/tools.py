@@ -13,7 +13,7 @@ import numpy as np
 from . import dlt as _dlt
 
 __all__ = ["ArgusError", "dlt_inverse", "reconstruct_uv", "undistort_pts", "normalize", "solve_dlt", "uv_to_xyz",
-           "get_repo_errors", "uv_to_xyz_and_errors"]
+           "get_repo_errors", "uv_to_xyz_and_errors", "bootstrapXYZs"]
 
 
 class Error(Exception):
@@ -133,3 +133,70 @@ def uv_to_xyz_and_errors(pts, profs, dlt):
     every track slice and get_repo_errors on the result, with one host<->device round trip."""
     pts = np.asarray(pts, dtype=np.float64)
     return _dlt.reconstruct(pts, profs, np.asarray(dlt, dtype=np.float64))
+
+
+def bootstrapXYZs(pts, rmses, prof, dlt, bsIter=250, display_progress=False, subframeinterp=True, seed=None, noise=None):
+    """95 % confidence intervals of the triangulated points by bootstrapping (tools.py:448-544): same arguments and return
+    values (CIs N x 3k, spline weights, tolerances) as the reference.  The ``bsIter`` perturbed re-triangulations per track run
+    as ONE kernel (argus_dlt_bootstrap: on-device Philox noise, Welford standard deviation); the optional sub-frame offset
+    search (21 candidate offsets per camera, tools.py:455-510) keeps the reference's host logic with the GPU
+    triangulation / reprojection calls inside.  ``seed`` / ``noise`` (extension): reproducible device noise, or explicit
+    standard-normal numbers of shape (tracks, bsIter, frames, 2 * cameras) in the reference's draw order."""
+    from scipy import interpolate
+    numcams = len(prof)
+    numpts = int(pts.shape[1] / (2 * numcams))
+    dlt = np.asarray(dlt, dtype=np.float64)
+    if subframeinterp and numcams > 2:
+        print('Checking subframe interpolation')
+        redormse = False
+        step = list(np.linspace(-1, 1, 21))
+        for c in range(1, numcams):
+            steprmses = np.zeros((21, numpts)) * np.nan
+            ocam = 1 if c > 1 else 2
+            for k in range(numpts):
+                base = k * 2 * numcams
+                c1pts = pts[:, base:base + 2]
+                cpts_clean = pts[:, base + c * 2:base + c * 2 + 2]
+                ocpts = pts[:, base + ocam * 2:base + ocam * 2 + 2]
+                fin = np.where(np.isfinite(cpts_clean[:, 0]))[0]
+                if not np.any(fin):
+                    continue
+                sprof = np.vstack([prof[0], prof[ocam], prof[c]])
+                sdlt = np.vstack([dlt[0], dlt[ocam], dlt[c]])
+                f = interpolate.interp1d(fin, cpts_clean[fin], axis=0, kind='linear', fill_value='extrapolate')
+                for i, s in enumerate(step):
+                    cpts = cpts_clean.copy()
+                    cpts[fin] = f(fin + s)
+                    spts = np.hstack([c1pts, ocpts, cpts])
+                    spts = np.ascontiguousarray(spts[np.where(np.sum(np.isfinite(spts), axis=1) > 4)[0]])
+                    sxyzs, srms = _dlt.reconstruct(spts, sprof, sdlt)
+                    with np.errstate(all='ignore'):
+                        import warnings
+                        with warnings.catch_warnings():
+                            warnings.simplefilter('ignore', category=RuntimeWarning)
+                            steprmses[i, k] = np.nanmedian(srms)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore', category=RuntimeWarning)
+                poff = step[np.nanargmin(np.nanmedian(steprmses, axis=1))]
+            if poff != 0:
+                redormse = True
+                print('partial offset of {} frames found for cam {}, remaking pts'.format(poff, c + 1))
+                for k in range(numpts):
+                    sl = slice(k * 2 * numcams + c * 2, k * 2 * numcams + c * 2 + 2)
+                    cpts = pts[:, sl]
+                    # NOTE: the reference indexes with the `fin` of the LAST track's clean points here (tools.py:497-498); kept
+                    cpts[fin] = interpolate.interp1d(fin, cpts[fin], axis=0, kind='linear', fill_value='extrapolate')(fin + poff)
+                    pts[:, sl] = cpts
+        if redormse:
+            xyzs, err = _dlt.reconstruct(np.ascontiguousarray(pts), prof, dlt)
+            rmses = err.T
+    if seed is None and noise is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+    ret = _dlt.bootstrap_sd(np.ascontiguousarray(pts), np.asarray(rmses, dtype=np.float64)[:, :numpts], prof, dlt, bs_iter=bsIter, noise=noise, seed=seed or 0)
+    import warnings
+    with warnings.catch_warnings(), np.errstate(all='ignore'):
+        warnings.simplefilter('ignore', category=RuntimeWarning)
+        weights = 1 / (ret / np.tile(np.nanmin(ret, axis=0), (ret.shape[0], 1)))
+        tols = np.nansum(np.multiply(weights, np.power(ret, 2)), axis=0)
+    return ret * 1.96, weights, tols

@@ -218,6 +218,14 @@ def bench_dlt(torch, device, stream, steps, warmup, rank, world, hbm_peak):
                                      "frac": err_bytes / (err_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
            "e2e": {"value": npts / e2e_s, "unit": "points/s", "h2d_bytes_per_step": int(d["pts"].nbytes), "d2h_bytes_per_step": int(xyz.nbytes + err.nbytes)},
            "gpu_launches": 3 * steps}
+    # bootstrap confidence intervals (bootstrapXYZs: 250 perturbed re-triangulations per point), host API, 100k frames
+    nb = 100_000
+    rm = np.ascontiguousarray(np.nan_to_num(err[:, :nb].T, nan=1.0))
+    t0 = time.perf_counter()
+    sd = dlt_host.bootstrap_sd(np.ascontiguousarray(d["pts"][:nb]), rm, d["prof"], d["dlt"], bs_iter=250, seed=1)
+    bt = time.perf_counter() - t0
+    out["bootstrap"] = {"points_per_sec": nb * k / bt, "retriangulations_per_sec": nb * k * 250 / bt, "bs_iter": 250,
+                        "sample": "%d frames x %d tracks through argus_dlt_bootstrap (host buffers)" % (nb, k)}
     if rank == 0 and world == 1:
         from oracle import dlt_port
         ns = 1500

@@ -116,6 +116,12 @@ int  argus_dlt_reproj_error(const double *xyz, const double *pts, int64_t N, int
 /* both in one host round trip (pts copied to the device once): xyz N x 3k, err k x N */
 int  argus_dlt_reconstruct(const double *pts, int64_t N, int m, int k, const double *prof, const double *dlt,
                            double *xyz, double *err, int flags);
+/* Bootstrap standard deviations of the triangulated points (the 250-iteration loop of bootstrapXYZs, tools.py:513-530):
+ * rmses N x k, sd N x 3k (sample standard deviation, ddof = 1, over bs_iter perturbed re-triangulations).  noise: optional
+ * explicit standard-normal numbers [k][bs_iter][N][2m] (the reference's np.random.randn draw order) for exact parity tests;
+ * NULL = Philox generator on the device seeded with `seed`. */
+int  argus_dlt_bootstrap(const double *pts, int64_t N, int m, int k, const double *prof, const double *dlt, const double *rmses,
+                         int bs_iter, const double *noise, uint64_t seed, double *sd);
 /* pts: N x 2 pixels -> out: N x 2 undistorted pixels, float32-faithful to cv2.undistortPoints(P=K) (tools.py:129-148) */
 int  argus_undistort_points(const double *pts, int64_t N, const double *prof8, float *out);
 

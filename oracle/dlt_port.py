@@ -12,6 +12,8 @@ Restates, vectorised over frames but with the same arithmetic per frame:
                       visible camera; rows beyond n+1 stay zero.  numpy lstsq (SVD, min-norm) per frame.
   reconstruct_uv      /root/reference/argus_gui/tools.py:64-76
   get_repo_errors     /root/reference/argus_gui/tools.py:360-423
+  bootstrap_sd        /root/reference/argus_gui/tools.py:513-530  (the perturb / re-triangulate / nanstd loop of bootstrapXYZs,
+                      with the standard-normal numbers passed in explicitly instead of drawn from np.random)
 
 Pinned against the reference itself: tests/golden/dlt_golden.npz was produced by importing the reference's
 tools.py (tests/golden/make_dlt_golden.py) and tests/test_oracle_dlt.py checks this file against it.
@@ -111,3 +113,28 @@ def get_repo_errors(xyzs, pts, prof, dlt):
                     out[t, i] = np.sqrt(np.float64(eps) / float(2 * n - 3))
     out[out == 0] = np.nan
     return out
+
+
+def bootstrap_sd(pts, rmses, prof, dlt, noise):
+    """pts N x 2mk, rmses N x k, noise (k, bsIter, N, 2m) -> N x 3k standard deviations (ddof = 1, NaN-aware), exactly the
+    loop of bootstrapXYZs (tools.py:513-530) for given random numbers."""
+    import warnings
+    pts = np.asarray(pts, dtype=np.float64)
+    m = len(prof)
+    N = pts.shape[0]
+    k = pts.shape[1] // (2 * m)
+    bs = noise.shape[1]
+    ret = np.zeros((N, 3 * k))
+    with np.errstate(all="ignore"), warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=RuntimeWarning)
+        for t in range(k):
+            track = pts[:, t * 2 * m:(t + 1) * 2 * m]
+            camSum = np.nansum(np.isfinite(track), axis=1) / 2
+            xyzBS = np.full((N, 3, bs), np.nan)
+            for j in range(bs):
+                per = noise[t, j] * np.tile((rmses[:, t] * 2 ** 0.5 / camSum).reshape((-1, 1)), (1, 2 * m)) + track
+                xyzBS[:, :, j] = uv_to_xyz(per, prof, dlt)
+            sd = np.nanstd(xyzBS, axis=2, ddof=1)
+            sd[sd == 0] = np.nan
+            ret[:, t * 3:(t + 1) * 3] = sd
+    return ret

@@ -95,3 +95,51 @@ def test_full_size_c2_properties():
         okk = ~np.isnan(xo)
         xs = xyz[sidx][:, 3 * t:3 * t + 3]
         assert np.array_equal(np.isnan(xs), np.isnan(xo)) and np.abs(xs[okk] - xo[okk]).max() <= 1e-9 * np.abs(xo[okk]).max()
+
+
+def _boot_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bootstrap_golden.npz"))
+
+
+def test_bootstrap_exact_noise_golden():
+    """bootstrapXYZs (tools.py:448-544) with the reference's own random numbers: CIs, weights and tolerances."""
+    from argus_gui_b200 import tools
+    g = _boot_golden()
+    ci, w, tol = tools.bootstrapXYZs(g["pts"].copy(), g["rmses"], list(g["prof"]), g["dlt"], bsIter=g["noise"].shape[1], subframeinterp=False,
+                                     noise=g["noise"])
+    assert np.array_equal(np.isnan(ci), np.isnan(g["ci"]))
+    ok = ~np.isnan(g["ci"])
+    assert np.abs(ci[ok] - g["ci"][ok]).max() <= 1e-8 * np.abs(g["ci"][ok]).max()      # standard deviations: 1e-8 relative
+    okw = ~np.isnan(g["w"])
+    assert np.array_equal(np.isnan(w), np.isnan(g["w"])) and np.abs(w[okw] - g["w"][okw]).max() <= 1e-7 * np.abs(g["w"][okw]).max()
+    assert np.abs(tol - g["tol"]).max() <= 1e-7 * np.abs(g["tol"]).max()
+
+
+def test_bootstrap_subframe_interpolation_golden():
+    """The sub-frame offset search (tools.py:455-510) finds the same offset, rewrites pts the same way, same CIs."""
+    from argus_gui_b200 import tools
+    g = _boot_golden()
+    pts = g["pts2_in"].copy()
+    ci, w, tol = tools.bootstrapXYZs(pts, g["rm2"], list(g["prof"]), g["dlt"], bsIter=g["noise2"].shape[1], subframeinterp=True, noise=g["noise2"])
+    assert np.abs(pts - g["pts2_out"]).max() < 1e-9                 # in-place rewrite of the shifted camera
+    ok = ~np.isnan(g["ci2"])
+    assert np.array_equal(np.isnan(ci), np.isnan(g["ci2"]))
+    assert np.abs(ci[ok] - g["ci2"][ok]).max() <= 1e-6 * np.abs(g["ci2"][ok]).max()
+
+
+def test_bootstrap_device_rng_statistics():
+    """On-device Philox noise: the standard deviations agree statistically with the explicit-noise estimate."""
+    g = _boot_golden()
+    rng = np.random.default_rng(0)
+    N, m2 = g["pts"].shape[0], g["pts"].shape[1] // 2
+    bs = 4000
+    a = dlt.bootstrap_sd(g["pts"], g["rmses"], g["prof"], g["dlt"], bs_iter=bs, seed=1234)
+    b = dlt.bootstrap_sd(g["pts"], g["rmses"], g["prof"], g["dlt"], bs_iter=bs, seed=99)
+    noise = rng.standard_normal((2, 400, N, 8))
+    c = dlt.bootstrap_sd(g["pts"], g["rmses"], g["prof"], g["dlt"], bs_iter=400, noise=noise)
+    ok = ~np.isnan(a) & ~np.isnan(c)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.median(np.abs(a[ok] / b[ok] - 1)) < 0.03              # two seeds, 4000 draws each: ~1.6 % standard error
+    assert np.median(np.abs(a[ok] / c[ok] - 1)) < 0.08              # vs 400 explicit numpy draws: ~3.5 %
+    assert not np.array_equal(a, b)

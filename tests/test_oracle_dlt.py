@@ -50,3 +50,13 @@ def test_edge_rows(golden_dlt):
     assert np.isnan(xyz[0, :3]).all()        # nothing visible
     assert np.isnan(xyz[1, :3]).all()        # a single camera
     assert not np.isnan(xyz[2, :3]).any()    # exactly two cameras
+
+
+def test_bootstrap_sd_golden():
+    """oracle restatement of the bootstrap loop (tools.py:513-530) against the reference run with the same random numbers"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bootstrap_golden.npz"))
+    ci = 1.96 * dlt_port.bootstrap_sd(g["pts"], g["rmses"], g["prof"], g["dlt"], g["noise"])
+    assert np.array_equal(np.isnan(ci), np.isnan(g["ci"]))
+    ok = ~np.isnan(g["ci"])
+    assert np.abs(ci[ok] - g["ci"][ok]).max() <= 1e-12 * np.abs(g["ci"][ok]).max()
