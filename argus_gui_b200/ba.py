@@ -151,12 +151,19 @@ class BundleAdjuster:
 
 
 def solve_motstr(vmask, p, rot0, x, nccalib=0, ncdist=0, itmax=DEFAULT_ITMAX, opts=DEFAULT_OPTS, ncon=0, mcon=0,
-                 verbose=0, compat=True):
-    """One-shot host-pointer call ``argus_ba_motstr_kdrts``.  Returns (p_new, info[10], retval)."""
+                 verbose=0, compat=True, inplace=False):
+    """One-shot host-pointer call ``argus_ba_motstr_kdrts``.  Returns (p_new, info[10], retval).
+    ``inplace=True`` updates the caller's contiguous float64 ``p`` like the reference's C call does (sba_levmar.c:503: p is
+    in/out) instead of working on a copy - with a pinned ``p`` both transfers then run at full PCIe speed."""
     lib = _lib.load()
     vmask = _as_mask(vmask)
     n, m = vmask.shape
-    p = np.array(p, dtype=np.float64, copy=True).ravel()
+    if inplace:
+        if not (isinstance(p, np.ndarray) and p.dtype == np.float64 and p.flags.c_contiguous and p.flags.writeable):
+            raise ValueError("inplace=True needs a writeable C-contiguous float64 array")
+        p = p.reshape(-1)
+    else:
+        p = np.array(p, dtype=np.float64, copy=True).ravel()
     rot0 = np.ascontiguousarray(rot0, dtype=np.float64).ravel()
     x = np.ascontiguousarray(x, dtype=np.float64).ravel()
     opts = np.ascontiguousarray(opts, dtype=np.float64)

@@ -42,6 +42,89 @@ struct LinTileOut {
 };
 
 // ---- static index construction (once per upload; visibility never changes during a solve) ----
+// The visibility mask arrives as the reference's n x m byte matrix (sba_levmar.c:639-650 turns it into a CRS on the host);
+// here the CSR (obs_ptr, obs_cam) and the per-point camera bit masks are built on the device from the raw bytes:
+//   k_index_count : per point bit mask + per-block observation totals   (kIdxPts points per block)
+//   k_index_scan  : exclusive scan of the block totals (one CTA)
+//   k_index_fill  : obs_ptr of every point, obs_cam of every observation
+constexpr int kIdxPer = 8;                    // points per thread
+constexpr int kIdxPts = 256 * kIdxPer;        // points per block
+
+__global__ void __launch_bounds__(256) k_index_count(int64_t n, int m, const uint8_t *__restrict__ vmask, uint64_t *__restrict__ pt_mask,
+                                                     int32_t *__restrict__ btot)
+{
+    __shared__ int s_w[8];
+    const int64_t base = (int64_t)blockIdx.x * kIdxPts + (int64_t)threadIdx.x * kIdxPer;
+    int cnt = 0;
+    for (int q = 0; q < kIdxPer; ++q) {
+        const int64_t i = base + q;
+        if (i >= n) break;
+        const uint8_t *row = vmask + (size_t)i * m;
+        uint64_t mk = 0;
+        for (int j = 0; j < m; ++j) if (row[j]) mk |= 1ull << j;
+        pt_mask[i] = mk;
+        cnt += __popcll(mk);
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_w[w]; btot[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(1024) k_index_scan(int nb, int32_t *__restrict__ btot /* in: totals, out: exclusive offsets; [nb] = grand total */)
+{
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        const int v = (b < nb) ? btot[b] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += u; }
+        if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s_w[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += u; }
+            s_w[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int wofs = (threadIdx.x >> 5) ? s_w[(threadIdx.x >> 5) - 1] : 0;
+        const int carry = s_carry;
+        if (b < nb) btot[b] = carry + wofs + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + wofs + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) btot[nb] = s_carry;
+}
+
+__global__ void __launch_bounds__(256) k_index_fill(int64_t n, const uint64_t *__restrict__ pt_mask, const int32_t *__restrict__ btot,
+                                                    int32_t *__restrict__ obs_ptr, uint8_t *__restrict__ obs_cam)
+{
+    __shared__ int s_w[8];
+    const int64_t base = (int64_t)blockIdx.x * kIdxPts + (int64_t)threadIdx.x * kIdxPer;
+    uint64_t mk[kIdxPer];
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < kIdxPer; ++q) { mk[q] = (base + q < n) ? pt_mask[base + q] : 0ull; cnt += __popcll(mk[q]); }
+    int inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if ((threadIdx.x & 31) >= o) inc += u; }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    int k = btot[blockIdx.x] + inc - cnt;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) k += s_w[w];
+#pragma unroll
+    for (int q = 0; q < kIdxPer; ++q) {
+        if (base + q >= n) break;
+        obs_ptr[base + q] = k;
+        uint64_t b = mk[q];
+        while (b) { obs_cam[k++] = (uint8_t)(__ffsll((long long)b) - 1); b &= b - 1; }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) obs_ptr[n] = k;     // last thread of the last block ends at the grand total
+}
+
 // pt_rank[i][cam] = position of cam in point i's observation list (rows pre-filled with 0xFF; fixed points stay 0xFF)
 __global__ void k_build_point_index(int64_t n, int64_t ncon, int mp, const int32_t *__restrict__ obs_ptr, const uint8_t *__restrict__ obs_cam,
                                     uint8_t *__restrict__ pt_rank)

@@ -94,7 +94,7 @@ struct argus_ba_ctx {
     int gen = 3;
     int schur_nw_pref = 12;
     DevBuf<int32_t> tile_pt, tile_o; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
-    DevBuf<uint8_t> obs_lpt, corder, pt_rank; int rank_mp = 16;
+    DevBuf<uint8_t> obs_lpt, corder, pt_rank, vmask_dev; DevBuf<int32_t> idx_btot; int rank_mp = 16;
     DevBuf<uint8_t> cam_fix; bool cam_fix_on = false; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect, cholwork;
     int grid_lin = 1; size_t lin_smem = 0;
     unsigned long long *lin_dbg = nullptr;
@@ -428,28 +428,18 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     const bool timing = getenv("ARGUS_TIMING") != nullptr;
     auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = tnow();
-    // visibility index (sba_levmar.c:639-650 builds the same CRS; here: point-major CSR + per-point camera bit mask)
-    std::vector<int32_t> optr((size_t)n + 1);
-    std::vector<uint64_t> mask((size_t)n);
+    // visibility: the host only counts (observations per point, for the sizes and the tile plan); the CSR and the per-point
+    // camera bit masks are built on the device from the raw mask bytes (k_index_*; sba_levmar.c:639-650 builds its CRS on the host)
+    std::vector<uint8_t> cnt((size_t)n);
     parallel_for(n, [&](int64_t lo, int64_t hi) {
         for (int64_t i = lo; i < hi; ++i) {
             const char *row = vmask + i * m;
-            uint64_t mk = 0;
-            for (int j = 0; j < m; ++j) if (row[j]) mk |= 1ull << j;
-            mask[i] = mk;
+            int k = 0;
+            for (int j = 0; j < m; ++j) k += row[j] != 0;
+            cnt[i] = (uint8_t)k;
         }
     });
-    int64_t nobs = 0;
-    for (int64_t i = 0; i < n; ++i) { optr[i] = (int32_t)nobs; nobs += __builtin_popcountll(mask[i]); if (nobs > 0x7fffffffLL) return ARGUS_E_ARG; }
-    optr[n] = (int32_t)nobs;
-    std::vector<uint8_t> ocam((size_t)nobs);
-    parallel_for(n, [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
-            uint64_t mk = mask[i]; int32_t k = optr[i];
-            while (mk) { ocam[k++] = (uint8_t)__builtin_ctzll(mk); mk &= mk - 1; }
-        }
-    });
-    c->n = n; c->ncon = ncon; c->m = m; c->mcon = mcon; c->nobs = nobs; c->nfix_k = nccalib; c->nfix_d = ncdist; c->cam_fix_on = false;
+    c->n = n; c->ncon = ncon; c->m = m; c->mcon = mcon; c->nfix_k = nccalib; c->nfix_d = ncdist; c->cam_fix_on = false;
     const int mf = m - mcon, N = 16 * mf;
     c->npairs = mf * (mf + 1) / 2;
     c->grid_pts128 = (int)std::min<int64_t>((n + 127) / 128, (int64_t)c->sms * 8); if (c->grid_pts128 < 1) c->grid_pts128 = 1;
@@ -463,22 +453,23 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         c->chunk_pts = (n + want - 1) / want; if (c->chunk_pts < 1) c->chunk_pts = 1;
     }
     // ---- generation-2 plans: point tiles (<= 32 points, <= tile_obs observations) and the block -> (group, warp, slot) map ----
-    std::vector<int32_t> tiles;
+    std::vector<int32_t> tiles, tile_o;
     c->tile_obs = 256;
+    int64_t nobs = 0;
     {
         int64_t i = 0;
         while (i < n) {
-            tiles.push_back((int32_t)i);
-            int64_t e = i; int32_t o0 = optr[i];
-            while (e < n && e - i < kTilePts && optr[e + 1] - o0 <= c->tile_obs) ++e;
-            if (e == i) ++e;
-            i = e;
+            tiles.push_back((int32_t)i); tile_o.push_back((int32_t)nobs);
+            int64_t e = i; int acc = 0;
+            while (e < n && e - i < kTilePts && acc + cnt[e] <= c->tile_obs) acc += cnt[e++];
+            if (e == i) acc = cnt[e++];
+            i = e; nobs += acc;
+            if (nobs > 0x7fffffffLL) return ARGUS_E_ARG;
         }
-        tiles.push_back((int32_t)n);
+        tiles.push_back((int32_t)n); tile_o.push_back((int32_t)nobs);
         c->ntiles = (int)tiles.size() - 1;
     }
-    std::vector<int32_t> tile_o(tiles.size());
-    for (size_t q = 0; q < tiles.size(); ++q) tile_o[q] = optr[tiles[q]];
+    c->nobs = nobs;
     {
         const int cand[4] = {1, 3, 5, 9};
         int NB = 9, NW = 8;
@@ -524,6 +515,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     PLAN_CHECK(c->obs_lpt.ensure((size_t)nobs)); PLAN_CHECK(c->corder.ensure((size_t)nobs)); PLAN_CHECK(c->cstart.ensure((size_t)c->ntiles * (m + 1)));
     PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1024);
     PLAN_CHECK(c->pt_rank.ensure((size_t)n * c->rank_mp));
+    PLAN_ENS(c->vmask_dev, n * m); PLAN_ENS(c->idx_btot, (n + kIdxPts - 1) / kIdxPts + 1);
     PLAN_ENS(c->obs_ptr, n + 1); PLAN_ENS(c->obs_cam, nobs); PLAN_ENS(c->obs_uv, nobs); PLAN_ENS(c->pt_mask, n);
     PLAN_ENS(c->rot0, 4 * m); PLAN_ENS(c->cam, 16 * m); PLAN_ENS(c->cam_new, 16 * m); PLAN_ENS(c->cam0, 16 * m);
     PLAN_ENS(c->pts, 3 * n); PLAN_ENS(c->pts_new, 3 * n); PLAN_ENS(c->pts0, 3 * n);
@@ -561,9 +553,15 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_o.p, tile_o.data(), tile_o.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_jk.p, hjk.data(), hjk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_pair.p, hpair.data(), hpair.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_ptr.p, optr.data(), (n + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_cam.p, ocam.data(), nobs * sizeof(uint8_t), cudaMemcpyHostToDevice, s));
-    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pt_mask.p, mask.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->vmask_dev.p, vmask, (size_t)n * m, cudaMemcpyHostToDevice, s));
+    if (n > 0) {
+        const int nb = (int)((n + kIdxPts - 1) / kIdxPts);
+        k_index_count<<<nb, 256, 0, s>>>(n, m, c->vmask_dev.p, c->pt_mask.p, c->idx_btot.p);
+        k_index_scan<<<1, 1024, 0, s>>>(nb, c->idx_btot.p);
+        k_index_fill<<<nb, 256, 0, s>>>(n, c->pt_mask.p, c->idx_btot.p, c->obs_ptr.p, c->obs_cam.p);
+    } else {
+        ARGUS_CUDA_CHECK(cudaMemsetAsync(c->obs_ptr.p, 0, sizeof(int32_t), s));
+    }
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_uv.p, x, nobs * sizeof(double2), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->rot0.p, rot0, 4 * m * sizeof(double), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cam0.p, p, 16 * m * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -578,7 +576,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         ARGUS_CUDA_CHECK(cudaGetLastError());
     }
     ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));      // host staging vectors go out of scope
-    c->h2d_bytes += (n + 1) * sizeof(int32_t) + nobs * (sizeof(uint8_t) + sizeof(double2)) + n * sizeof(uint64_t) + (4 + 16) * m * sizeof(double) + 3 * n * sizeof(double) +
+    c->h2d_bytes += (size_t)n * m + nobs * sizeof(double2) + (4 + 16) * m * sizeof(double) + 3 * n * sizeof(double) +
                     2 * tiles.size() * sizeof(int32_t);
     if (timing) fprintf(stderr, "argus_b200 upload: host index build %.1f ms, device alloc %.1f ms, H2D %.1f ms\n", 1e3 * (t_index - t_start), 1e3 * (t_alloc - t_index), 1e3 * (tnow() - t_alloc));
     return argus_ba_reset(c);
@@ -813,16 +811,26 @@ int argus_ba_motstr_kdrts(int64_t n, int64_t ncon, int m, int mcon, const char *
                           const double *x, int nccalib, int ncdist, int itmax, int verbose, const double opts[5], double info[10],
                           int flags)
 {
+    const bool timing = getenv("ARGUS_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = tnow();
     argus_ba_ctx *c = nullptr;
     int rc = argus_ba_create(&c, 0, nullptr);
     if (rc) return rc;
+    const double t1 = tnow();
     rc = argus_ba_upload(c, n, ncon, m, mcon, vmask, p, rot0, x, nccalib, ncdist);
+    const double t2 = tnow();
+    double t3 = t2, t4 = t2;
     int ret = rc;
     if (rc == ARGUS_OK) {
         ret = argus_ba_solve(c, itmax, verbose, opts, info, flags);
+        t3 = tnow();
         if (ret >= 0 || ret == ARGUS_E_SBA) { rc = argus_ba_download(c, p); if (rc) ret = rc; }
+        t4 = tnow();
     }
     argus_ba_destroy(c);
+    if (timing) fprintf(stderr, "argus_b200 one-shot: create %.1f ms, upload %.1f ms, solve %.1f ms, download %.1f ms, destroy %.1f ms\n",
+                        1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3), 1e3 * (tnow() - t4));
     return ret;
 }
 

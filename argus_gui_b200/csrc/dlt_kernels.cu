@@ -162,21 +162,22 @@ __device__ __forceinline__ double reproj_one(const double *__restrict__ row, con
 }
 
 // xyz: N x 3k, pts: N x 2mk, err: k x N
+// (ldN = row length of err: the whole job's frame count when a chunk of frames is processed)
 __global__ void __launch_bounds__(256) k_dlt_reproj(const double *__restrict__ xyz, const double *__restrict__ pts, int64_t N, int m, int k,
-                                                    DltCams cams, double *__restrict__ err)
+                                                    DltCams cams, double *__restrict__ err, int64_t ldN)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N * k) return;
     const int64_t frame = t / k; const int track = (int)(t % k);
     const double X[3] = {xyz[3 * t], xyz[3 * t + 1], xyz[3 * t + 2]};
-    err[(int64_t)track * N + frame] = reproj_one(pts + t * 2 * m, X, m, cams);
+    err[(int64_t)track * ldN + frame] = reproj_one(pts + t * 2 * m, X, m, cams);
 }
 
 // Fused triangulation + reprojection error (argus_dlt_reconstruct): every pixel is undistorted once instead of twice.
 // Identical results to k_dlt_triangulate followed by k_dlt_reproj (same per-camera arithmetic in the same order).
 template <int MMAX>
 __global__ void __launch_bounds__(256) k_dlt_fused(const double *__restrict__ pts, int64_t N, int m, int k, DltCams cams,
-                                                   double *__restrict__ xyz, double *__restrict__ err, int flags)
+                                                   double *__restrict__ xyz, double *__restrict__ err, int flags, int64_t ldN)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= N * k) return;
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(256) k_dlt_fused(const double *__restrict__ pt
         if (e == 0.0) e = nan;
     }
     const int64_t frame = t / k; const int track = (int)(t % k);
-    err[(int64_t)track * N + frame] = e;
+    err[(int64_t)track * ldN + frame] = e;
 }
 
 // Bootstrap confidence intervals of the triangulated points (bootstrapXYZs, /root/reference/argus_gui/tools.py:448-544, the
@@ -338,30 +339,33 @@ int launch_tri(const double *d_pts, int64_t N, int m, int k, const double *d_pro
     DLT_CUDA_CHECK(cudaGetLastError());
     return ARGUS_OK;
 }
-int launch_err(const double *d_xyz, const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt, double *d_err, cudaStream_t s)
+int launch_err(const double *d_xyz, const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt, double *d_err, cudaStream_t s,
+               int64_t ldN = -1)
 {
+    if (ldN < 0) ldN = N;
     const int64_t T = N * k;
     if (T == 0) return ARGUS_OK;
     DltCams cams{d_prof, d_dlt};
-    k_dlt_reproj<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(d_xyz, d_pts, N, m, k, cams, d_err);
+    k_dlt_reproj<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(d_xyz, d_pts, N, m, k, cams, d_err, ldN);
     DLT_CUDA_CHECK(cudaGetLastError());
     return ARGUS_OK;
 }
 
 int launch_fused(const double *d_pts, int64_t N, int m, int k, const double *d_prof, const double *d_dlt, double *d_xyz, double *d_err,
-                 int flags, cudaStream_t s)
+                 int flags, cudaStream_t s, int64_t ldN = -1)
 {
+    if (ldN < 0) ldN = N;
     const int64_t T = N * k;
     if (T == 0) return ARGUS_OK;
     DltCams cams{d_prof, d_dlt};
     const unsigned grid = (unsigned)((T + 255) / 256);
-    if (m <= 4) k_dlt_fused<4><<<grid, 256, 0, s>>>(d_pts, N, m, k, cams, d_xyz, d_err, flags);
-    else if (m <= 8) k_dlt_fused<8><<<grid, 256, 0, s>>>(d_pts, N, m, k, cams, d_xyz, d_err, flags);
-    else if (m <= 16) k_dlt_fused<16><<<grid, 256, 0, s>>>(d_pts, N, m, k, cams, d_xyz, d_err, flags);
+    if (m <= 4) k_dlt_fused<4><<<grid, 256, 0, s>>>(d_pts, N, m, k, cams, d_xyz, d_err, flags, ldN);
+    else if (m <= 8) k_dlt_fused<8><<<grid, 256, 0, s>>>(d_pts, N, m, k, cams, d_xyz, d_err, flags, ldN);
+    else if (m <= 16) k_dlt_fused<16><<<grid, 256, 0, s>>>(d_pts, N, m, k, cams, d_xyz, d_err, flags, ldN);
     else {      // many cameras: the two-kernel path (no per-thread camera arrays)
         int rc = launch_tri(d_pts, N, m, k, d_prof, d_dlt, d_xyz, flags, s);
         if (rc) return rc;
-        return launch_err(d_xyz, d_pts, N, m, k, d_prof, d_dlt, d_err, s);
+        return launch_err(d_xyz, d_pts, N, m, k, d_prof, d_dlt, d_err, s, ldN);
     }
     DLT_CUDA_CHECK(cudaGetLastError());
     return ARGUS_OK;
@@ -382,6 +386,28 @@ struct Scratch {
     template <typename T> cudaError_t alloc(T **out, size_t cnt) { cudaError_t e = cudaMalloc(out, (cnt ? cnt : 1) * sizeof(T)); if (e == cudaSuccess) p[n++] = *out; return e; }
     ~Scratch() { for (int i = 0; i < n; ++i) cudaFree(p[i]); }
 };
+
+// Host-pointer calls move the job through the device in chunks of frames on three streams, so that the upload of chunk c+1,
+// the kernel of chunk c and the download of chunk c-1 overlap (PCIe is full duplex; the kernel is far shorter than either copy).
+struct ChunkPipe {
+    static constexpr int kStreams = 3;
+    cudaStream_t s[kStreams] = {nullptr, nullptr, nullptr};
+    cudaError_t init() { for (auto &q : s) { cudaError_t e = cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking); if (e != cudaSuccess) return e; } return cudaSuccess; }
+    ~ChunkPipe() { for (auto &q : s) if (q) { cudaStreamSynchronize(q); cudaStreamDestroy(q); } }
+    cudaError_t finish() { cudaError_t r = cudaSuccess; for (auto &q : s) { cudaError_t e = cudaStreamSynchronize(q); if (e != cudaSuccess) r = e; } return r; }
+    static int64_t chunk_frames(int64_t N, size_t bytes_per_frame) {
+        int64_t c = (int64_t)((size_t)(24u << 20) / (bytes_per_frame ? bytes_per_frame : 1));
+        if (c < 1024) c = 1024;
+        return c < N ? c : (N > 0 ? N : 1);
+    }
+};
+
+// err is k x N on both sides: a chunk of frames is a k-row strided piece
+cudaError_t copy_err_chunk(double *err, const double *d_err, int64_t N, int k, int64_t f0, int64_t nf, cudaStream_t s)
+{
+    return cudaMemcpy2DAsync(err + f0, (size_t)N * sizeof(double), d_err + f0, (size_t)N * sizeof(double), (size_t)nf * sizeof(double), (size_t)k,
+                             cudaMemcpyDeviceToHost, s);
+}
 
 }  // namespace
 
@@ -415,12 +441,22 @@ int argus_dlt_triangulate(const double *pts, int64_t N, int m, int k, const doub
     Scratch sc; double *d_pts, *d_prof, *d_dlt, *d_xyz;
     DLT_CUDA_CHECK(sc.alloc(&d_pts, (size_t)N * 2 * m * k)); DLT_CUDA_CHECK(sc.alloc(&d_prof, (size_t)m * 8));
     DLT_CUDA_CHECK(sc.alloc(&d_dlt, (size_t)m * 11)); DLT_CUDA_CHECK(sc.alloc(&d_xyz, (size_t)N * 3 * k));
-    DLT_CUDA_CHECK(cudaMemcpy(d_pts, pts, (size_t)N * 2 * m * k * sizeof(double), cudaMemcpyHostToDevice));
     DLT_CUDA_CHECK(cudaMemcpy(d_prof, prof, (size_t)m * 8 * sizeof(double), cudaMemcpyHostToDevice));
     DLT_CUDA_CHECK(cudaMemcpy(d_dlt, dlt, (size_t)m * 11 * sizeof(double), cudaMemcpyHostToDevice));
-    int rc = launch_tri(d_pts, N, m, k, d_prof, d_dlt, d_xyz, flags, 0);
-    if (rc) return rc;
-    DLT_CUDA_CHECK(cudaMemcpy(xyz, d_xyz, (size_t)N * 3 * k * sizeof(double), cudaMemcpyDeviceToHost));
+    DLT_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));      // the pipe's streams do not order against the legacy stream
+    ChunkPipe pipe; DLT_CUDA_CHECK(pipe.init());
+    const size_t wp = (size_t)2 * m * k, wx = (size_t)3 * k;
+    const int64_t cf = ChunkPipe::chunk_frames(N, wp * sizeof(double));
+    int q = 0;
+    for (int64_t f0 = 0; f0 < N; f0 += cf, q = (q + 1) % ChunkPipe::kStreams) {
+        const int64_t nf = (N - f0 < cf) ? N - f0 : cf;
+        cudaStream_t s = pipe.s[q];
+        DLT_CUDA_CHECK(cudaMemcpyAsync(d_pts + f0 * wp, pts + f0 * wp, nf * wp * sizeof(double), cudaMemcpyHostToDevice, s));
+        int rc = launch_tri(d_pts + f0 * wp, nf, m, k, d_prof, d_dlt, d_xyz + f0 * wx, flags, s);
+        if (rc) return rc;
+        DLT_CUDA_CHECK(cudaMemcpyAsync(xyz + f0 * wx, d_xyz + f0 * wx, nf * wx * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    DLT_CUDA_CHECK(pipe.finish());
     return ARGUS_OK;
 }
 
@@ -432,13 +468,23 @@ int argus_dlt_reproj_error(const double *xyz, const double *pts, int64_t N, int 
     DLT_CUDA_CHECK(sc.alloc(&d_pts, (size_t)N * 2 * m * k)); DLT_CUDA_CHECK(sc.alloc(&d_prof, (size_t)m * 8));
     DLT_CUDA_CHECK(sc.alloc(&d_dlt, (size_t)m * 11)); DLT_CUDA_CHECK(sc.alloc(&d_xyz, (size_t)N * 3 * k));
     DLT_CUDA_CHECK(sc.alloc(&d_err, (size_t)N * k));
-    DLT_CUDA_CHECK(cudaMemcpy(d_pts, pts, (size_t)N * 2 * m * k * sizeof(double), cudaMemcpyHostToDevice));
-    DLT_CUDA_CHECK(cudaMemcpy(d_xyz, xyz, (size_t)N * 3 * k * sizeof(double), cudaMemcpyHostToDevice));
     DLT_CUDA_CHECK(cudaMemcpy(d_prof, prof, (size_t)m * 8 * sizeof(double), cudaMemcpyHostToDevice));
     DLT_CUDA_CHECK(cudaMemcpy(d_dlt, dlt, (size_t)m * 11 * sizeof(double), cudaMemcpyHostToDevice));
-    int rc = launch_err(d_xyz, d_pts, N, m, k, d_prof, d_dlt, d_err, 0);
-    if (rc) return rc;
-    DLT_CUDA_CHECK(cudaMemcpy(err, d_err, (size_t)N * k * sizeof(double), cudaMemcpyDeviceToHost));
+    DLT_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));      // the pipe's streams do not order against the legacy stream
+    ChunkPipe pipe; DLT_CUDA_CHECK(pipe.init());
+    const size_t wp = (size_t)2 * m * k, wx = (size_t)3 * k;
+    const int64_t cf = ChunkPipe::chunk_frames(N, (wp + wx) * sizeof(double));
+    int q = 0;
+    for (int64_t f0 = 0; f0 < N; f0 += cf, q = (q + 1) % ChunkPipe::kStreams) {
+        const int64_t nf = (N - f0 < cf) ? N - f0 : cf;
+        cudaStream_t s = pipe.s[q];
+        DLT_CUDA_CHECK(cudaMemcpyAsync(d_pts + f0 * wp, pts + f0 * wp, nf * wp * sizeof(double), cudaMemcpyHostToDevice, s));
+        DLT_CUDA_CHECK(cudaMemcpyAsync(d_xyz + f0 * wx, xyz + f0 * wx, nf * wx * sizeof(double), cudaMemcpyHostToDevice, s));
+        int rc = launch_err(d_xyz + f0 * wx, d_pts + f0 * wp, nf, m, k, d_prof, d_dlt, d_err + f0, s, N);
+        if (rc) return rc;
+        DLT_CUDA_CHECK(copy_err_chunk(err, d_err, N, k, f0, nf, s));
+    }
+    DLT_CUDA_CHECK(pipe.finish());
     return ARGUS_OK;
 }
 
@@ -450,13 +496,23 @@ int argus_dlt_reconstruct(const double *pts, int64_t N, int m, int k, const doub
     DLT_CUDA_CHECK(sc.alloc(&d_pts, (size_t)N * 2 * m * k)); DLT_CUDA_CHECK(sc.alloc(&d_prof, (size_t)m * 8));
     DLT_CUDA_CHECK(sc.alloc(&d_dlt, (size_t)m * 11)); DLT_CUDA_CHECK(sc.alloc(&d_xyz, (size_t)N * 3 * k));
     DLT_CUDA_CHECK(sc.alloc(&d_err, (size_t)N * k));
-    DLT_CUDA_CHECK(cudaMemcpy(d_pts, pts, (size_t)N * 2 * m * k * sizeof(double), cudaMemcpyHostToDevice));
     DLT_CUDA_CHECK(cudaMemcpy(d_prof, prof, (size_t)m * 8 * sizeof(double), cudaMemcpyHostToDevice));
     DLT_CUDA_CHECK(cudaMemcpy(d_dlt, dlt, (size_t)m * 11 * sizeof(double), cudaMemcpyHostToDevice));
-    int rc = launch_fused(d_pts, N, m, k, d_prof, d_dlt, d_xyz, d_err, flags, 0);
-    if (rc) return rc;
-    DLT_CUDA_CHECK(cudaMemcpy(xyz, d_xyz, (size_t)N * 3 * k * sizeof(double), cudaMemcpyDeviceToHost));
-    DLT_CUDA_CHECK(cudaMemcpy(err, d_err, (size_t)N * k * sizeof(double), cudaMemcpyDeviceToHost));
+    DLT_CUDA_CHECK(cudaStreamSynchronize(cudaStreamLegacy));      // the pipe's streams do not order against the legacy stream
+    ChunkPipe pipe; DLT_CUDA_CHECK(pipe.init());
+    const size_t wp = (size_t)2 * m * k, wx = (size_t)3 * k;
+    const int64_t cf = ChunkPipe::chunk_frames(N, wp * sizeof(double));
+    int q = 0;
+    for (int64_t f0 = 0; f0 < N; f0 += cf, q = (q + 1) % ChunkPipe::kStreams) {
+        const int64_t nf = (N - f0 < cf) ? N - f0 : cf;
+        cudaStream_t s = pipe.s[q];
+        DLT_CUDA_CHECK(cudaMemcpyAsync(d_pts + f0 * wp, pts + f0 * wp, nf * wp * sizeof(double), cudaMemcpyHostToDevice, s));
+        int rc = launch_fused(d_pts + f0 * wp, nf, m, k, d_prof, d_dlt, d_xyz + f0 * wx, d_err + f0, flags, s, N);
+        if (rc) return rc;
+        DLT_CUDA_CHECK(cudaMemcpyAsync(xyz + f0 * wx, d_xyz + f0 * wx, nf * wx * sizeof(double), cudaMemcpyDeviceToHost, s));
+        DLT_CUDA_CHECK(copy_err_chunk(err, d_err, N, k, f0, nf, s));
+    }
+    DLT_CUDA_CHECK(pipe.finish());
     return ARGUS_OK;
 }
 

@@ -51,12 +51,19 @@ def reproj_error(xyz, pts, prof, dlt):
     return err
 
 
-def reconstruct(pts, prof, dlt, textbook=False):
-    """Both in one device round trip: -> (xyz N x 3k, err k x N)."""
+def reconstruct(pts, prof, dlt, textbook=False, out=None):
+    """Both in one device round trip: -> (xyz N x 3k, err k x N).  ``out=(xyz, err)``: preallocated C-contiguous float64
+    results (e.g. pinned memory, so that the download overlaps the upload at full PCIe speed)."""
     lib = _lib.load()
     pts, prof, dlt, m, k = _prep(pts, prof, dlt)
     N = pts.shape[0]
-    xyz = np.empty((N, 3 * k)); err = np.empty((k, N))
+    if out is None:
+        xyz = np.empty((N, 3 * k)); err = np.empty((k, N))
+    else:
+        xyz, err = out
+        for a, shp in ((xyz, (N, 3 * k)), (err, (k, N))):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous and a.shape == shp):
+                raise ValueError("out must be C-contiguous float64 arrays of shape (N, 3k) and (k, N)")
     _lib.check(lib.argus_dlt_reconstruct(_ptr(pts), N, m, k, _ptr(prof), _ptr(dlt), _ptr(xyz), _ptr(err), 1 if textbook else 0),
                "argus_dlt_reconstruct")
     return xyz, err

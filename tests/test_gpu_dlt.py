@@ -88,6 +88,15 @@ def test_full_size_c2_properties():
     idx = np.random.default_rng(1).permutation(N)[:50_000]
     x2, e2 = dlt.reconstruct(np.ascontiguousarray(pts[idx]), d["prof"], d["dlt"])
     assert np.array_equal(x2, xyz[idx], equal_nan=True) and np.array_equal(e2, err[:, idx], equal_nan=True)
+    # the two-call path (uv_to_xyz then get_repo_errors) over several transfer chunks gives the fused call's numbers
+    sub = np.ascontiguousarray(pts[:120_000])
+    x3 = dlt.triangulate(sub, d["prof"], d["dlt"])
+    e3 = dlt.reproj_error(x3, sub, d["prof"], d["dlt"])
+    assert np.array_equal(x3, xyz[:120_000], equal_nan=True) and np.array_equal(e3, err[:, :120_000], equal_nan=True)
+    # preallocated outputs
+    xo_, eo_ = np.empty((120_000, 3 * k)), np.empty((k, 120_000))
+    dlt.reconstruct(sub, d["prof"], d["dlt"], out=(xo_, eo_))
+    assert np.array_equal(xo_, x3, equal_nan=True) and np.array_equal(eo_, e3, equal_nan=True)
     # oracle on a sample of frames
     sidx = idx[:300]
     for t in (0, 7):
