@@ -44,11 +44,16 @@ def shard_points(n, world, rank, nobs_per_point=None):
 class BundleAdjuster:
     """Problem resident on one GPU.  ``vmask`` (n x m), ``p`` = [16 m | 3 n], ``rot0`` (4 m), ``x`` (nobs x 2)."""
 
-    def __init__(self, device=0, stream=None):
+    MODES = {"motstr": 0, "mot": 1, "str": 2}
+
+    def __init__(self, device=0, stream=None, mode="motstr"):
+        """``mode``: which parameters move - "motstr" (sba_motstr_levmar_x), "mot" (cameras only, sba_mot_levmar_x) or
+        "str" (points only, sba_str_levmar_x)."""
         self.lib = _lib.load()
         h = ctypes.c_void_p()
         _lib.check(self.lib.argus_ba_create(ctypes.byref(h), int(device), ctypes.c_void_p(stream or 0)), "argus_ba_create")
         self.h = h
+        _lib.check(self.lib.argus_ba_set_mode(self.h, self.MODES[mode]), "argus_ba_set_mode")
         self.n = self.m = 0
         self._cb = None
         self._keep = None
@@ -173,6 +178,48 @@ def solve_motstr(vmask, p, rot0, x, nccalib=0, ncdist=0, itmax=DEFAULT_ITMAX, op
     if ret < _lib.ARGUS_E_SBA:
         _lib.check(ret, "argus_ba_motstr_kdrts")
     return p, info, ret
+
+
+def solve_mot(vmask, cams, pts, rot0, x, nccalib=0, ncdist=0, itmax=DEFAULT_ITMAX, opts=DEFAULT_OPTS, mcon=0, verbose=0, compat=True):
+    """Motion-only bundle adjustment, ``argus_ba_mot_kdrts`` (the reference's sba_mot_levmar_x with the KDRT callbacks):
+    the points stay where they are.  Returns (cams_new (16 m), info[10], retval)."""
+    lib = _lib.load()
+    vmask = _as_mask(vmask)
+    n, m = vmask.shape
+    cams = np.array(cams, dtype=np.float64, copy=True).ravel()
+    pts = np.ascontiguousarray(pts, dtype=np.float64).ravel()
+    rot0 = np.ascontiguousarray(rot0, dtype=np.float64).ravel()
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    if cams.size != 16 * m or pts.size != 3 * n or rot0.size != 4 * m or x.size != 2 * int((vmask != 0).sum()):
+        raise ValueError("inconsistent BA problem sizes")
+    opts = np.ascontiguousarray(opts, dtype=np.float64)
+    info = np.zeros(10)
+    ret = lib.argus_ba_mot_kdrts(n, m, int(mcon), _ptr(vmask), _ptr(cams), _ptr(pts), _ptr(rot0), _ptr(x), int(nccalib), int(ncdist),
+                                 int(itmax), int(verbose), _ptr(opts), _ptr(info), _lib.COMPAT_SBA16 if compat else 0)
+    if ret < _lib.ARGUS_E_SBA:
+        _lib.check(ret, "argus_ba_mot_kdrts")
+    return cams, info, ret
+
+
+def solve_str(vmask, pts, cams, rot0, x, itmax=DEFAULT_ITMAX, opts=DEFAULT_OPTS, ncon=0, verbose=0, compat=True):
+    """Structure-only bundle adjustment, ``argus_ba_str_kdrts`` (sba_str_levmar_x with the KDS callbacks): the cameras stay
+    where they are (re-triangulation by reprojection-error minimisation).  Returns (pts_new (3 n), info[10], retval)."""
+    lib = _lib.load()
+    vmask = _as_mask(vmask)
+    n, m = vmask.shape
+    pts = np.array(pts, dtype=np.float64, copy=True).ravel()
+    cams = np.ascontiguousarray(cams, dtype=np.float64).ravel()
+    rot0 = np.ascontiguousarray(rot0, dtype=np.float64).ravel()
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    if cams.size != 16 * m or pts.size != 3 * n or rot0.size != 4 * m or x.size != 2 * int((vmask != 0).sum()):
+        raise ValueError("inconsistent BA problem sizes")
+    opts = np.ascontiguousarray(opts, dtype=np.float64)
+    info = np.zeros(10)
+    ret = lib.argus_ba_str_kdrts(n, int(ncon), m, _ptr(vmask), _ptr(pts), _ptr(cams), _ptr(rot0), _ptr(x),
+                                 int(itmax), int(verbose), _ptr(opts), _ptr(info), _lib.COMPAT_SBA16 if compat else 0)
+    if ret < _lib.ARGUS_E_SBA:
+        _lib.check(ret, "argus_ba_str_kdrts")
+    return pts, info, ret
 
 
 def host_allreduce_hook(group=None):

@@ -18,6 +18,7 @@
 #include "ba_kernels.cuh"
 #include "ba_schur_mma.cuh"
 #include "ba_lin_tile.cuh"
+#include "ba_blockdiag.cuh"
 
 using namespace argus;
 
@@ -92,6 +93,7 @@ struct argus_ba_ctx {
     DevBuf<int> flags;     // [0] singular V*, [1] chol status
     // generation-2 (tile / MMA) plan
     int gen = 3;
+    int mode = kModeMotStr;   // which half of the parameters moves (argus_ba_set_mode)
     int schur_nw_pref = 12;
     DevBuf<int32_t> tile_pt, tile_o; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
     DevBuf<uint8_t> obs_lpt, corder, pt_rank, vmask_dev; DevBuf<int32_t> idx_btot; int rank_mp = 16;
@@ -123,7 +125,7 @@ struct argus_ba_ctx {
     }
     BaProblem problem() const {
         BaProblem pb;
-        pb.n = n; pb.ncon = ncon; pb.m = m; pb.mcon = mcon; pb.nobs = nobs; pb.nfix_k = nfix_k; pb.nfix_d = nfix_d; pb.cam_fix = cam_fix_on ? cam_fix.p : nullptr;
+        pb.n = n; pb.ncon = (mode == kModeMot) ? n : ncon; pb.m = m; pb.mcon = (mode == kModeStr) ? m : mcon; pb.nobs = nobs; pb.nfix_k = nfix_k; pb.nfix_d = nfix_d; pb.cam_fix = cam_fix_on ? cam_fix.p : nullptr;
         pb.obs_ptr = obs_ptr.p; pb.obs_cam = obs_cam.p; pb.obs_uv = obs_uv.p; pb.pt_mask = pt_mask.p; pb.rot0 = rot0.p;
         return pb;
     }
@@ -240,6 +242,21 @@ int run_lin_tile(argus_ba_ctx *c, int mode, double mu, int use_state, int write_
     return ARGUS_OK;
 }
 
+// red3 = {cost, ||db||^2, dL} summed over ranks; the "a block was singular" flag travels in red3[3] so that every rank takes the
+// same accept / reject decision
+__global__ void k_flag_to_double(const int *__restrict__ flags, double *__restrict__ dst) { if (threadIdx.x == 0) *dst = (double)flags[0]; }
+__global__ void k_double_to_flag(const double *__restrict__ src, int *__restrict__ flags) { if (threadIdx.x == 0) flags[0] = (*src != 0.0) ? 1 : 0; }
+int reduce_attempt_scalars(argus_ba_ctx *c)
+{
+    if (c->world <= 1) return ARGUS_OK;
+    k_flag_to_double<<<1, 32, 0, c->stream>>>(c->flags.p, c->red3.p + 3);
+    int rc = do_allreduce(c, c->red3.p, 4, 0);
+    if (rc) return rc;
+    k_double_to_flag<<<1, 32, 0, c->stream>>>(c->red3.p + 3, c->flags.p);
+    c->launches += 2;
+    return ARGUS_OK;
+}
+
 // ---- one damping attempt: prepare, Schur complement, solve, back-substitute, evaluate; scalars in att[0..3] ----
 int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int write_state, double *dbout, bool need_lin = true)
 {
@@ -324,7 +341,7 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
         k_reduce_sum<<<1, 32, 0, c->stream>>>(c->part3.p, c->grid_pts128, 3, 3, c->red3.p);
     }
     ARGUS_CUDA_CHECK(cudaGetLastError());
-    rc = do_allreduce(c, c->red3.p, 3, 0);
+    rc = reduce_attempt_scalars(c);
     if (rc) return rc;
     k_attempt_finalize<<<1, 32, 0, c->stream>>>(c->flags.p, c->cam2.p, c->red3.p, c->att.p);
     c->launches += 10;
@@ -339,6 +356,169 @@ int read_back(argus_ba_ctx *c, const double *dsrc, int count, double *hdst)
     memcpy(hdst, c->h_pinned, count * sizeof(double));
     c->d2h_bytes += count * sizeof(double);
     return ARGUS_OK;
+}
+
+
+// ---- motion-only / structure-only LM (sba_mot_levmar_x sba_levmar.c:1437-1980, sba_str_levmar_x :1987-2540) ----
+int run_bd_linearize(argus_ba_ctx *c)
+{
+    const int m = c->m;
+    {
+        ProfScope ps(c, P_LINEARIZE);
+#define LIN_LAUNCH(MC_) k_lin_tile<MC_><<<c->grid_lin, 256, c->lin_smem, c->stream>>>(c->problem(), c->tile_plan(), c->lin_plan(), c->cam.p, \
+                                                                                    c->pts.p, 0, 0.0, 0, 0, c->lin_out())
+        const int mc = (m - c->mcon + 7) / 8;
+        if (mc <= 2) LIN_LAUNCH(2); else if (mc <= 4) LIN_LAUNCH(4); else LIN_LAUNCH(8);
+#undef LIN_LAUNCH
+    }
+    {
+        ProfScope ps(c, P_LIN_REDUCE);
+        k_lin_tile_reduce<<<m, 192, 0, c->stream>>>(m, c->grid_lin, c->Upart2.p, c->scpart.p, c->red1.p, c->red2.p + (int64_t)c->npairs * 256,
+                                                   c->red1.p + (int64_t)m * kU, c->max2.p);
+    }
+    ARGUS_CUDA_CHECK(cudaGetLastError());
+    int rc = do_allreduce(c, c->red1.p, (int64_t)m * kU + 2, 0);
+    if (rc) return rc;
+    rc = do_allreduce(c, c->max2.p, 2, 1);
+    if (rc) return rc;
+    k_bd_finalize<<<1, 32, 0, c->stream>>>(c->mode, c->red1.p, c->cam.p, m, c->mcon, c->red1.p + (int64_t)m * kU, c->max2.p, c->scal.p);
+    c->launches += 3;
+    ARGUS_CUDA_CHECK(cudaGetLastError());
+    return ARGUS_OK;
+}
+
+// one attempt: att = {all blocks solved, ||dp||^2, dL, cost at the trial point, 0}
+int run_bd_attempt(argus_ba_ctx *c, double mu, double mu_diag)
+{
+    const int m = c->m;
+    ARGUS_CUDA_CHECK(cudaMemsetAsync(c->flags.p, 0, 2 * sizeof(int), c->stream));
+    if (c->mode == kModeMot) {
+        {
+            ProfScope ps(c, P_CHOL);
+            k_mot_solve<<<1, 64, 0, c->stream>>>(m, c->mcon, c->red1.p, mu_diag, mu, c->cam.p, c->cam_new.p, c->cam2.p, c->flags.p);
+        }
+        ARGUS_CUDA_CHECK(cudaMemsetAsync(c->red3.p, 0, 4 * sizeof(double), c->stream));
+        int rc = run_residual(c, c->cam_new.p, c->pts.p, nullptr);           // cost -> red3[0] (all-reduced)
+        if (rc) return rc;
+        c->launches += 1;
+    } else {
+        ProfScope ps(c, P_BACKSUB);
+        ARGUS_CUDA_CHECK(cudaMemsetAsync(c->da_full.p, 0, 16 * m * sizeof(double), c->stream));
+        ARGUS_CUDA_CHECK(cudaMemsetAsync(c->cam2.p, 0, 2 * sizeof(double), c->stream));
+        k_str_invert<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->n, c->ncon, mu_diag, c->V.p, c->Vinv.p, c->flags.p);
+        const size_t sm = 2 * cam_smem(m) + (size_t)m * 16 * sizeof(double);
+        k_backsub_recompute<<<c->grid_pts128, 128, sm, c->stream>>>(c->problem(), mu, c->cam.p, c->cam.p, c->da_full.p, c->pts.p, c->Vinv.p,
+                                                                   c->eb.p, c->pts_new.p, nullptr, c->part3.p);
+        k_reduce_sum<<<1, 32, 0, c->stream>>>(c->part3.p, c->grid_pts128, 3, 3, c->red3.p);
+        ARGUS_CUDA_CHECK(cudaGetLastError());
+        int rc = reduce_attempt_scalars(c);
+        if (rc) return rc;
+        c->launches += 3;
+    }
+    k_attempt_finalize<<<1, 32, 0, c->stream>>>(c->flags.p, c->cam2.p, c->red3.p, c->att.p);
+    c->launches += 1;
+    ARGUS_CUDA_CHECK(cudaGetLastError());
+    return ARGUS_OK;
+}
+
+int solve_blockdiag(argus_ba_ctx *c, int itmax, int verbose, const double opts[5], double info[10], int flags)
+{
+    const bool compat = (flags & ARGUS_BA_COMPAT_SBA16) != 0;
+    const bool mot = c->mode == kModeMot;
+    const int m = c->m;
+    const int64_t nvis = c->nobs;
+    double h[8];
+    int rc;
+    // number of block systems per attempt (info[9] counts every one of them, :1851 / :2396), over all ranks
+    double nblocks = mot ? (double)(m - c->mcon) : (double)(c->n - c->ncon);
+    if (c->world == 1) {
+        const int64_t nobs2 = nvis * 2, nvars = mot ? (int64_t)m * 16 : c->n * 3;
+        if (nobs2 < nvars) {
+            fprintf(stderr, "argus_b200: cannot solve a problem with fewer measurements [%lld] than unknowns [%lld]\n",
+                    (long long)nobs2, (long long)nvars);
+            return ARGUS_E_SBA;
+        }
+    } else if (!mot) {
+        ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->red3.p, &nblocks, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        ARGUS_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if ((rc = do_allreduce(c, c->red3.p, 1, 0))) return rc;
+        if ((rc = read_back(c, c->red3.p, 1, h))) return rc;
+        nblocks = h[0];
+    }
+    if (itmax == 0) return 0;
+    const double tau = fabs(opts[0]), eps1 = fabs(opts[1]), eps2 = fabs(opts[2]), eps2_sq = opts[2] * opts[2],
+                 eps3_sq = opts[3] * opts[3], eps4_sq = opts[4] * opts[4];
+    double mu = 0.0, g_inf = 0.0, p_eL2, pdp_eL2, p_L2 = 0.0, dp_L2 = DBL_MAX, dF, dL, dmax = DBL_MIN, init_p_eL2, nlss = 0.0;
+    int nu = 2, nu2, stop = 0, nfev = 0, njev = 0, itno;
+
+    if ((rc = run_residual(c, c->cam.p, c->pts.p, nullptr))) return rc;
+    if ((rc = read_back(c, c->red3.p, 1, h))) return rc;
+    p_eL2 = h[0]; nfev = 1;
+    if (verbose) printf("initial %s-SBA error %g [%g]\n", mot ? "mot" : "str", p_eL2, p_eL2 / (double)nvis);
+    init_p_eL2 = p_eL2;
+    if (!isfinite(p_eL2)) stop = 7;
+
+    for (itno = 0; itno < itmax && !stop; ++itno) {
+        if ((rc = run_bd_linearize(c))) return rc;
+        ++njev;
+        if ((rc = read_back(c, c->scal.p, 4, h))) return rc;
+        g_inf = h[1]; p_L2 = h[2]; dmax = h[3];
+        if (g_inf <= eps1) { dp_L2 = 0.0; stop = 1; break; }
+        if (itno == 0) mu = tau * dmax;
+        double mu_diag = 0.0;       // what sits on the diagonals: never taken off after a rejected step in sba 1.6 (:1932, :2477 are #if 0)
+        while (1) {
+            mu_diag = compat ? mu_diag + mu : mu;
+            if ((rc = run_bd_attempt(c, mu, mu_diag))) return rc;
+            if ((rc = read_back(c, c->att.p, 5, h))) return rc;
+            nlss += nblocks;
+            const bool solved = mot ? (h[0] != 0.0) : (h[4] == 0.0);
+            if (solved) {
+                dp_L2 = h[1];
+                if (dp_L2 <= eps2_sq * p_L2) { stop = 2; break; }
+                if (dp_L2 >= (p_L2 + eps2) / 1e-24) {
+                    fprintf(stderr, "argus_b200: the matrix of the augmented normal equations is almost singular,\n"
+                                    "     minimization should be restarted from the current solution with an increased damping term\n");
+                    if (c->profiling) prof_collect(c);
+                    return ARGUS_E_SBA;
+                }
+                ++nfev;
+                pdp_eL2 = h[3];
+                if (!isfinite(pdp_eL2)) { stop = 7; break; }
+                dL = h[2];
+                dF = p_eL2 - pdp_eL2;
+                if (verbose > 1)
+                    printf("\ndamping term %8g, gain ratio %8g, errors %8g / %8g = %g\n", mu, dL != 0.0 ? dF / dL : dF / DBL_EPSILON,
+                           p_eL2 / nvis, pdp_eL2 / nvis, p_eL2 / pdp_eL2);
+                if (dL > 0.0 && dF > 0.0) {
+                    double tmp = (2.0 * dF / dL - 1.0);
+                    tmp = 1.0 - tmp * tmp * tmp;
+                    mu = mu * ((tmp >= 0.3333333334) ? tmp : 0.3333333334);
+                    nu = 2;
+                    if (pdp_eL2 - 2.0 * sqrt(p_eL2 * pdp_eL2) < (eps4_sq - 1.0) * p_eL2) stop = 4;
+                    if (mot) { std::swap(c->cam.p, c->cam_new.p); std::swap(c->cam.cap, c->cam_new.cap); }
+                    else { std::swap(c->pts.p, c->pts_new.p); std::swap(c->pts.cap, c->pts_new.cap); }
+                    p_eL2 = pdp_eL2;
+                    break;
+                }
+            }
+            mu *= nu;
+            nu2 = (int)((unsigned)nu << 1);
+            if (nu2 <= nu) {
+                fprintf(stderr, "argus_b200: too many failed attempts to increase the damping factor! Singular Hessian matrix?\n");
+                stop = 6;
+                break;
+            }
+            nu = nu2;
+        }
+        if (p_eL2 <= eps3_sq) stop = 5;
+    }
+    if (itno >= itmax) stop = 3;
+    if (c->profiling) prof_collect(c);
+    if (info) {
+        info[0] = init_p_eL2; info[1] = p_eL2; info[2] = g_inf; info[3] = dp_L2; info[4] = mu / dmax;
+        info[5] = itno; info[6] = stop; info[7] = nfev; info[8] = njev; info[9] = nlss;
+    }
+    return (stop != 7) ? itno : ARGUS_E_SBA;
 }
 
 }  // namespace
@@ -511,21 +691,21 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
 #define PLAN_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 #define PLAN_ENS(buf, cnt) PLAN_CHECK((buf).ensure((size_t)(cnt)))
     PLAN_CHECK(c->tile_pt.ensure(tiles.size())); PLAN_CHECK(c->tile_o.ensure(tiles.size())); PLAN_CHECK(c->blk_jk.ensure(hjk.size())); PLAN_CHECK(c->blk_pair.ensure(hpair.size()));
-    PLAN_CHECK(c->zsign.ensure((size_t)n)); if (c->gen >= 2) { PLAN_ENS(c->Z, 48 * nobs); }
+    PLAN_CHECK(c->zsign.ensure((size_t)n)); if (c->gen >= 2 && c->mode == kModeMotStr) { PLAN_ENS(c->Z, 48 * nobs); }
     PLAN_CHECK(c->obs_lpt.ensure((size_t)nobs)); PLAN_CHECK(c->corder.ensure((size_t)nobs)); PLAN_CHECK(c->cstart.ensure((size_t)c->ntiles * (m + 1)));
     PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1024);
-    PLAN_CHECK(c->pt_rank.ensure((size_t)n * c->rank_mp));
+    PLAN_CHECK(c->pt_rank.ensure(c->mode == kModeMotStr ? (size_t)n * c->rank_mp : 1));
     PLAN_ENS(c->vmask_dev, n * m); PLAN_ENS(c->idx_btot, (n + kIdxPts - 1) / kIdxPts + 1);
     PLAN_ENS(c->obs_ptr, n + 1); PLAN_ENS(c->obs_cam, nobs); PLAN_ENS(c->obs_uv, nobs); PLAN_ENS(c->pt_mask, n);
     PLAN_ENS(c->rot0, 4 * m); PLAN_ENS(c->cam, 16 * m); PLAN_ENS(c->cam_new, 16 * m); PLAN_ENS(c->cam0, 16 * m);
     PLAN_ENS(c->pts, 3 * n); PLAN_ENS(c->pts_new, 3 * n); PLAN_ENS(c->pts0, 3 * n);
-    if (c->gen < 3) { PLAN_ENS(c->W, 48 * nobs); }
-    if (c->gen < 2) { PLAN_ENS(c->Y, 48 * nobs); } PLAN_ENS(c->V, 6 * n); PLAN_ENS(c->eb, 3 * n); PLAN_ENS(c->vstate, 3 * n); PLAN_ENS(c->Vinv, 6 * n);
+    if (c->gen < 3 && c->mode == kModeMotStr) { PLAN_ENS(c->W, 48 * nobs); }
+    if (c->gen < 2 && c->mode == kModeMotStr) { PLAN_ENS(c->Y, 48 * nobs); } PLAN_ENS(c->V, 6 * n); PLAN_ENS(c->eb, 3 * n); PLAN_ENS(c->vstate, 3 * n); PLAN_ENS(c->Vinv, 6 * n);
     PLAN_ENS(c->cvec, 3 * n); PLAN_ENS(c->dbuf, 3 * n);
     PLAN_ENS(c->Upart, (int64_t)c->grid_pts128 * m * kU); PLAN_ENS(c->scpart, 4 * std::max(c->grid_pts128, c->grid_lin)); PLAN_ENS(c->red1, m * kU + 2); PLAN_ENS(c->max2, 2);
     PLAN_ENS(c->Epart, (int64_t)c->grid_pts128 * m * 16); PLAN_ENS(c->Spart, (int64_t)std::max(c->nchunks, c->schur_nchunk) * c->npairs * 256);
     PLAN_ENS(c->red2, (int64_t)c->npairs * 256 + m * 16); PLAN_ENS(c->S, (int64_t)N * N); PLAN_ENS(c->E, N); PLAN_ENS(c->da_free, N); PLAN_ENS(c->da_full, 16 * m);
-    PLAN_ENS(c->part3, 3 * c->grid_pts128); PLAN_ENS(c->red3, 3); PLAN_ENS(c->cam2, 2); PLAN_ENS(c->scal, 8); PLAN_ENS(c->att, 8); PLAN_ENS(c->respart, c->grid_pts256);
+    PLAN_ENS(c->part3, 3 * c->grid_pts128); PLAN_ENS(c->red3, 4); PLAN_ENS(c->cam2, 2); PLAN_ENS(c->scal, 8); PLAN_ENS(c->att, 8); PLAN_ENS(c->respart, c->grid_pts256);
     PLAN_CHECK(c->flags.ensure(2));
 #undef PLAN_ENS
 #undef PLAN_CHECK
@@ -568,8 +748,10 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pts0.p, p + 16 * m, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
     // derived static indices, built on the device
     if (n > 0) {
-        ARGUS_CUDA_CHECK(cudaMemsetAsync(c->pt_rank.p, 0xFF, (size_t)n * c->rank_mp, s));
-        k_build_point_index<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, ncon, c->rank_mp, c->obs_ptr.p, c->obs_cam.p, c->pt_rank.p);
+        if (c->mode == kModeMotStr) {
+            ARGUS_CUDA_CHECK(cudaMemsetAsync(c->pt_rank.p, 0xFF, (size_t)n * c->rank_mp, s));
+            k_build_point_index<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, ncon, c->rank_mp, c->obs_ptr.p, c->obs_cam.p, c->pt_rank.p);
+        }
         if (c->ntiles > 0)
             k_build_tile_index<<<c->ntiles, 256, 0, s>>>(m, c->tile_pt.p, c->tile_o.p, c->obs_ptr.p, c->obs_cam.p, c->obs_lpt.p, c->corder.p,
                                                          c->cstart.p);
@@ -580,6 +762,14 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
                     2 * tiles.size() * sizeof(int32_t);
     if (timing) fprintf(stderr, "argus_b200 upload: host index build %.1f ms, device alloc %.1f ms, H2D %.1f ms\n", 1e3 * (t_index - t_start), 1e3 * (t_alloc - t_index), 1e3 * (tnow() - t_alloc));
     return argus_ba_reset(c);
+}
+
+int argus_ba_set_mode(argus_ba_ctx *c, int mode)
+{
+    if (!c || mode < kModeMotStr || mode > kModeStr) return ARGUS_E_ARG;
+    if (c->m != 0 && mode != c->mode && (mode == kModeMotStr) != (c->mode == kModeMotStr)) return ARGUS_E_ARG;   // set it before upload
+    c->mode = mode;
+    return ARGUS_OK;
 }
 
 int argus_ba_set_camera_fix(argus_ba_ctx *c, const int *nccalib, const int *ncdist)
@@ -707,6 +897,7 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
     const bool compat = (flags & ARGUS_BA_COMPAT_SBA16) != 0;
     c->profiling = (flags & ARGUS_BA_PROFILE) != 0;
     memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_n, 0, sizeof(c->prof_n));
+    if (c->mode != kModeMotStr) return solve_blockdiag(c, itmax, verbose, opts, info, flags);
     const int m = c->m;
     const int64_t nvis = c->nobs;
     if (c->world == 1) {      // with several ranks the host wrapper checks the global counts
@@ -832,6 +1023,47 @@ int argus_ba_motstr_kdrts(int64_t n, int64_t ncon, int m, int mcon, const char *
     if (timing) fprintf(stderr, "argus_b200 one-shot: create %.1f ms, upload %.1f ms, solve %.1f ms, download %.1f ms, destroy %.1f ms\n",
                         1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (t4 - t3), 1e3 * (tnow() - t4));
     return ret;
+}
+
+namespace {
+int blockdiag_oneshot(int mode, int64_t n, int64_t ncon, int m, int mcon, const char *vmask, double *moving, const double *frozen,
+                      const double *rot0, const double *x, int nccalib, int ncdist, int itmax, int verbose, const double opts[5],
+                      double info[10], int flags)
+{
+    if (!moving || !frozen || n < 0 || m < 1) return ARGUS_E_ARG;
+    std::vector<double> p((size_t)16 * m + (size_t)3 * n);
+    const bool mot = mode == kModeMot;
+    memcpy(p.data(), mot ? moving : frozen, (size_t)16 * m * sizeof(double));
+    memcpy(p.data() + 16 * m, mot ? frozen : moving, (size_t)3 * n * sizeof(double));
+    argus_ba_ctx *c = nullptr;
+    int rc = argus_ba_create(&c, 0, nullptr);
+    if (rc) return rc;
+    rc = argus_ba_set_mode(c, mode);
+    if (rc == ARGUS_OK) rc = argus_ba_upload(c, n, ncon, m, mcon, vmask, p.data(), rot0, x, nccalib, ncdist);
+    int ret = rc;
+    if (rc == ARGUS_OK) {
+        ret = argus_ba_solve(c, itmax, verbose, opts, info, flags);
+        if (ret >= 0 || ret == ARGUS_E_SBA) {
+            rc = argus_ba_download(c, p.data());
+            if (rc) ret = rc;
+            else memcpy(moving, mot ? p.data() : p.data() + 16 * m, (mot ? (size_t)16 * m : (size_t)3 * n) * sizeof(double));
+        }
+    }
+    argus_ba_destroy(c);
+    return ret;
+}
+}  // namespace
+
+int argus_ba_mot_kdrts(int64_t n, int m, int mcon, const char *vmask, double *cams, const double *pts, const double *rot0,
+                       const double *x, int nccalib, int ncdist, int itmax, int verbose, const double opts[5], double info[10], int flags)
+{
+    return blockdiag_oneshot(kModeMot, n, 0, m, mcon, vmask, cams, pts, rot0, x, nccalib, ncdist, itmax, verbose, opts, info, flags);
+}
+
+int argus_ba_str_kdrts(int64_t n, int64_t ncon, int m, const char *vmask, double *pts, const double *cams, const double *rot0,
+                       const double *x, int itmax, int verbose, const double opts[5], double info[10], int flags)
+{
+    return blockdiag_oneshot(kModeStr, n, ncon, m, 0, vmask, pts, cams, rot0, x, 0, 0, itmax, verbose, opts, info, flags);
 }
 
 }  // extern "C"

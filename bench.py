@@ -7,7 +7,7 @@
 
 Workload (BASELINE.json config 4 per GPU, weak scaling): 16 cameras, 2,000,000 points x 10 views = 20,000,000
 observations per rank, all 10 Argus intrinsics + pose free (nccalib = ncdist = 0), cameras shared by all ranks.
-A "step" is one pass of the hot path over that batch: ITERS_PER_STEP (5) Levenberg-Marquardt iterations from the same
+A "step" is one pass of the hot path over that batch: ITERS_PER_STEP (10) Levenberg-Marquardt iterations from the same
 perturbed start (stop tests disabled so every step does identical work; asserted).
 metric = observations x LM iterations per second, whole job (all ranks).  The reduced camera system and three
 scalars are all-reduced (NCCL) per iteration when N > 1; points/observations never move.
@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 
 FP64_PEAK_TFLOPS = 37.1      # measured on this pool's B200 with tools/microbench/fp64_peak.cu (DMMA.8x8x4, sustained);
                              # MEASURED_PEAKS.json has no fp64 entry - see profiles/r01_fp64_peak.txt
-ITERS_PER_STEP = 5
+ITERS_PER_STEP = 10
 WORKLOADS = {
     # name: (cameras, points per rank, views per point, nccalib, ncdist)
     "c4": (16, 2_000_000, 10, 0, 0),
@@ -254,7 +254,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-points", type=int, default=4096, help="points in the bounded CPU sample")
-    ap.add_argument("--cpu-baseline-points", type=int, default=8192)
+    ap.add_argument("--cpu-baseline-points", type=int, default=32768)
     ap.add_argument("--no-dlt", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -313,6 +313,12 @@ def main():
         clocks = sampler.stop()
         ms_total = e0.elapsed_time(e1)
         c1 = B.counters()
+        # time to convergence with the reference's default options, outside the timed region
+        B.reset(); torch.cuda.synchronize()
+        tc0 = time.perf_counter()
+        retc, infoc = B.solve(itmax=150)
+        conv = {"iterations": int(infoc[5]), "stop_reason": int(infoc[6]), "ms": 1e3 * (time.perf_counter() - tc0),
+                "initial_cost": float(infoc[0]), "final_cost": float(infoc[1]), "opts": "default (1e-3, 1e-12, 1e-12, 1e-12, 0), itmax 150"}
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device=device)
     tot_obs = torch.tensor([float(nobs_local)], dtype=torch.float64, device=device)
     if world > 1:
@@ -385,10 +391,12 @@ def main():
         kind = "reference" if sba_ref.available() else "port"
         fn = sba_ref.ref_motstr if kind == "reference" else ba_port.port_motstr
         t0 = time.perf_counter()
-        _, iref, _ = fn(ps, xs, vm, rot0, nk, nd, itmax=2, opts=OPTS_FIXED_WORK)
+        _, iref, _ = fn(ps, xs, vm, rot0, nk, nd, itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
         dt_ref = time.perf_counter() - t0
-        cpu = {"value": int(vm.sum()) * 2 / dt_ref, "unit": "obs*iters/s", "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
-               "sample": "first %d points (%d observations) of the same scene, %d cameras, 2 LM iterations, %.1f s" % (vm.shape[0], int(vm.sum()), m, dt_ref)}
+        assert int(iref[5]) == ITERS_PER_STEP, iref
+        cpu = {"value": int(vm.sum()) * ITERS_PER_STEP / dt_ref, "unit": "obs*iters/s", "cores": 1, "kind": kind, "host_cores": os.cpu_count(),
+               "sample": "first %d points (%d observations) of the same scene, %d cameras, %d LM iterations, %.1f s"
+                         % (vm.shape[0], int(vm.sum()), m, ITERS_PER_STEP, dt_ref)}
 
     B.close()
     dlt_res = None
@@ -408,6 +416,7 @@ def main():
                            "iters_per_step": ITERS_PER_STEP, "parallelism": "points sharded x%d, cameras replicated" % world,
                            "l2": "inputs larger than L2 (>= %.1f GB of per-observation blocks per pass)" % (nobs_local * 48 * 8 / 1e9),
                            "final_cost": final_cost},
+                "convergence": conv,
                 "lm_iters_per_sec": ITERS_PER_STEP * args.steps / (ms_total * 1e-3),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(c1["launches"] - c0["launches"]),
                 "allreduces": int(c1["allreduces"] - c0["allreduces"]), "roofline": rl, "cpu_baseline": cpu, "dlt": dlt_res}

@@ -67,6 +67,21 @@ int argus_ba_motstr_kdrts(int64_t n, int64_t ncon, int m, int mcon, const char *
                           const double *rot0, const double *x, int nccalib, int ncdist,
                           int itmax, int verbose, const double opts[5], double info[10], int flags);
 
+/* ---- motion-only and structure-only bundle adjustment (SBA/sba.h:118-130) ----
+ * argus_ba_mot_kdrts: the drop-in for sba_mot_levmar_x (SBA/sba_levmar.c:1437-1980) + img_projsKDRT_x/_jac_x
+ * (libsbaprojs/sbaprojs.c:1261-1370): cams (16 per camera) is updated in place, pts (3 per point) is what the reference
+ * passes in globs_.ptparams.
+ * argus_ba_str_kdrts: the drop-in for sba_str_levmar_x (:1987-2540) + img_projsKDS_x/_jac_x (sbaprojs.c:1375-1445): pts is
+ * updated in place, cams is globs_.camparams.  The reference's KDS callbacks read entries 10..12 of a camera row as the
+ * vector part of the camera's FULL rotation quaternion; that is rot0 = (1,0,0,0) per camera here, while a general rot0
+ * keeps the (rot0, local rotation) form the motstr driver returns.  info[9] counts every block system solved. */
+int argus_ba_mot_kdrts(int64_t n, int m, int mcon, const char *vmask, double *cams, const double *pts,
+                       const double *rot0, const double *x, int nccalib, int ncdist,
+                       int itmax, int verbose, const double opts[5], double info[10], int flags);
+int argus_ba_str_kdrts(int64_t n, int64_t ncon, int m, const char *vmask, double *pts, const double *cams,
+                       const double *rot0, const double *x,
+                       int itmax, int verbose, const double opts[5], double info[10], int flags);
+
 /* ---- resident-data interface (what the one-shot call is built from; used by bench.py and the multi-GPU host) ---- */
 int  argus_ba_create(argus_ba_ctx **ctx, int device, void *stream /* cudaStream_t or NULL */);
 void argus_ba_destroy(argus_ba_ctx *ctx);
@@ -75,6 +90,12 @@ int  argus_ba_set_comm(argus_ba_ctx *ctx, int rank, int world, argus_allreduce_f
 /* copy a problem (or this rank's shard of the points, with all cameras) to the device and build the indices */
 int  argus_ba_upload(argus_ba_ctx *ctx, int64_t n, int64_t ncon, int m, int mcon, const char *vmask,
                      const double *p, const double *rot0, const double *x, int nccalib, int ncdist);
+/* which parameters move: ARGUS_BA_MODE_MOTSTR (default), _MOT (points frozen) or _STR (cameras frozen); call before
+ * argus_ba_upload (p keeps the [16 per camera | 3 per point] layout in every mode) */
+#define ARGUS_BA_MODE_MOTSTR 0
+#define ARGUS_BA_MODE_MOT    1
+#define ARGUS_BA_MODE_STR    2
+int  argus_ba_set_mode(argus_ba_ctx *ctx, int mode);
 /* EXTENSION (no counterpart in the reference, whose nccalib / ncdist are global, sbaprojs.c:1229-1247): per-camera numbers
  * of fixed trailing intrinsics / distortion coefficients, m entries each, after argus_ba_upload; NULL, NULL restores the global
  * values.  BASELINE config 5 ("mixed fixed/free intrinsics") needs it. */

@@ -437,3 +437,132 @@ done:
     vis_free(&vs);
     return retval;
 }
+
+/* ---------- motion-only / structure-only LM (sba_mot_levmar_x sba_levmar.c:1437-1980, sba_str_levmar_x :1987-2540) ----------
+ * Both are the same block-diagonal LM: which = 0 keeps the points fixed and solves one 16x16 system (U_j + mu I) da_j = ea_j
+ * per camera j >= mcon (:1838-1852); which = 1 keeps the cameras fixed and solves one 3x3 system (V_i + mu I) db_i = eb_i per
+ * point i >= ncon (:2383-2397).  The systems go through sba_Axb_Chol on a COPY of the block (sba_lapack.c:412-426,
+ * iscolmaj = 0), so - unlike the motstr driver - the blocks are not overwritten; the damping is still never taken off the
+ * diagonals after a rejected step (the restore loops are #if 0, :1932-1940 / :2477-2485), which `compat` reproduces.
+ * p = [16 m | 3 n] as in orc_motstr; only the free half is updated.  nlss counts every block solve (:1851, :2396). */
+int orc_blockdiag(int which, int64_t n, int64_t ncon, int m, int mcon, const char *vmask, double *p, const double *rot0,
+                  const double *x, int nccalib, int ncdist, int itmax, int verbose, const double opts[5], double info[10], int compat)
+{
+    vis_t vs; vis_build(&vs, n, m, vmask);
+    const int64_t nvis = vs.nobs, nobs = 2 * nvis;
+    const int bs = which == 0 ? CNP : PNP;                       /* block size */
+    const int64_t nblk = which == 0 ? m : n, nfix = which == 0 ? mcon : ncon, nvars = nblk * bs;
+    double *q = which == 0 ? p : p + CNP * m;                    /* the free half of p */
+    if (nobs < nvars) {
+        fprintf(stderr, "oracle: cannot solve a problem with fewer measurements [%lld] than unknowns [%lld]\n", (long long)nobs, (long long)nvars);
+        vis_free(&vs); return -1;
+    }
+    if (itmax == 0) { vis_free(&vs); return 0; }
+    const int64_t ntot = (int64_t)m * CNP + n * PNP;
+    double *H = (double *)calloc((size_t)(nblk ? nblk : 1) * bs * bs, sizeof(double));     /* U_j or V_i, full row-major blocks */
+    double *g = (double *)calloc((size_t)(nvars ? nvars : 1), sizeof(double));             /* ea or eb */
+    double *dq = (double *)calloc((size_t)(nvars ? nvars : 1), sizeof(double));
+    double *pdp = (double *)malloc((size_t)ntot * sizeof(double));
+    double *e = (double *)malloc((size_t)(nobs ? nobs : 1) * sizeof(double));
+    double *hx = (double *)malloc((size_t)(nobs ? nobs : 1) * sizeof(double));
+    double *diag = (double *)calloc((size_t)(nvars ? nvars : 1), sizeof(double));
+    double blk[CNP * CNP];
+    const double tau = fabs(opts[0]), eps1 = fabs(opts[1]), eps2 = fabs(opts[2]), eps2_sq = opts[2] * opts[2],
+                 eps3_sq = opts[3] * opts[3], eps4_sq = opts[4] * opts[4];
+    double mu = 0.0, g_inf = 0.0, p_eL2, pdp_eL2, p_L2 = 0.0, dp_L2 = DBL_MAX, dF, dL, tmp, init_p_eL2;
+    int nu = 2, nu2, stop = 0, nfev, njev = 0, nlss = 0, itno, retval;
+    p_eL2 = eval_cost(&vs, p, rot0, x, e); nfev = 1;
+    if (verbose) printf("initial %s-SBA error %g [%g]\n", which == 0 ? "mot" : "str", p_eL2, p_eL2 / (double)nvis);
+    init_p_eL2 = p_eL2;
+    if (!isfinite(p_eL2)) stop = 7;
+    for (itno = 0; itno < itmax && !stop; ++itno) {
+        memset(H, 0, (size_t)nblk * bs * bs * sizeof(double)); memset(g, 0, (size_t)nvars * sizeof(double));
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t k = vs.ptr[i]; k < vs.ptr[i + 1]; ++k) {
+                const int j = vs.cam[k];
+                const int64_t b = which == 0 ? j : i;
+                if (b < nfix) continue;
+                double A[32], B[6];
+                const int nk = g_cam_nk ? g_cam_nk[j] : nccalib, nd = g_cam_nd ? g_cam_nd[j] : ncdist;
+                jac_one(p + CNP * j, rot0 + 4 * j, p + CNP * m + PNP * i, nk, nd, A, B, NULL);
+                const double *J = which == 0 ? A : B;            /* 2 x bs, row-major */
+                double *Hb = H + b * bs * bs, *gb = g + b * bs;
+                for (int r = 0; r < bs; ++r) {
+                    for (int c = r; c < bs; ++c) Hb[r * bs + c] += J[r] * J[c] + J[bs + r] * J[bs + c];
+                    gb[r] += J[r] * e[2 * k] + J[bs + r] * e[2 * k + 1];
+                }
+            }
+        for (int64_t b = nfix; b < nblk; ++b)                    /* symmetric copy (:1757-1759) and saved diagonal */
+            for (int r = 0; r < bs; ++r) {
+                for (int c = 0; c < r; ++c) H[b * bs * bs + r * bs + c] = H[b * bs * bs + c * bs + r];
+                diag[b * bs + r] = H[b * bs * bs + r * bs + r];
+            }
+        ++njev;
+        p_L2 = 0.0; g_inf = 0.0;
+        for (int64_t t = 0; t < nvars; ++t) { if (g_inf < (tmp = fabs(g[t]))) g_inf = tmp; p_L2 += q[t] * q[t]; }
+        if (g_inf <= eps1) { dp_L2 = 0.0; stop = 1; break; }
+        if (itno == 0) {
+            tmp = DBL_MIN;
+            for (int64_t t = nfix * bs; t < nvars; ++t) if (diag[t] > tmp) tmp = diag[t];
+            mu = tau * tmp;
+        }
+        while (1) {
+            for (int64_t b = nfix; b < nblk; ++b)
+                for (int r = 0; r < bs; ++r) H[b * bs * bs + r * bs + r] += mu;
+            int64_t nsolved = nfix;
+            memset(dq, 0, (size_t)nfix * bs * sizeof(double));
+            for (int64_t b = nfix; b < nblk; ++b) {
+                memcpy(blk, H + b * bs * bs, (size_t)bs * bs * sizeof(double));
+                nsolved += chol_solve(blk, g + b * bs, dq + b * bs, bs);
+                ++nlss;
+            }
+            if (nsolved == nblk) {
+                memcpy(pdp, p, (size_t)ntot * sizeof(double));
+                double *qn = which == 0 ? pdp : pdp + CNP * m;
+                dp_L2 = 0.0;
+                for (int64_t t = 0; t < nvars; ++t) { qn[t] = q[t] + (tmp = dq[t]); dp_L2 += tmp * tmp; }
+                if (dp_L2 <= eps2_sq * p_L2) { stop = 2; break; }
+                if (dp_L2 >= (p_L2 + eps2) / 1e-24) {
+                    fprintf(stderr, "oracle: the matrix of the augmented normal equations is almost singular\n");
+                    retval = -1; goto done;
+                }
+                pdp_eL2 = eval_cost(&vs, pdp, rot0, x, hx); ++nfev;
+                if (!isfinite(pdp_eL2)) { stop = 7; break; }
+                dL = 0.0;
+                for (int64_t t = 0; t < nvars; ++t) dL += dq[t] * (mu * dq[t] + g[t]);
+                dF = p_eL2 - pdp_eL2;
+                if (dL > 0.0 && dF > 0.0) {
+                    tmp = 2.0 * dF / dL - 1.0;
+                    tmp = 1.0 - tmp * tmp * tmp;
+                    mu = mu * ((tmp >= 0.3333333334) ? tmp : 0.3333333334);
+                    nu = 2;
+                    if (pdp_eL2 - 2.0 * sqrt(p_eL2 * pdp_eL2) < (eps4_sq - 1.0) * p_eL2) stop = 4;
+                    memcpy(p, pdp, (size_t)ntot * sizeof(double));
+                    memcpy(e, hx, (size_t)nobs * sizeof(double));
+                    p_eL2 = pdp_eL2;
+                    break;
+                }
+            }
+            mu *= nu;
+            nu2 = (int)((unsigned)nu << 1);
+            if (nu2 <= nu) { stop = 6; break; }
+            nu = nu2;
+            if (!compat)                                         /* textbook LM: take the damping off again */
+                for (int64_t b = nfix; b < nblk; ++b)
+                    for (int r = 0; r < bs; ++r) H[b * bs * bs + r * bs + r] = diag[b * bs + r];
+        }
+        if (p_eL2 <= eps3_sq) stop = 5;
+    }
+    if (itno >= itmax) stop = 3;
+    if (info) {
+        tmp = DBL_MIN;
+        for (int64_t t = nfix * bs; t < nvars; ++t) if (tmp < diag[t]) tmp = diag[t];      /* restored diagonals (:1945-1962) */
+        info[0] = init_p_eL2; info[1] = p_eL2; info[2] = g_inf; info[3] = dp_L2; info[4] = mu / tmp;
+        info[5] = itno; info[6] = stop; info[7] = nfev; info[8] = njev; info[9] = nlss;
+    }
+    retval = (stop != 7) ? itno : -1;
+done:
+    free(H); free(g); free(dq); free(pdp); free(e); free(hx); free(diag);
+    vis_free(&vs);
+    return retval;
+}

@@ -71,3 +71,28 @@ def port_motstr(p, x, vmask, rot0, nccalib, ncdist, itmax=150, opts=None, ncon=0
     if cam_fix is not None:
         lib.orc_set_camera_fix(None, None)
     return p, info, ret
+
+
+def _blockdiag(which, p, x, vmask, rot0, nccalib, ncdist, itmax, opts, ncon, mcon, verbose, compat):
+    lib = load()
+    vmask = np.ascontiguousarray(vmask, dtype=np.int8); n, m = vmask.shape
+    p = np.array(p, dtype=np.float64, copy=True).ravel()
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel(); rot0 = np.ascontiguousarray(rot0, dtype=np.float64).ravel()
+    opts = np.ascontiguousarray([1e-3, 1e-12, 1e-12, 1e-12, 0.0] if opts is None else opts, dtype=np.float64)
+    info = np.zeros(10)
+    lib.orc_blockdiag.restype = ctypes.c_int
+    ret = lib.orc_blockdiag(ctypes.c_int(which), ctypes.c_int64(n), ctypes.c_int64(ncon), ctypes.c_int(m), ctypes.c_int(mcon), _p(vmask), _p(p),
+                            _p(rot0), _p(x), ctypes.c_int(nccalib), ctypes.c_int(ncdist), ctypes.c_int(itmax), ctypes.c_int(verbose), _p(opts),
+                            _p(info), ctypes.c_int(1 if compat else 0))
+    return p, info, ret
+
+
+def port_mot(p, x, vmask, rot0, nccalib, ncdist, itmax=150, opts=None, mcon=0, verbose=0, compat=True):
+    """Motion-only LM (sba_mot_levmar_x, sba_levmar.c:1437): p = [16 m | 3 n], only the cameras move.
+    Returns (p_new, info[10], retval)."""
+    return _blockdiag(0, p, x, vmask, rot0, nccalib, ncdist, itmax, opts, 0, mcon, verbose, compat)
+
+
+def port_str(p, x, vmask, rot0, itmax=150, opts=None, ncon=0, verbose=0, compat=True):
+    """Structure-only LM (sba_str_levmar_x, sba_levmar.c:1987): p = [16 m | 3 n], only the points move."""
+    return _blockdiag(1, p, x, vmask, rot0, 0, 0, itmax, opts, ncon, 0, verbose, compat)

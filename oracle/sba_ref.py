@@ -9,6 +9,8 @@ It drives the *unmodified* sba 1.6 + libsbaprojs binaries that oracle/build_ref.
 * ``ref_motstr``  -> ``sba_motstr_levmar_x``      (sba-1.6p/sba_levmar.c:449-1428, prototype sba.h:111-116)
   with the callbacks ``img_projsKDRTS_x`` / ``img_projsKDRTS_jac_x``
   (sba-1.6p/libsbaprojs/sbaprojs.c:1135-1184, 1193-1250) and ``struct globs_`` (sbaprojs.h:123-156).
+* ``ref_mot`` / ``ref_str`` -> ``sba_mot_levmar_x`` / ``sba_str_levmar_x`` (sba_levmar.c:1437, 1987) with the
+  ``img_projsKDRT_*`` / ``img_projsKDS_*`` callbacks.
 * ``ref_project`` / ``ref_jacobian`` call the two callbacks directly on a CRS index built the way
   sba_levmar.c:640-650 builds it, so the projection and the Jacobian can be compared in isolation.
 
@@ -89,7 +91,18 @@ def load():
         ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_int,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
-    for fn in (prj.img_projsKDRTS_x, prj.img_projsKDRTS_jac_x):
+    # motion-only / structure-only drivers (sba.h:118-130): no pnp (mot) / no cnp (str) argument, one fixed-count argument
+    sba.sba_mot_levmar_x.restype = ctypes.c_int
+    sba.sba_mot_levmar_x.argtypes = [
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p,
+        ctypes.POINTER(ctypes.c_double), ctypes.c_int,
+        ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_int,
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    sba.sba_str_levmar_x.restype = ctypes.c_int
+    sba.sba_str_levmar_x.argtypes = sba.sba_mot_levmar_x.argtypes
+    for fn in (prj.img_projsKDRTS_x, prj.img_projsKDRTS_jac_x, prj.img_projsKDRT_x, prj.img_projsKDRT_jac_x,
+               prj.img_projsKDS_x, prj.img_projsKDS_jac_x):
         fn.restype = None
         fn.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(Crsm),
                        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
@@ -153,6 +166,53 @@ def ref_motstr(p, x, vmask, rot0, nccalib, ncdist, itmax=150, opts=None, ncon=0,
         ctypes.cast(prj.img_projsKDRTS_x, ctypes.c_void_p), ctypes.cast(prj.img_projsKDRTS_jac_x, ctypes.c_void_p),
         ctypes.cast(ctypes.pointer(g), ctypes.c_void_p), int(itmax), int(verbose), _dptr(opts), _dptr(info))
     return p, info, ret
+
+
+def ref_mot(cams, pts, x, vmask, rot0, nccalib, ncdist, itmax=150, opts=None, mcon=0, verbose=0):
+    """Motion-only reference LM: ``sba_mot_levmar_x`` (sba-1.6p/sba_levmar.c:1437-1980) with the callbacks
+    ``img_projsKDRT_x`` / ``img_projsKDRT_jac_x`` (libsbaprojs/sbaprojs.c:1261-1370); the fixed points travel in
+    ``globs_.ptparams``.  ``cams`` (16 m) is updated on a copy.  Returns (cams_new, info[10], retval)."""
+    sba, prj = load()
+    vmask = np.ascontiguousarray(vmask, dtype=np.int8)
+    n, m = vmask.shape
+    cams = np.array(cams, dtype=np.float64, copy=True).ravel()
+    pts = np.ascontiguousarray(pts, dtype=np.float64).ravel()
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    rot0 = np.ascontiguousarray(rot0, dtype=np.float64).ravel()
+    assert cams.size == CNP * m and pts.size == PNP * n and rot0.size == 4 * m
+    opts = np.ascontiguousarray([1e-3, 1e-12, 1e-12, 1e-12, 0.0] if opts is None else opts, dtype=np.float64)
+    info = np.zeros(10, dtype=np.float64)
+    g = _globs(rot0, nccalib, ncdist)
+    g.ptparams = _dptr(pts)
+    ret = sba.sba_mot_levmar_x(
+        n, m, mcon, vmask.ctypes.data_as(ctypes.c_char_p), _dptr(cams), CNP, _dptr(x), None, MNP,
+        ctypes.cast(prj.img_projsKDRT_x, ctypes.c_void_p), ctypes.cast(prj.img_projsKDRT_jac_x, ctypes.c_void_p),
+        ctypes.cast(ctypes.pointer(g), ctypes.c_void_p), int(itmax), int(verbose), _dptr(opts), _dptr(info))
+    return cams, info, ret
+
+
+def ref_str(cams, pts, x, vmask, itmax=150, opts=None, ncon=0, verbose=0):
+    """Structure-only reference LM: ``sba_str_levmar_x`` (sba-1.6p/sba_levmar.c:1987-2540) with the callbacks
+    ``img_projsKDS_x`` / ``img_projsKDS_jac_x`` (libsbaprojs/sbaprojs.c:1375-1445).  The fixed cameras travel in
+    ``globs_.camparams``; these callbacks take entries 10:13 of a camera row as the vector part of its FULL rotation
+    quaternion (there is no rot0 on this path).  ``pts`` (3 n) is updated on a copy."""
+    sba, prj = load()
+    vmask = np.ascontiguousarray(vmask, dtype=np.int8)
+    n, m = vmask.shape
+    cams = np.ascontiguousarray(cams, dtype=np.float64).ravel()
+    pts = np.array(pts, dtype=np.float64, copy=True).ravel()
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    assert cams.size == CNP * m and pts.size == PNP * n
+    opts = np.ascontiguousarray([1e-3, 1e-12, 1e-12, 1e-12, 0.0] if opts is None else opts, dtype=np.float64)
+    info = np.zeros(10, dtype=np.float64)
+    rot0 = np.tile([1.0, 0.0, 0.0, 0.0], m)
+    g = _globs(rot0, 0, 0)
+    g.camparams = _dptr(cams)
+    ret = sba.sba_str_levmar_x(
+        n, ncon, m, vmask.ctypes.data_as(ctypes.c_char_p), _dptr(pts), PNP, _dptr(x), None, MNP,
+        ctypes.cast(prj.img_projsKDS_x, ctypes.c_void_p), ctypes.cast(prj.img_projsKDS_jac_x, ctypes.c_void_p),
+        ctypes.cast(ctypes.pointer(g), ctypes.c_void_p), int(itmax), int(verbose), _dptr(opts), _dptr(info))
+    return pts, info, ret
 
 
 def ref_project(p, vmask, rot0):

@@ -36,6 +36,12 @@ def golden_ba():
 
 
 @pytest.fixture(scope="session")
+def golden_bd():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "blockdiag_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_dlt():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "dlt_golden.npz"))
