@@ -227,20 +227,33 @@ class Information(object):
 
 
 def SparseBundleAdjust(cameras, points, options):
-    """Motion + structure bundle adjustment of ``cameras`` / ``points`` (sba_motstr_levmar_x with the KDRTS callbacks);
-    returns (newcameras, newpoints, info).  Inputs are not modified."""
+    """Bundle adjustment of ``cameras`` / ``points``; returns (newcameras, newpoints, info).  Inputs are not modified.
+    ``options.motstruct`` selects the driver as in the reference's demo (sba-1.6p/demo/eucsbademo.c:1560-1602):
+    OPTS_MOTSTRUCT (sba_motstr_levmar_x + KDRTS callbacks, what Argus uses), OPTS_MOT (cameras only, sba_mot_levmar_x + KDRT)
+    or OPTS_STRUCT (points only, sba_str_levmar_x + KDS)."""
     if options.camera != OPTS_CAMS:
         raise NotImplementedError("only the full Argus camera model (OPTS_CAMS: intrinsics + distortion + pose) is supported")
-    if options.motstruct != OPTS_MOTSTRUCT:
-        raise NotImplementedError("only simultaneous motion + structure adjustment is supported")
+    if options.motstruct not in (OPTS_MOTSTRUCT, OPTS_MOT, OPTS_STRUCT):
+        raise ValueError("options.motstruct must be OPTS_MOTSTRUCT, OPTS_MOT or OPTS_STRUCT")
     if points.ncameras != cameras.ncameras:
         raise ValueError("points were built for %d cameras, got %d" % (points.ncameras, cameras.ncameras))
     a, rot0 = cameras.pack()
     m, n = cameras.ncameras, points.n
-    p = np.concatenate([a.ravel(), points.B.ravel()])
-    pn, info, ret = _ba.solve_motstr(points.vmask, p, rot0.ravel(), points.X, options.nccalib, options.ncdist, itmax=options.maxIter,
-                                     opts=options.opts, ncon=options.ncon, mcon=options.mcon, verbose=options.verbose,
-                                     compat=options.compat_sba16)
+    common = dict(itmax=options.maxIter, opts=options.opts, verbose=options.verbose, compat=options.compat_sba16)
+    if options.motstruct == OPTS_MOT:
+        cams, info, ret = _ba.solve_mot(points.vmask, a.ravel(), points.B.ravel(), rot0.ravel(), points.X, options.nccalib, options.ncdist,
+                                        mcon=options.mcon, **common)
+        pn = np.concatenate([cams, points.B.ravel()])
+        nvars = 16 * m
+    elif options.motstruct == OPTS_STRUCT:
+        pts, info, ret = _ba.solve_str(points.vmask, points.B.ravel(), a.ravel(), rot0.ravel(), points.X, ncon=options.ncon, **common)
+        pn = np.concatenate([a.ravel(), pts])
+        nvars = 3 * n
+    else:
+        p = np.concatenate([a.ravel(), points.B.ravel()])
+        pn, info, ret = _ba.solve_motstr(points.vmask, p, rot0.ravel(), points.X, options.nccalib, options.ncdist, ncon=options.ncon,
+                                         mcon=options.mcon, **common)
+        nvars = 16 * m + 3 * n
     newcams = Cameras(Cameras.unpack(pn[:16 * m].reshape(m, 16), rot0))
     newpts = Points(pn[16 * m:].reshape(n, 3), points.vmask, points.X)
-    return newcams, newpts, Information(info, ret, points.X.shape[0], 16 * m + 3 * n)
+    return newcams, newpts, Information(info, ret, points.X.shape[0], nvars)

@@ -159,6 +159,49 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bench_blockdiag(torch, ba, stream, local, s, p0, rot0, m, nk, nd, steps, cpu_points):
+    """Motion-only / structure-only LM on the same scene: device-resident throughput by CUDA events and the
+    reference's sba_mot_levmar_x / sba_str_levmar_x on a bounded sample of the same scene (rank 0, N = 1)."""
+    out = {}
+    for mode, iters in (("mot", 10), ("str", 3)):
+        with torch.cuda.stream(stream):
+            B = ba.BundleAdjuster(device=local, stream=stream.cuda_stream, mode=mode)
+            B.upload(s["vmask"], p0, rot0, s["x"], nk, nd)
+            for _ in range(2):
+                B.reset(); ret, info = B.solve(itmax=iters, opts=OPTS_FIXED_WORK)
+            c0 = B.counters()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                B.reset(); ret, info = B.solve(itmax=iters, opts=OPTS_FIXED_WORK)
+                assert ret == iters and int(info[5]) == iters, (mode, ret, info)
+            e1.record(stream); e1.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            c1 = B.counters()
+            B.close()
+        out[mode] = {"obs_iters_per_sec": s["nobs"] * iters / (ms * 1e-3), "ms_per_iteration": ms / iters, "iters_per_step": iters,
+                     "linear_systems": int(info[9]), "gpu_launches": int(c1["launches"] - c0["launches"])}
+    if cpu_points:
+        from oracle import sba_ref, ba_port
+        vm, xs, ps = reference_sample(s, p0, m, cpu_points)
+        for mode, iters in (("mot", 10), ("str", 3)):
+            t0 = time.perf_counter()
+            if sba_ref.available() and mode == "mot":
+                _, iref, _ = sba_ref.ref_mot(ps[:16 * m], ps[16 * m:], xs, vm, rot0, nk, nd, itmax=iters, opts=OPTS_FIXED_WORK); kind = "reference"
+            elif sba_ref.available():
+                # the reference's structure-only callbacks read the full camera quaternion from the camera row (no rot0)
+                cf = ps[:16 * m].reshape(m, 16).copy(); q = np.asarray(rot0).reshape(m, 4); cf[:, 10:13] = q[:, 1:4] * np.sign(q[:, :1] + (q[:, :1] == 0))
+                _, iref, _ = sba_ref.ref_str(cf.ravel(), ps[16 * m:], xs, vm, itmax=iters, opts=OPTS_FIXED_WORK); kind = "reference"
+            else:
+                fn = ba_port.port_mot if mode == "mot" else ba_port.port_str
+                _, iref, _ = (fn(ps, xs, vm, rot0, nk, nd, itmax=iters, opts=OPTS_FIXED_WORK) if mode == "mot"
+                              else fn(ps, xs, vm, rot0, itmax=iters, opts=OPTS_FIXED_WORK)); kind = "port"
+            dt = time.perf_counter() - t0
+            out[mode]["cpu_baseline"] = {"value": int(vm.sum()) * int(iref[5]) / dt, "unit": "obs*iters/s", "cores": 1, "kind": kind,
+                                         "sample": "first %d points of the same scene, %d LM iterations, %.1f s" % (vm.shape[0], int(iref[5]), dt)}
+    return out
+
+
 def bench_dlt(torch, device, stream, steps, warmup, rank, world, hbm_peak):
     """BASELINE config 2 per rank: 1M frames x 4 cameras x 10 tracks; triangulation + reprojection error."""
     import ctypes
@@ -257,6 +300,7 @@ def main():
     ap.add_argument("--cpu-baseline-points", type=int, default=32768)
     ap.add_argument("--no-dlt", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-blockdiag", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -399,6 +443,10 @@ def main():
                          % (vm.shape[0], int(vm.sum()), m, ITERS_PER_STEP, dt_ref)}
 
     B.close()
+    bd_res = None
+    if not args.no_blockdiag and args.workload != "c5" and world == 1:
+        bd_res = bench_blockdiag(torch, ba, stream, local, s, p0, rot0, m, nk, nd, max(2, min(args.steps, 5)),
+                                 args.cpu_baseline_points if (rank == 0 and world == 1) else 0)
     dlt_res = None
     if not args.no_dlt:
         dlt_res = bench_dlt(torch, device, stream, max(3, min(args.steps, 10)), 3, rank, world, hbm_peak)
@@ -419,7 +467,7 @@ def main():
                 "convergence": conv,
                 "lm_iters_per_sec": ITERS_PER_STEP * args.steps / (ms_total * 1e-3),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(c1["launches"] - c0["launches"]),
-                "allreduces": int(c1["allreduces"] - c0["allreduces"]), "roofline": rl, "cpu_baseline": cpu, "dlt": dlt_res}
+                "allreduces": int(c1["allreduces"] - c0["allreduces"]), "roofline": rl, "cpu_baseline": cpu, "blockdiag": bd_res, "dlt": dlt_res}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -190,14 +190,17 @@ def test_full_size_properties_c3():
     assert info[1] / s0["nobs"] < 1e-12
 
 
-def test_m0_two_shards_equal_single(golden_ba):
+@pytest.mark.parametrize("mode", ["motstr", "mot", "str"])
+def test_m0_two_shards_equal_single(mode):
     """Multi-rank path on one GPU: two solver contexts (threads) exchange through the all-reduce hook; the result
-    equals the single-context run to rounding (M0)."""
+    equals the single-context run to rounding (M0) - for the full, the motion-only and the structure-only driver."""
     import torch
     s = scenes.make_ba_scene(6, 2000, 4, seed=77)
     m, n = 6, 2000
     p0, rot0 = scenes.pack_ba_problem(s["cams0"], s["pts0"])
-    p_ref, info_ref, ret_ref = ba.solve_motstr(s["vmask"], p0, rot0, s["x"], 2, 3, itmax=8)
+    B0 = ba.BundleAdjuster(mode=mode).upload(s["vmask"], p0, rot0, s["x"], 2, 3)
+    ret_ref, info_ref = B0.solve(itmax=8 if mode != "str" else 3)
+    p_ref = B0.download(); B0.close()
     world = 2
     rowptr = np.concatenate([[0], np.cumsum(s["vmask"].sum(axis=1).astype(np.int64))])
     barrier = threading.Barrier(world)
@@ -227,11 +230,11 @@ def test_m0_two_shards_equal_single(golden_ba):
 
     def run(rank):
         lo, hi = ba.shard_points(n, world, rank)
-        B = ba.BundleAdjuster()
+        B = ba.BundleAdjuster(mode=mode)
         B.set_comm(rank, world, make_hook(rank))
         p_loc = np.concatenate([p0[:16 * m], p0[16 * m + 3 * lo:16 * m + 3 * hi]])
         B.upload(s["vmask"][lo:hi], p_loc, rot0, s["x"][rowptr[lo]:rowptr[hi]], 2, 3)
-        ret, info = B.solve(itmax=8)
+        ret, info = B.solve(itmax=8 if mode != "str" else 3)
         results[rank] = (ret, info, B.download(), lo, hi)
         B.close()
 
@@ -244,6 +247,10 @@ def test_m0_two_shards_equal_single(golden_ba):
         p_sh[:16 * m] = p_loc[:16 * m]
         p_sh[16 * m + 3 * lo:16 * m + 3 * hi] = p_loc[16 * m:]
     assert rel_blocks(p_sh, p_ref, m) < 1e-9
+    if mode == "mot":
+        assert np.array_equal(p_sh[16 * m:], p0[16 * m:])
+    if mode == "str":
+        assert np.array_equal(p_sh[:16 * m], p0[:16 * m])
 
 
 def test_config5_shape_per_camera_fixed_intrinsics_and_outliers():

@@ -133,3 +133,30 @@ def test_full_size_properties():
     assert retm > 0 and infom[1] / (2 * s["nobs"]) < 0.5 and int(infom[6]) in (1, 2, 3, 4)
     cams2, infom2, _ = ba.solve_mot(s["vmask"], pm[:16 * m], pm[16 * m:], rot0m, s["x"], 0, 0, itmax=40)
     assert np.array_equal(cams, cams2) and list(infom) == list(infom2)
+
+
+def test_sba_module_mot_and_struct_modes(golden_bd):
+    """The python-sba style front end: options.motstruct = OPTS_MOT / OPTS_STRUCT reach the same drivers
+    (the reference's demo switches the same way, sba-1.6p/demo/eucsbademo.c:1560-1602)."""
+    from argus_gui_b200 import sba
+    g = golden_bd
+    p0, rot0 = g["M1_p0"], g["M1_rot0"].reshape(M, 4)
+    cams17 = sba.Cameras.unpack(p0[:16 * M].reshape(M, 16), rot0)
+    cameras = sba.Cameras.fromDylan(cams17)
+    points = sba.Points(p0[16 * M:].reshape(-1, 3), g["M1_vmask"], g["M1_x"])
+    opt = sba.Options.fromInput(cameras, points)
+    opt.camera = sba.OPTS_CAMS; opt.nccalib = sba.OPTS_FIX2_INTR; opt.ncdist = sba.OPTS_FIX3_DIST
+    opt.motstruct = sba.OPTS_MOT; opt.mcon = 1; opt.maxIter = 10
+    nc, npts, info = sba.SparseBundleAdjust(cameras, points, opt)
+    ref_i = g["M1b_info_it10"]
+    assert info.iterations == int(ref_i[5]) and info.linSystems == int(ref_i[9]) and abs(info.finalError - ref_i[1]) <= 1e-9 * ref_i[1]
+    assert np.array_equal(npts.B, points.B) and np.allclose(nc.arr[0], cameras.arr[0], rtol=1e-14, atol=1e-15)   # points and camera 0 fixed
+    a_ref = g["M1b_cams_it10"].reshape(M, 16)
+    assert np.abs(nc.arr[:, :10] - a_ref[:, :10]).max() <= 1e-8 * np.abs(a_ref[:, :10]).max()
+    assert np.abs(nc.arr[:, 14:] - a_ref[:, 13:]).max() <= 1e-8
+    opt.motstruct = sba.OPTS_STRUCT; opt.mcon = 0; opt.ncon = 17; opt.maxIter = 3
+    nc, npts, info = sba.SparseBundleAdjust(cameras, points, opt)
+    ref_i = g["S1b_info_it3"]
+    assert info.iterations == 3 and info.linSystems == int(ref_i[9]) and abs(info.finalError - ref_i[1]) <= 1e-10 * ref_i[1]
+    assert np.allclose(nc.arr, cameras.arr, rtol=1e-14, atol=1e-15)
+    assert np.abs(npts.B.ravel() - g["S1b_pts_it3"]).max() <= 1e-9 * np.abs(g["S1b_pts_it3"]).max()
