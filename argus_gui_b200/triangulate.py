@@ -1,20 +1,25 @@
 """Initial structure / pose estimate that feeds the bundle adjustment: same interface as
 /root/reference/argus_gui/triangulate.py (``multiTriangulator(pts, intrins).triangulate()`` -> xyz, attribute ``.ext``
-= m x 7 [qw qx qy qz tx ty tz], last camera = reference frame), host-side (OpenCV + numpy) - SURVEY.md section 8 lists it
-as "next" row f1; it runs once per calibration, outside the LM loop.
+= m x 7 [qw qx qy qz tx ty tz], last camera = reference frame).  SURVEY.md section 8 row f1: the per-point work of every
+camera pair runs on the GPU (C ABI ``argus_pair_triangulate``, csrc/pair_kernels.cu); the cross-pair rescale / average is numpy.
 
 Per camera k paired with the last (reference) camera (triangulate.py:27-212): undistort + normalise both pixel sets
 (cv2.undistortPoints, float32), 8-point fundamental matrix, SVD -> two candidate rotations x two baselines, two-view
 triangulation of every point for the forward and the inverse view, cheirality vote, sign of the baseline.  Across pairs the
 point clouds are rescaled to the first pair's mean range and nan-averaged (triangulate.py:292-307).
 """
+import ctypes
 import numpy as np
-import cv2
 
+from . import _lib
 from .sba import quaternions
 from .tools import ArgusError
 
 __all__ = ["gs", "Triangulator", "multiTriangulator"]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
 
 
 def gs(X, row_vecs=False, norm=True):
@@ -33,74 +38,43 @@ def gs(X, row_vecs=False, norm=True):
     return out if row_vecs else out.T
 
 
-def _triangulate_pairs(P_a, P_b, xa, xb):
-    """Batched two-view linear triangulation (what cv2.triangulatePoints does per point): for every point the null
-    vector of the 4x4 system [x P3 - P1; y P3 - P2] for both views, de-homogenised."""
-    n = xa.shape[0]
-    A = np.empty((n, 4, 4))
-    A[:, 0] = xa[:, 0:1] * P_a[2] - P_a[0]
-    A[:, 1] = xa[:, 1:2] * P_a[2] - P_a[1]
-    A[:, 2] = xb[:, 0:1] * P_b[2] - P_b[0]
-    A[:, 3] = xb[:, 1:2] * P_b[2] - P_b[1]
-    _, _, Vt = np.linalg.svd(A)
-    X = Vt[:, 3, :]
-    return X[:, :3] / X[:, 3:4]
-
-
 class Triangulator(object):
+    """One camera paired with the reference camera (triangulate.py:27-212).  ``triangulate()`` runs the whole pair on the GPU
+    (``argus_pair_triangulate``: undistortion, 8-point fundamental matrix, candidate poses, two-view triangulation of every
+    point under the four hypotheses, cheirality vote) and leaves ``R``, ``t`` like the reference."""
+
     def __init__(self, p1, p2, f1, f2, c1, c2, dist1, dist2):
         self.f1, self.f2, self.c1, self.c2 = f1, f2, c1, c2
         self.dist1, self.dist2 = dist1, dist2
         self.R = None
         self.t = None
-        self.p1 = self._normalize(p1, f1, c1, dist1)
-        self.p2 = self._normalize(p2, f2, c2, dist2)
+        self.F = None
+        self.p1 = np.ascontiguousarray(p1, dtype=np.float64).reshape(-1, 2)
+        self.p2 = np.ascontiguousarray(p2, dtype=np.float64).reshape(-1, 2)
 
-    @staticmethod
-    def _normalize(p, f, c, dist):
-        src = np.zeros((1, p.shape[0], 2), dtype=np.float32)
-        src[0] = p
-        K = np.asarray([[f, 0.0, c[0]], [0.0, f, c[1]], [0.0, 0.0, 1.0]])
-        return cv2.undistortPoints(src, K, np.asarray(dist, dtype=np.float64), P=None).reshape(-1, 2)
-
-    def getFundamentalMat(self):
-        return cv2.findFundamentalMat(self.p2, self.p1, method=cv2.FM_8POINT)[0]
+    def _profile(self, f, c, dist):
+        return np.ascontiguousarray(np.concatenate([[f, c[0], c[1]], np.asarray(dist, dtype=np.float64)[-5:]]), dtype=np.float64)
 
     def getQuaternion(self):
         if self.R is not None and self.R.any():
             return quaternions.quatFromRotationMatrix(gs(self.R)).asVector()
 
     def triangulate(self):
-        F = self.getFundamentalMat()
-        U, _, Vt = np.linalg.svd(F)
-        W = np.array([[0.0, -1.0, 0.0], [1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
-        t = U[:, 2]
-        cands = [U @ W.T @ Vt, U @ W @ Vt, U @ W.T @ (-Vt), U @ W @ (-Vt)]
-        Rs2 = cands[:2]
-        cnt = 0
-        for R in cands:                         # keep the proper rotations (det != -1), as the reference does
-            if np.round(np.linalg.det(R)) != -1:
-                Rs2[cnt] = R
-                cnt += 1
-        P1 = np.hstack([np.eye(3), np.zeros((3, 1))])
-        x1 = self.p1.astype(np.float64); x2 = self.p2.astype(np.float64)
-        outs, plusses = [], []
-        for R in Rs2:
-            P = np.hstack([R, t.reshape(3, 1)])
-            Pi = np.hstack([np.linalg.inv(R), (-t @ R).reshape(3, 1)])
-            out = _triangulate_pairs(P, P1, x1, x2)
-            out_ = _triangulate_pairs(P1, Pi, x1, x2)
-            outs += [out, out_]
-            plusses += [int(np.sum(np.where(out[:, 2] > 0, 1, -1))), int(np.sum(np.where(out_[:, 2] > 0, 1, -1)))]
-        if abs(plusses[0]) > abs(plusses[2]):
-            zdx = 0
-        elif abs(plusses[0]) < abs(plusses[2]):
-            zdx = 2
-        else:
-            zdx = 0 if abs(plusses[0] + plusses[1]) > abs(plusses[2] + plusses[3]) else 2
-        self.R = Rs2[zdx // 2]
-        self.t = t if plusses[zdx] < 0 else -t
-        return outs[zdx] * -1 * np.sign(plusses[zdx])
+        lib = _lib.load()
+        n = self.p1.shape[0]
+        if n < 8 or self.p2.shape[0] != n:
+            raise ArgusError("at least 8 point pairs seen by both cameras are needed")
+        xyz = np.empty((n, 3)); R = np.empty((3, 3)); t = np.empty(3); F = np.empty((3, 3))
+        pr1 = self._profile(self.f1, self.c1, self.dist1); pr2 = self._profile(self.f2, self.c2, self.dist2)
+        rc = lib.argus_pair_triangulate(_ptr(self.p1), _ptr(self.p2), n, _ptr(pr1), _ptr(pr2), _ptr(xyz), _ptr(R), _ptr(t), _ptr(F))
+        _lib.check(rc, "argus_pair_triangulate")
+        self.R, self.t, self.F = R, t, F
+        return xyz
+
+    def getFundamentalMat(self):
+        if self.F is None:
+            self.triangulate()
+        return self.F
 
 
 class multiTriangulator(object):

@@ -156,6 +156,15 @@ int  argus_dlt_reproj_error_dev(const double *d_xyz, const double *d_pts, int64_
 
 const char *argus_b200_version(void);
 
+/* ---- two-view initialisation (what feeds the bundle adjustment) ----
+ * One camera paired with the reference camera: Triangulator(p1, p2, f1, f2, c1, c2, dist1, dist2).triangulate() of
+ * argus_gui/triangulate.py:27-212 as one call.  p1 / p2: N x 2 pixel coordinates in camera k / in the reference camera (N >= 8,
+ * no NaN); prof1 / prof2: [f, cx, cy, k1, k2, p1, p2, k3].  Outputs: xyz (N x 3, in the reference camera's frame), R (3 x 3
+ * row-major, Triangulator.R before its Gram-Schmidt), t (3, Triangulator.t), F (3 x 3, optional, may be NULL: the 8-point
+ * fundamental matrix of cv2.findFundamentalMat(p2, p1, FM_8POINT)). */
+int argus_pair_triangulate(const double *p1, const double *p2, int64_t N, const double *prof1, const double *prof2,
+                           double *xyz, double *R, double *t, double *F);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,10 +9,13 @@ from argus_gui_b200 import sba, scenes, triangulate, ba
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_multitriangulator_golden():
+def test_multitriangulator_oracle_golden():
+    """The CPU restatement of triangulate.py (oracle/tri_port.py) against the output of the reference module itself; the
+    CUDA path is checked against both in tests/test_gpu_pair.py."""
+    from oracle import tri_port
     g = np.load(os.path.join(ROOT, "tests", "golden", "tri_golden.npz"))
     for tag in ("A", "B"):
-        t = triangulate.multiTriangulator(g[tag + "_pts"].copy(), g[tag + "_intr"])
+        t = tri_port.multiTriangulator(g[tag + "_pts"].copy(), g[tag + "_intr"])
         xyz = t.triangulate()
         ref = g[tag + "_xyz"]
         assert np.array_equal(np.isnan(xyz), np.isnan(ref))

@@ -9,7 +9,13 @@ from argus_gui_b200 import scenes, sbaDriver, sba
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_constructor_matches_reference_golden(tmp_path):
+@pytest.mark.parametrize("backend", ["oracle", pytest.param("cuda", marks=pytest.mark.gpu)])
+def test_constructor_matches_reference_golden(tmp_path, backend, monkeypatch):
+    """Host logic of the constructor (parse / count / rearrange / stacking) + the initial triangulation.  On CPU the
+    triangulator is the oracle's restatement (the product one needs the GPU); with a GPU the product path runs as shipped."""
+    if backend == "oracle":
+        from oracle import tri_port
+        monkeypatch.setattr(sbaDriver, "multiTriangulator", tri_port.multiTriangulator)
     g = np.load(os.path.join(ROOT, "tests", "golden", "driver_golden.npz"))
     ppts, uppts, cams = g["ppts"].copy(), g["uppts"].copy(), g["cams"].copy()
     d = sbaDriver.sbaArgusDriver(ppts, uppts, cams, display=False, scale=0.5, modeString="01", name=str(tmp_path / "x"), temp="", report=False)
