@@ -202,6 +202,31 @@ def bench_blockdiag(torch, ba, stream, local, s, p0, rot0, m, nk, nd, steps, cpu
     return out
 
 
+def bench_pair(rank):
+    """Two-view initialisation (Triangulator.triangulate of one camera pair): 1M point pairs through the host
+    API (argus_pair_triangulate: H2D, undistortion, 8-point F, 4 hypotheses x N two-view solves, vote, final cloud, D2H), and
+    the CPU restatement (vectorised numpy + OpenCV; the reference itself loops in Python) on a bounded sample."""
+    from argus_gui_b200 import scenes, triangulate
+    n = 1_000_000
+    s = scenes.make_ba_scene(2, n, 2, seed=5, radius=5.0)
+    dense = np.ascontiguousarray(s["x"].reshape(n, 4))
+    intr = s["cams_true"][:, :10]
+    mk = lambda mod, sl: mod.Triangulator(dense[sl, :2], dense[sl, 2:], intr[0, 0], intr[1, 0], intr[0, 1:3], intr[1, 1:3], intr[0, -5:], intr[1, -5:])
+    mk(triangulate, slice(0, n)).triangulate()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        mk(triangulate, slice(0, n)).triangulate()
+    dt = (time.perf_counter() - t0) / 3
+    out = {"points_per_sec": n / dt, "ms": 1e3 * dt, "sample": "%d point pairs, one camera pair, host API" % n}
+    if rank == 0:
+        from oracle import tri_port
+        ns = 50_000
+        t0 = time.perf_counter(); mk(tri_port, slice(0, ns)).triangulate(); dtc = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": ns / dtc, "unit": "points/s", "cores": 1, "kind": "port",
+                               "sample": "first %d point pairs (vectorised numpy + OpenCV restatement of triangulate.py), %.1f s" % (ns, dtc)}
+    return out
+
+
 def bench_dlt(torch, device, stream, steps, warmup, rank, world, hbm_peak):
     """BASELINE config 2 per rank: 1M frames x 4 cameras x 10 tracks; triangulation + reprojection error."""
     import ctypes
@@ -447,6 +472,7 @@ def main():
     if not args.no_blockdiag and args.workload != "c5" and world == 1:
         bd_res = bench_blockdiag(torch, ba, stream, local, s, p0, rot0, m, nk, nd, max(2, min(args.steps, 5)),
                                  args.cpu_baseline_points if (rank == 0 and world == 1) else 0)
+    pair_res = bench_pair(rank) if (not args.no_blockdiag and world == 1) else None
     dlt_res = None
     if not args.no_dlt:
         dlt_res = bench_dlt(torch, device, stream, max(3, min(args.steps, 10)), 3, rank, world, hbm_peak)
@@ -467,7 +493,7 @@ def main():
                 "convergence": conv,
                 "lm_iters_per_sec": ITERS_PER_STEP * args.steps / (ms_total * 1e-3),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(c1["launches"] - c0["launches"]),
-                "allreduces": int(c1["allreduces"] - c0["allreduces"]), "roofline": rl, "cpu_baseline": cpu, "blockdiag": bd_res, "dlt": dlt_res}
+                "allreduces": int(c1["allreduces"] - c0["allreduces"]), "roofline": rl, "cpu_baseline": cpu, "blockdiag": bd_res, "pair_init": pair_res, "dlt": dlt_res}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
