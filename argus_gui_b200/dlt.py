@@ -97,3 +97,19 @@ def bootstrap_sd(pts, rmses, prof, dlt, bs_iter=250, noise=None, seed=0):
                                  _ptr(noise) if noise is not None else None, ctypes.c_uint64(int(seed)), _ptr(sd))
     _lib.check(rc, "argus_dlt_bootstrap")
     return sd
+
+
+def fit(xyz, uv, both_coordinates=False):
+    """Least-squares 11-parameter DLT fit of one camera (argus_dlt_fit): xyz N x 3, uv N x 2 (NaN = not seen) ->
+    (L (11,), errors (N,; NaN where skipped), (n_used, sum, mean, std))."""
+    lib = _lib.load()
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64); uv = np.ascontiguousarray(uv, dtype=np.float64)
+    if xyz.ndim != 2 or xyz.shape[1] != 3 or uv.shape != (xyz.shape[0], 2):
+        raise ValueError("xyz must be N x 3 and uv N x 2")
+    N = xyz.shape[0]
+    L = np.empty(11); err = np.empty(N); stats = np.empty(4)
+    rc = lib.argus_dlt_fit(_ptr(xyz), _ptr(uv), N, 1 if both_coordinates else 0, _ptr(L), _ptr(err), _ptr(stats))
+    if rc == _lib.ARGUS_E_SBA:
+        raise ArithmeticError("argus_dlt_fit: rank-deficient system (the points seen by this camera do not span 3-D space)")
+    _lib.check(rc, "argus_dlt_fit")
+    return L, err, (int(stats[0]), float(stats[1]), float(stats[2]), float(stats[3]))

@@ -26,6 +26,7 @@ import numpy as np
 import pandas
 
 from . import sba
+from . import dlt as _dlt
 from .tools import undistort_pts
 from .triangulate import multiTriangulator
 
@@ -306,16 +307,11 @@ class WandResults(object):
     def getCoefficients(self, xyz, uv, cam_index=0):
         uv = np.asarray(uv, dtype=np.float64)
         idx = np.nonzero(~np.isnan(uv[:, 0]))[0]
-        X = xyz[idx]; n = len(idx)
-        A = np.zeros((2 * n, 11)); B = np.zeros((2 * n, 1))
-        A[0::2, 0:3] = X; A[0::2, 3] = 1; A[0::2, 8:] = X * -uv[idx, 0:1]
-        A[1::2, 4:7] = X; A[1::2, 7] = 1; A[1::2, 8:] = X * -uv[idx, 1:2]
-        B[0::2, 0] = uv[idx, 0]; B[1::2, 0] = uv[idx, 1]
-        L = np.linalg.lstsq(A, B, rcond=None)[0]
-        den = X @ L[8:11, 0] + 1.0
-        rec = np.stack([(X @ L[0:3, 0] + L[3, 0]) / den, (X @ L[4:7, 0] + L[7, 0]) / den], axis=1)
-        errors = np.sqrt(((rec - uv[idx]) ** 2).sum(axis=1))
-        merr, stderr = np.mean(errors), np.std(errors)
+        n = len(idx)
+        # least squares + reprojection distances on the GPU (argus_dlt_fit); the index bookkeeping below stays on the host
+        Lv, err_all, (n_used, esum, merr, stderr) = _dlt.fit(np.asarray(xyz, dtype=np.float64), uv)
+        L = Lv.reshape(11, 1)
+        errors = err_all[idx]
         camera_number = (self.order[cam_index] + 1) if self.order is not None else cam_index + 1
         pb_1 = len(self.indices['paired'][0]) if self.indices['paired'] is not None else -1
         upidx = np.hstack(self.indices['unpaired']) if self.indices['unpaired'] is not None else None
@@ -338,7 +334,7 @@ class WandResults(object):
                         outliers.append(dict(base, frame=int(upidx[j]) + 1, kind='unpaired', paired_point=None, unpaired_track=t))
                         break
                     acc += len(lst)
-        rmse = float(errors.sum() / float(n)) if n else float('nan')
+        rmse = float(esum / float(n)) if n else float('nan')
         return L, rmse, outliers, ptsi
 
     def writePoints(self, p1, p2):

@@ -4,7 +4,8 @@ the per-frame Python loops of the reference are replaced by the batched CUDA ker
     uv_to_xyz(pts, profs, dlt)            tools.py:296-337   -> argus_dlt_triangulate
     get_repo_errors(xyzs, pts, prof, dlt) tools.py:360-423   -> argus_dlt_reproj_error
     undistort_pts(pts, prof)              tools.py:129-148   -> argus_undistort_points   (pinhole profiles)
-    reconstruct_uv(L, xyz), dlt_inverse(L, xyz), normalize(pts, prof), solve_dlt(xyz, uv)   (host numpy, not hot)
+    solve_dlt(xyz, uv)                    tools.py:220-280   -> argus_dlt_fit
+    reconstruct_uv(L, xyz), dlt_inverse(L, xyz), normalize(pts, prof)   (host numpy, not hot)
 
 Only pinhole profiles (list / ndarray) are supported; the omnidirectional model objects of the external ``argus.ocam``
 package are out of scope."""
@@ -77,7 +78,7 @@ def normalize(pts, prof):
 
 
 def solve_dlt(xyz, uv):
-    """11-parameter DLT fit (tools.py:220-280): returns (L (11 x 1), mean reprojection distance)."""
+    """11-parameter DLT fit (tools.py:220-280) on the GPU (argus_dlt_fit): returns (L (11 x 1), mean reprojection distance)."""
     if type(xyz) != np.ndarray or type(uv) != np.ndarray:
         raise ArgusError("uv and xyz must be numpy arrays")
     if xyz.ndim != 2 or uv.ndim != 2:
@@ -88,17 +89,8 @@ def solve_dlt(xyz, uv):
         raise ArgusError("xyz must be an Nx3 array")
     if uv.shape[1] != 2:
         raise ArgusError("uv must be an Nx2 array")
-    keep = ~np.isnan(uv).any(axis=1)
-    xyz, uv = xyz[keep], uv[keep]
-    n = xyz.shape[0]
-    A = np.zeros((2 * n, 11)); B = np.zeros((2 * n, 1))
-    A[0::2, 0:3] = xyz; A[0::2, 3] = 1.0; A[0::2, 8:11] = -xyz * uv[:, 0:1]
-    A[1::2, 4:7] = xyz; A[1::2, 7] = 1.0; A[1::2, 8:11] = -xyz * uv[:, 1:2]
-    B[0::2, 0] = uv[:, 0]; B[1::2, 0] = uv[:, 1]
-    L = np.linalg.lstsq(A, B, rcond=None)[0]
-    rec = dlt_inverse(L[:, 0], xyz)
-    rmse = float(np.sqrt(((rec - uv) ** 2).sum(axis=1)).sum() / float(n)) if n else float("nan")
-    return L, rmse
+    L, _, (n, total, _, _) = _dlt.fit(xyz, uv, both_coordinates=True)        # rows with a NaN in uv are skipped (tools.py:233-240)
+    return L.reshape(11, 1), (total / float(n) if n else float("nan"))
 
 
 def _check_cams(pts, profs, dlt):

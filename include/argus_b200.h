@@ -165,6 +165,14 @@ const char *argus_b200_version(void);
 int argus_pair_triangulate(const double *p1, const double *p2, int64_t N, const double *prof1, const double *prof2,
                            double *xyz, double *R, double *t, double *F);
 
+/* ---- 11-parameter DLT fit of one camera (the step after the bundle adjustment) ----
+ * tools.solve_dlt (argus_gui/tools.py:220-280) / OutlierWindow.getCoefficients (argus_gui/sbaDriver.py:1027-1075):
+ * xyz (N x 3), uv (N x 2 undistorted pixels; NaN in u - or, with flags & 1, in u or v - skips the point),
+ * L (11) = least-squares DLT coefficients, errors (N, optional, may be NULL): reprojection distance of every used point
+ * (NaN for skipped ones), stats = {points used, sum of distances, mean, population standard deviation}.
+ * Returns ARGUS_E_SBA when the system is rank deficient. */
+int argus_dlt_fit(const double *xyz, const double *uv, int64_t N, int flags, double *L, double *errors, double *stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,3 +138,22 @@ def bootstrap_sd(pts, rmses, prof, dlt, noise):
             sd[sd == 0] = np.nan
             ret[:, t * 3:(t + 1) * 3] = sd
     return ret
+
+
+def solve_dlt(xyz, uv, both_coordinates=True):
+    """tools.solve_dlt (tools.py:220-280; rows with a NaN in uv dropped) / OutlierWindow.getCoefficients
+    (sbaDriver.py:1027-1075; rows with a NaN in u dropped): numpy lstsq on the 2n x 11 system, reprojection distances.
+    -> (L (11,), errors over the used rows, used-row indices)."""
+    xyz = np.asarray(xyz, dtype=np.float64); uv = np.asarray(uv, dtype=np.float64)
+    keep = ~np.isnan(uv).any(axis=1) if both_coordinates else ~np.isnan(uv[:, 0])
+    idx = np.nonzero(keep)[0]
+    X, w = xyz[idx], uv[idx]
+    n = len(idx)
+    A = np.zeros((2 * n, 11)); B = np.zeros((2 * n, 1))
+    A[0::2, 0:3] = X; A[0::2, 3] = 1.0; A[0::2, 8:11] = -X * w[:, 0:1]
+    A[1::2, 4:7] = X; A[1::2, 7] = 1.0; A[1::2, 8:11] = -X * w[:, 1:2]
+    B[0::2, 0] = w[:, 0]; B[1::2, 0] = w[:, 1]
+    L = np.linalg.lstsq(A, B, rcond=None)[0][:, 0]
+    den = X @ L[8:11] + 1.0
+    rec = np.stack([(X @ L[0:3] + L[3]) / den, (X @ L[4:7] + L[7]) / den], axis=1)
+    return L, np.sqrt(((rec - w) ** 2).sum(axis=1)), idx

@@ -60,3 +60,18 @@ def test_bootstrap_sd_golden():
     assert np.array_equal(np.isnan(ci), np.isnan(g["ci"]))
     ok = ~np.isnan(g["ci"])
     assert np.abs(ci[ok] - g["ci"][ok]).max() <= 1e-12 * np.abs(g["ci"][ok]).max()
+
+
+def test_oracle_solve_dlt_golden():
+    """numpy restatement of the per-camera DLT fit against golden output of the reference's OutlierWindow.getCoefficients
+    (tests/golden/make_fit_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fit_golden.npz"))
+    for tag in ("A", "B", "C"):
+        for j in range(3):
+            k = "%s%d" % (tag, j)
+            L, err, idx = dlt_port.solve_dlt(g[k + "_xyz"], g[k + "_uv"], both_coordinates=False)
+            assert np.abs(L - g[k + "_L"]).max() <= 1e-12 * np.abs(g[k + "_L"]).max()
+            assert abs(err.mean() - float(g[k + "_rmse"])) <= 1e-9 * float(g[k + "_rmse"]) + 1e-12
+            if tag != "B":
+                assert list(idx[err >= 3 * err.std() + err.mean()]) == list(g[k + "_flagged"])
