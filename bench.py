@@ -224,6 +224,25 @@ def bench_pair(rank):
         t0 = time.perf_counter(); mk(tri_port, slice(0, ns)).triangulate(); dtc = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": ns / dtc, "unit": "points/s", "cores": 1, "kind": "port",
                                "sample": "first %d point pairs (vectorised numpy + OpenCV restatement of triangulate.py), %.1f s" % (ns, dtc)}
+    # per-camera DLT fit + reprojection distances (tools.solve_dlt / getCoefficients), 2M points, host API
+    from argus_gui_b200 import dlt as dlt_host
+    nf = 2_000_000
+    sc = scenes.make_dlt_scene(nf, m=2, ntracks=1, seed=9, nan_frac=0.0)
+    xyz = sc["xyz_true"].reshape(nf, 3); L0 = sc["dlt"][0]
+    den = xyz @ L0[8:11] + 1.0
+    uv = np.stack([(xyz @ L0[0:3] + L0[3]) / den, (xyz @ L0[4:7] + L0[7]) / den], axis=1) + np.random.default_rng(1).normal(0, 0.5, (nf, 2))
+    dlt_host.fit(xyz, uv)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        dlt_host.fit(xyz, uv)
+    dtf = (time.perf_counter() - t0) / 3
+    out["dlt_fit"] = {"points_per_sec": nf / dtf, "ms": 1e3 * dtf, "sample": "%d points, one camera, host API (H2D + QR tree + distances + D2H)" % nf}
+    if rank == 0:
+        from oracle import dlt_port
+        ns = 200_000
+        t0 = time.perf_counter(); dlt_port.solve_dlt(xyz[:ns], uv[:ns]); dtc = time.perf_counter() - t0
+        out["dlt_fit"]["cpu_baseline"] = {"value": ns / dtc, "unit": "points/s", "cores": os.cpu_count(), "kind": "port",
+                                          "sample": "first %d points, numpy lstsq (vectorised; the reference fills the matrix in a Python loop), %.1f s" % (ns, dtc)}
     return out
 
 
