@@ -289,19 +289,21 @@ __global__ void k_assemble(int m, int mcon, const double *__restrict__ Ured, con
 // reference then increases the damping, sba_levmar.c:1201-1210).  S is overwritten.
 constexpr int kCholNB = 32;
 constexpr int kCholThreads = 512;
-__global__ void __launch_bounds__(kCholThreads) k_chol_solve(double *__restrict__ S, const double *__restrict__ E, double *__restrict__ x, int N,
+// NB = panel width: 32 by default; 16 for systems whose 32-wide panel would not fit in shared memory (N > 864, i.e. 55..64 free cameras)
+template <int NB>
+__global__ void __launch_bounds__(kCholThreads) k_chol_solve_t(double *__restrict__ S, const double *__restrict__ E, double *__restrict__ x, int N,
                                                              int *__restrict__ status)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *P = reinterpret_cast<double *>(smem_raw);          // N x 33 panel (also the running rhs later)
-    __shared__ double D[kCholNB][kCholNB + 1];
-    __shared__ double ys[kCholNB];
+    __shared__ double D[NB][NB + 1];
+    __shared__ double ys[NB];
     __shared__ int fail;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) fail = 0;
     __syncthreads();
-    for (int kb = 0; kb < N; kb += kCholNB) {
-        const int nb = min(kCholNB, N - kb);
+    for (int kb = 0; kb < N; kb += NB) {
+        const int nb = min(NB, N - kb);
         // (1) diagonal block (lower triangle, row r >= col c)
         for (int t = tid; t < nb * nb; t += blockDim.x) { const int r = t / nb, c = t % nb; D[r][c] = S[(int64_t)(kb + r) * N + kb + c]; }
         __syncthreads();
@@ -327,14 +329,14 @@ __global__ void __launch_bounds__(kCholThreads) k_chol_solve(double *__restrict_
         const int r0 = kb + nb, R = N - r0;
         for (int i = tid; i < R; i += blockDim.x) {
             double *row = S + (int64_t)(r0 + i) * N + kb;
-            double *pr = P + i * 33;
+            double *pr = P + i * (NB + 1);
             for (int c = 0; c < nb; ++c) {
                 double s = row[c];
                 for (int q = 0; q < c; ++q) s -= pr[q] * D[c][q];
                 s /= D[c][c];
                 pr[c] = s; row[c] = s;
             }
-            for (int c = nb; c < kCholNB; ++c) pr[c] = 0.0;
+            for (int c = nb; c < NB; ++c) pr[c] = 0.0;
         }
         __syncthreads();
         // (3) trailing update of the lower triangle: 4x4 register tiles
@@ -348,10 +350,10 @@ __global__ void __launch_bounds__(kCholThreads) k_chol_solve(double *__restrict_
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
             const int i0 = 4 * ti, j0 = 4 * tj;
-            for (int c = 0; c < kCholNB; ++c) {
+            for (int c = 0; c < NB; ++c) {
                 double pi[4], pj[4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) { pi[a] = (i0 + a < R) ? P[(i0 + a) * 33 + c] : 0.0; pj[a] = (j0 + a < R) ? P[(j0 + a) * 33 + c] : 0.0; }
+                for (int a = 0; a < 4; ++a) { pi[a] = (i0 + a < R) ? P[(i0 + a) * (NB + 1) + c] : 0.0; pj[a] = (j0 + a < R) ? P[(j0 + a) * (NB + 1) + c] : 0.0; }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -372,8 +374,8 @@ __global__ void __launch_bounds__(kCholThreads) k_chol_solve(double *__restrict_
     double *rhs = P;
     for (int i = tid; i < N; i += blockDim.x) rhs[i] = E[i];
     __syncthreads();
-    for (int kb = 0; kb < N; kb += kCholNB) {
-        const int nb = min(kCholNB, N - kb);
+    for (int kb = 0; kb < N; kb += NB) {
+        const int nb = min(NB, N - kb);
         if (warp == 0) {      // warp 0 solves the diagonal block
             double b = (lane < nb) ? rhs[kb + lane] : 0.0;
             for (int j = 0; j < nb; ++j) {
@@ -394,8 +396,8 @@ __global__ void __launch_bounds__(kCholThreads) k_chol_solve(double *__restrict_
         __syncthreads();
     }
     // backward substitution L^T x = y
-    for (int kb = ((N - 1) / kCholNB) * kCholNB; kb >= 0; kb -= kCholNB) {
-        const int nb = min(kCholNB, N - kb);
+    for (int kb = ((N - 1) / NB) * NB; kb >= 0; kb -= NB) {
+        const int nb = min(NB, N - kb);
         if (warp == 0) {
             double b = (lane < nb) ? rhs[kb + lane] : 0.0;
             for (int j = nb - 1; j >= 0; --j) {

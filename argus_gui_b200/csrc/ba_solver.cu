@@ -320,11 +320,13 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
     }
     {
         ProfScope ps(c, P_CHOL);
-        size_t rows = (size_t)(N > 32 ? N - 32 : 1);
-        size_t sm = rows * 33 * sizeof(double);
+        const int nbw = (N > 864) ? 16 : 32;                   // panel width: the 32-wide panel of N > 864 exceeds the shared memory of one SM
+        size_t rows = (size_t)(N > nbw ? N - nbw : 1);
+        size_t sm = rows * (nbw + 1) * sizeof(double);
         if (sm < (size_t)N * sizeof(double)) sm = (size_t)N * sizeof(double);
         if (c->gen >= 3 && N <= 832) k_chol_solve2<<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->cholwork.p, c->flags.p + 1);
-        else k_chol_solve<<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->flags.p + 1);
+        else if (nbw == 32) k_chol_solve_t<32><<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->flags.p + 1);
+        else k_chol_solve_t<16><<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->flags.p + 1);
     }
     {
         ProfScope ps(c, P_BACKSUB);
@@ -547,7 +549,8 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
     memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_n, 0, sizeof(c->prof_n));
     // opt in to large dynamic shared memory where needed
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve_t<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
+    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve_t<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, 214000));
     if (const char *e = getenv("ARGUS_BA_GEN")) c->gen = atoi(e);
     {

@@ -286,3 +286,54 @@ def test_earlier_kernel_generations_still_agree(gen, golden_ba, monkeypatch):
     assert list(info[5:]) == list(rinfo[5:]) and abs(info[1] - rinfo[1]) <= 1e-10 * rinfo[1]
     p2, info2, _ = ba.solve_motstr(g["G2_vmask"], g["G2_p0"], g["G2_rot0"], g["G2_x"], 0, 0, itmax=6, opts=g["G2_opts"], mcon=1)
     assert list(info2[5:]) == list(g["G2_info_it6"][5:])
+
+
+def _subset(s, keep):
+    """Scene restricted to the visibility entries where ``keep`` is non-zero: (vmask, x)."""
+    vm = s["vmask"]
+    idx = np.cumsum(vm.ravel()).reshape(vm.shape) - 1
+    vm2 = (vm != 0) & (keep != 0)
+    return vm2.astype(np.uint8), s["x"][idx[vm2]]
+
+
+def test_unobserved_points_and_cameras():
+    """Rows / columns of the visibility mask that are entirely zero (a point nobody sees, a camera that sees nothing): their
+    blocks are just mu I (sba_levmar.c:992-1001), parameters must not move, the rest must follow the oracle."""
+    m, n = 5, 600
+    s = scenes.make_ba_scene(m, n, 4, seed=12)
+    keep = np.ones_like(s["vmask"])
+    keep[[0, 17, 18, 599]] = 0            # unobserved points, first / last / adjacent
+    keep[:, 2] = 0                        # camera 2 sees nothing
+    vm, x = _subset(s, keep)
+    p0, rot0 = scenes.pack_ba_problem(s["cams0"], s["pts0"])
+    po, io, ro = ba_port.port_motstr(p0, x, vm, rot0, 2, 3, itmax=6)
+    pg, ig, rg = ba.solve_motstr(vm, p0, rot0, x, 2, 3, itmax=6)
+    assert ro == rg and list(io[5:]) == list(ig[5:]) and abs(io[1] - ig[1]) <= 1e-9 * io[1]
+    assert rel_blocks(pg, po, m) < 1e-7
+    assert np.array_equal(pg[32:48], p0[32:48])                               # camera 2: zero gradient, no motion
+    for i in (0, 17, 18, 599):
+        assert np.array_equal(pg[16 * m + 3 * i:16 * m + 3 * i + 3], p0[16 * m + 3 * i:16 * m + 3 * i + 3])
+
+
+def test_sixty_four_cameras():
+    """The visibility bit mask holds at most 64 cameras: the largest supported camera count against the oracle."""
+    m, n = 64, 700
+    s = scenes.make_ba_scene(m, n, 9, seed=64)
+    p0, rot0 = scenes.pack_ba_problem(s["cams0"], s["pts0"])
+    po, io, ro = ba_port.port_motstr(p0, s["x"], s["vmask"], rot0, 5, 5, itmax=3)
+    pg, ig, rg = ba.solve_motstr(s["vmask"], p0, rot0, s["x"], 5, 5, itmax=3)
+    assert ro == rg and list(io[5:]) == list(ig[5:]) and abs(io[1] - ig[1]) <= 1e-9 * io[1]
+    assert rel_blocks(pg, po, m) < 1e-7
+
+
+@pytest.mark.parametrize("ncon,mcon", [(400, 0), (0, 3), (399, 3)])
+def test_almost_everything_fixed(ncon, mcon):
+    """ncon = n (every point fixed), mcon = m - 1 (one free camera) and both at once."""
+    m, n = 4, 400
+    s = scenes.make_ba_scene(m, n, 4, seed=33)
+    p0, rot0 = scenes.pack_ba_problem(s["cams0"], s["pts0"])
+    po, io, ro = ba_port.port_motstr(p0, s["x"], s["vmask"], rot0, 0, 0, itmax=5, ncon=ncon, mcon=mcon)
+    pg, ig, rg = ba.solve_motstr(s["vmask"], p0, rot0, s["x"], 0, 0, itmax=5, ncon=ncon, mcon=mcon)
+    assert ro == rg and list(io[5:]) == list(ig[5:]) and abs(io[1] - ig[1]) <= 1e-9 * io[1]
+    assert rel_blocks(pg, po, m) < 1e-7
+    assert np.array_equal(pg[:16 * mcon], p0[:16 * mcon]) and np.array_equal(pg[16 * m:16 * m + 3 * ncon], p0[16 * m:16 * m + 3 * ncon])
