@@ -152,3 +152,28 @@ def test_bootstrap_device_rng_statistics():
     assert np.median(np.abs(a[ok] / b[ok] - 1)) < 0.03              # two seeds, 4000 draws each: ~1.6 % standard error
     assert np.median(np.abs(a[ok] / c[ok] - 1)) < 0.08              # vs 400 explicit numpy draws: ~3.5 %
     assert not np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("m,k", [(2, 1), (3, 5), (8, 2), (12, 1), (16, 3), (17, 2), (40, 1), (64, 1)])
+def test_camera_count_paths_vs_oracle(m, k):
+    """Every kernel variant: fused <4>, <8>, <16> and the two-kernel path for more than 16 cameras, up to the 64-camera limit;
+    the fused call equals the two separate calls bit for bit in all of them."""
+    N = 120
+    d = scenes.make_dlt_scene(N, m=m, ntracks=k, seed=100 + m, nan_frac=0.25)
+    pts = d["pts"]
+    xyz, err = dlt.reconstruct(pts, d["prof"], d["dlt"])
+    x1 = dlt.triangulate(pts, d["prof"], d["dlt"]); e1 = dlt.reproj_error(x1, pts, d["prof"], d["dlt"])
+    assert np.array_equal(xyz, x1, equal_nan=True) and np.array_equal(err, e1, equal_nan=True)
+    for t in range(k):
+        sl = pts[:, t * 2 * m:(t + 1) * 2 * m]
+        xo = dlt_port.uv_to_xyz(sl, d["prof"], d["dlt"])
+        assert np.array_equal(np.isnan(xo), np.isnan(xyz[:, 3 * t:3 * t + 3]))
+        ok = ~np.isnan(xo)
+        assert np.abs(xyz[:, 3 * t:3 * t + 3][ok] - xo[ok]).max() <= 1e-9 * np.abs(xo[ok]).max()
+    eo = dlt_port.get_repo_errors(xyz, pts, d["prof"], d["dlt"])
+    ok = ~np.isnan(eo)
+    assert np.array_equal(np.isnan(eo), np.isnan(err)) and np.abs(err[ok] - eo[ok]).max() <= 1e-9 * np.abs(eo[ok]).max()
+    if m == 64:
+        with pytest.raises(ValueError):
+            d65 = scenes.make_dlt_scene(4, m=65, ntracks=1, seed=1)
+            dlt.triangulate(d65["pts"], d65["prof"], d65["dlt"])
