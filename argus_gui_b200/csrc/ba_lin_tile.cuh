@@ -468,9 +468,9 @@ __global__ void __launch_bounds__(128) k_backsub_recompute(BaProblem pb, double 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);          // old cameras
     CamConst *sn = sc + pb.m;                                        // trial cameras
-    double *das = reinterpret_cast<double *>(sn + pb.m);             // 16 m
+    double *das = reinterpret_cast<double *>(sn + pb.m);             // m rows of 17 (16 + 1 pad: lanes with different cameras hit different banks)
     __shared__ double red[32];
-    for (int t = threadIdx.x; t < 16 * pb.m; t += blockDim.x) das[t] = da[t];
+    for (int t = threadIdx.x; t < 16 * pb.m; t += blockDim.x) das[(t >> 4) * 17 + (t & 15)] = da[t];
     for (int j = threadIdx.x; j < pb.m; j += blockDim.x) { cam_precompute(cam + 16 * j, pb.rot0 + 4 * j, sc[j]); cam_precompute(cam_new + 16 * j, pb.rot0 + 4 * j, sn[j]); }
     __syncthreads();
     double cost = 0.0, dbsq = 0.0, dl = 0.0;
@@ -486,13 +486,9 @@ __global__ void __launch_bounds__(128) k_backsub_recompute(BaProblem pb, double 
             for (int k = k0; k < k1; ++k) {
                 const int j = pb.obs_cam[k];
                 if (j < pb.mcon) continue;
-                double u, v, A[32], B[6];
+                double B[6], s0, s1;
                 const int nfk = pb.cam_fix ? pb.cam_fix[2 * j] : pb.nfix_k, nfd = pb.cam_fix ? pb.cam_fix[2 * j + 1] : pb.nfix_d;
-                cam_project_jac(sc[j], M0, M1, M2, nfk, nfd, u, v, A, B);
-                const double *dj = das + 16 * j;
-                double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-                for (int r = 0; r < 16; ++r) { s0 += A[r] * dj[r]; s1 += A[16 + r] * dj[r]; }
+                cam_step_dir(sc[j], M0, M1, M2, nfk, nfd, das + 17 * j, s0, s1, B);        // (A_ij da_j, B_ij) without forming A_ij
                 t0 -= B[0] * s0 + B[3] * s1; t1 -= B[1] * s0 + B[4] * s1; t2 -= B[2] * s0 + B[5] * s1;
             }
             const double *Ni = Vinv + 6 * i;

@@ -332,7 +332,7 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
         ProfScope ps(c, P_BACKSUB);
         k_cam_update<<<1, 256, 0, c->stream>>>(m, mcon, c->cam.p, c->da_free.p, c->red1.p, mu, c->cam_new.p, c->da_full.p, c->cam2.p);
         if (c->gen >= 3) {
-            const size_t sm = 2 * cam_smem(m) + (size_t)m * 16 * sizeof(double);
+            const size_t sm = 2 * cam_smem(m) + (size_t)m * 17 * sizeof(double);
             k_backsub_recompute<<<c->grid_pts128, 128, sm, c->stream>>>(c->problem(), mu, c->cam.p, c->cam_new.p, c->da_full.p, c->pts.p,
                                                                        c->Vinv.p, c->eb.p, c->pts_new.p, dbout, c->part3.p);
         } else {
@@ -408,7 +408,7 @@ int run_bd_attempt(argus_ba_ctx *c, double mu, double mu_diag)
         ARGUS_CUDA_CHECK(cudaMemsetAsync(c->da_full.p, 0, 16 * m * sizeof(double), c->stream));
         ARGUS_CUDA_CHECK(cudaMemsetAsync(c->cam2.p, 0, 2 * sizeof(double), c->stream));
         k_str_invert<<<(unsigned)((c->n + 255) / 256), 256, 0, c->stream>>>(c->n, c->ncon, mu_diag, c->V.p, c->Vinv.p, c->flags.p);
-        const size_t sm = 2 * cam_smem(m) + (size_t)m * 16 * sizeof(double);
+        const size_t sm = 2 * cam_smem(m) + (size_t)m * 17 * sizeof(double);
         k_backsub_recompute<<<c->grid_pts128, 128, sm, c->stream>>>(c->problem(), mu, c->cam.p, c->cam.p, c->da_full.p, c->pts.p, c->Vinv.p,
                                                                    c->eb.p, c->pts_new.p, nullptr, c->part3.p);
         k_reduce_sum<<<1, 32, 0, c->stream>>>(c->part3.p, c->grid_pts128, 3, 3, c->red3.p);

@@ -173,6 +173,64 @@ ARGUS_HD void cam_project_jac(const CamConst &c, const double M0, const double M
     }
 }
 
+// Projection-free directional derivative for the back-substitution: s = A da (the change of the predicted pixel along the
+// camera step da[16]) and B, without forming the 32 entries of A (W_ij^T da_j = B_ij^T (A_ij da_j), sba_levmar.c:1215-1256).
+// Fixed parameters: their da entries are exactly zero (zero gradient, mu on the diagonal), the counts are applied all the same.
+ARGUS_HD void cam_step_dir(const CamConst &c, const double M0, const double M1, const double M2, const int nfix_k, const int nfix_d,
+                           const double *da, double &su, double &sv, double *B)
+{
+    const double Q0 = c.R[0] * M0 + c.R[1] * M1 + c.R[2] * M2;
+    const double Q1 = c.R[3] * M0 + c.R[4] * M1 + c.R[5] * M2;
+    const double Q2 = c.R[6] * M0 + c.R[7] * M1 + c.R[8] * M2;
+    const double P0 = Q0 + c.t[0], P1 = Q1 + c.t[1], P2 = Q2 + c.t[2];
+    const double iz = 1.0 / P2;
+    const double x = P0 * iz, y = P1 * iz;
+    const double xx = x * x, yy = y * y, xy = x * y;
+    const double r2 = xx + yy;
+    const double r4 = r2 * r2, r6 = r4 * r2;
+    const double rho = 1.0 + c.k1 * r2 + c.k2 * r4 + c.k3 * r6;
+    const double drho = c.k1 + 2.0 * c.k2 * r2 + 3.0 * c.k3 * r4;
+    const double a1 = 2.0 * xy, a2 = r2 + 2.0 * xx, a3 = r2 + 2.0 * yy;
+    const double xd = rho * x + c.p1 * a1 + c.p2 * a2;
+    const double yd = rho * y + c.p1 * a3 + c.p2 * a1;
+    const double fv = c.fu * c.ar;
+    double d[10];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 5; ++k) {
+        d[k] = (k >= 5 - nfix_k) ? 0.0 : da[k];
+        d[5 + k] = (k >= 5 - nfix_d) ? 0.0 : da[5 + k];
+    }
+    // intrinsics + distortion
+    const double rad = r2 * d[5] + r4 * d[6] + r6 * d[9];
+    const double dxd = x * rad + a1 * d[7] + a2 * d[8];
+    const double dyd = y * rad + a3 * d[7] + a1 * d[8];
+    su = xd * d[0] + d[1] + yd * d[4] + c.fu * dxd + c.s * dyd;
+    sv = c.ar * yd * d[0] + d[2] + c.fu * yd * d[3] + fv * dyd;
+    // pose: dP = dt + (Om dv) x Q
+    const double w0 = c.Om[0] * da[10] + c.Om[1] * da[11] + c.Om[2] * da[12];
+    const double w1 = c.Om[3] * da[10] + c.Om[4] * da[11] + c.Om[5] * da[12];
+    const double w2 = c.Om[6] * da[10] + c.Om[7] * da[11] + c.Om[8] * da[12];
+    const double dP0 = da[13] + w1 * Q2 - w2 * Q1, dP1 = da[14] + w2 * Q0 - w0 * Q2, dP2 = da[15] + w0 * Q1 - w1 * Q0;
+    const double dxdx = rho + 2.0 * xx * drho + 2.0 * c.p1 * y + 6.0 * c.p2 * x;
+    const double dxdy = 2.0 * xy * drho + 2.0 * c.p1 * x + 2.0 * c.p2 * y;
+    const double dydy = rho + 2.0 * yy * drho + 6.0 * c.p1 * y + 2.0 * c.p2 * x;
+    const double ux = c.fu * dxdx + c.s * dxdy, uy = c.fu * dxdy + c.s * dydy;
+    const double vx = fv * dxdy,                vy = fv * dydy;
+    const double G00 = ux * iz, G01 = uy * iz, G02 = -(ux * x + uy * y) * iz;
+    const double G10 = vx * iz, G11 = vy * iz, G12 = -(vx * x + vy * y) * iz;
+    su += G00 * dP0 + G01 * dP1 + G02 * dP2;
+    sv += G10 * dP0 + G11 * dP1 + G12 * dP2;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int b_ = 0; b_ < 3; ++b_) {
+        B[b_]     = G00 * c.R[b_] + G01 * c.R[3 + b_] + G02 * c.R[6 + b_];
+        B[3 + b_] = G10 * c.R[b_] + G11 * c.R[3 + b_] + G12 * c.R[6 + b_];
+    }
+}
+
 // Symmetric 3x3 factorisation V = L D L^T (unit lower L, no pivoting) of the damped point block.
 // in: v = [v00 v01 v02 v11 v12 v22] (upper triangle).  out: li = [l10 l20 l21] of L^-1 (unit lower),
 // di = 1/d.  Returns false when a pivot is exactly zero (the reference's "singular V*_i" branch,
