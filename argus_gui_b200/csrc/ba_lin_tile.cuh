@@ -125,21 +125,13 @@ __global__ void __launch_bounds__(256) k_index_fill(int64_t n, const uint64_t *_
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) obs_ptr[n] = k;     // last thread of the last block ends at the grand total
 }
 
-// pt_rank[i][cam] = position of cam in point i's observation list (rows pre-filled with 0xFF; fixed points stay 0xFF)
-__global__ void k_build_point_index(int64_t n, int64_t ncon, int mp, const int32_t *__restrict__ obs_ptr, const uint8_t *__restrict__ obs_cam,
-                                    uint8_t *__restrict__ pt_rank)
-{
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || i < ncon) return;
-    const int k0 = obs_ptr[i], k1 = obs_ptr[i + 1];
-    uint8_t *rr = pt_rank + (size_t)i * mp;
-    for (int k = k0; k < k1; ++k) rr[obs_cam[k]] = (uint8_t)(k - k0);
-}
-
-// per tile: local point index of every observation, camera-sorted (stable) observation order and the camera run starts
+// per tile: local point index of every observation, camera-sorted (stable) observation order, the camera run starts, and the
+// rank table of the Schur kernel: pt_rank[tile][cam][local point] = position of cam in that point's observation list (the table
+// is pre-filled with 0xFF: camera not seen, or point fixed; camera-major so that a warp reads 32 consecutive bytes)
 __global__ void __launch_bounds__(256) k_build_tile_index(int m, const int32_t *__restrict__ tile_pt, const int32_t *__restrict__ tile_o,
                                                           const int32_t *__restrict__ obs_ptr, const uint8_t *__restrict__ obs_cam,
-                                                          uint8_t *__restrict__ obs_lpt, uint8_t *__restrict__ corder, uint16_t *__restrict__ cstart)
+                                                          uint8_t *__restrict__ obs_lpt, uint8_t *__restrict__ corder, uint16_t *__restrict__ cstart,
+                                                          int64_t ncon, int mp, uint8_t *__restrict__ pt_rank /* may be nullptr */)
 {
     __shared__ int s_pofs[kTilePts + 1];
     __shared__ uint8_t s_cam[256];
@@ -155,6 +147,7 @@ __global__ void __launch_bounds__(256) k_build_tile_index(int m, const int32_t *
         int lp = 0;
         while (lp + 1 < npts && tid >= s_pofs[lp + 1]) ++lp;
         obs_lpt[o0 + tid] = (uint8_t)lp;
+        if (pt_rank && (int64_t)p0 + lp >= ncon) pt_rank[((size_t)tile * mp + s_cam[tid]) * kTilePts + lp] = (uint8_t)(tid - s_pofs[lp]);
         atomicAdd(&s_cnt[s_cam[tid] + 1], 1);               // integer histogram: order-independent
     }
     __syncthreads();

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(128) k_make_z(BaProblem pb, double mu, int use
 // Spart[chunk][pair][256]: per-chunk partial sums in fragment order (lane * 8 + q), q = (ri*2 + ci)*2 + e for the
 // 8x8 sub-tile (ri, ci) of the block: element (row = ri*8 + lane>>2, col = ci*8 + 2*(lane&3) + e).
 //
-// pt_rank[n][mp] (uint8, static): position of camera j in point i's observation list, 0xFF when i does not see j (or i is
+// pt_rank[tile][mp][32] (uint8, static): position of camera j in point i's observation list, 0xFF when i does not see j (or i is
 // a fixed point).  It travels with the Z tile, so finding the points that see both cameras of a block is two byte loads.
 // K mapping: one hit (K = 3, padded to the DMMA's 4) per step; the k-lanes 0..2 of a step read the three components of the
 // same observation at consecutive 16-byte addresses, which is free of shared-memory bank conflicts (a 4-hits-per-3-steps
@@ -186,12 +186,12 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
             const int t = chunk + it * sp.nchunk;
             const int p0 = tp.tile_pt[t], p1 = tp.tile_pt[t + 1];
             const int o0 = pb.obs_ptr[p0], o1 = pb.obs_ptr[p1];
-            const uint32_t zb = (uint32_t)(o1 - o0) * 384u, rb = (uint32_t)(p1 - p0) * (uint32_t)mp;
+            const uint32_t zb = (uint32_t)(o1 - o0) * 384u, rb = (uint32_t)kTilePts * (uint32_t)mp; (void)p1;
             unsigned char *dst = smem_raw + (size_t)b * stage;
             const char *src = reinterpret_cast<const char *>(Z + 48 * (int64_t)o0);
             mbar_expect_tx(&mfull[b], zb + rb);
             for (uint32_t off = 0; off < zb; off += 8192u) bulk_g2s(dst + off, src + off, (zb - off < 8192u) ? (zb - off) : 8192u, &mfull[b]);
-            bulk_g2s(dst + zbytes, pt_rank + (size_t)p0 * mp, rb, &mfull[b]);
+            bulk_g2s(dst + zbytes, pt_rank + (size_t)t * rb, rb, &mfull[b]);
         }
         __syncwarp();
     };
@@ -249,14 +249,14 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
         mbar_wait(&mfull[sb], (uint32_t)((it >> 1) & 1));
         const uint32_t zoff = (uint32_t)sb * stage;                           // byte offset of this stage from smem_base
         const uint32_t zbase = smem_base + zoff;
-        const unsigned char *rk = smem_raw + zoff + zbytes + (size_t)lane * mp;
+        const unsigned char *rk = smem_raw + zoff + zbytes + lane;          // rank tile is camera-major: [cam][32 points]
         const bool anyneg = __any_sync(0xffffffffu, sg != 0);
 
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             const int j = bj[b], k = bk[b];
             if (j < 0) continue;
-            const uint32_t rj = have ? rk[j] : 0xFFu, rkk = have ? rk[k] : 0xFFu;
+            const uint32_t rj = have ? rk[j * kTilePts] : 0xFFu, rkk = have ? rk[k * kTilePts] : 0xFFu;
             const bool hit = (rj | rkk) < 0x80u;
             const uint32_t bal = __ballot_sync(0xffffffffu, hit);
             const int nh = __popc(bal);

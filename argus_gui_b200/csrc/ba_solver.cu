@@ -697,7 +697,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     PLAN_CHECK(c->zsign.ensure((size_t)n)); if (c->gen >= 2 && c->mode == kModeMotStr) { PLAN_ENS(c->Z, 48 * nobs); }
     PLAN_CHECK(c->obs_lpt.ensure((size_t)nobs)); PLAN_CHECK(c->corder.ensure((size_t)nobs)); PLAN_CHECK(c->cstart.ensure((size_t)c->ntiles * (m + 1)));
     PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1024);
-    PLAN_CHECK(c->pt_rank.ensure(c->mode == kModeMotStr ? (size_t)n * c->rank_mp : 1));
+    PLAN_CHECK(c->pt_rank.ensure(c->mode == kModeMotStr ? (size_t)c->ntiles * kTilePts * c->rank_mp : 1));
     PLAN_ENS(c->vmask_dev, n * m); PLAN_ENS(c->idx_btot, (n + kIdxPts - 1) / kIdxPts + 1);
     PLAN_ENS(c->obs_ptr, n + 1); PLAN_ENS(c->obs_cam, nobs); PLAN_ENS(c->obs_uv, nobs); PLAN_ENS(c->pt_mask, n);
     PLAN_ENS(c->rot0, 4 * m); PLAN_ENS(c->cam, 16 * m); PLAN_ENS(c->cam_new, 16 * m); PLAN_ENS(c->cam0, 16 * m);
@@ -751,13 +751,11 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pts0.p, p + 16 * m, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
     // derived static indices, built on the device
     if (n > 0) {
-        if (c->mode == kModeMotStr) {
-            ARGUS_CUDA_CHECK(cudaMemsetAsync(c->pt_rank.p, 0xFF, (size_t)n * c->rank_mp, s));
-            k_build_point_index<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, ncon, c->rank_mp, c->obs_ptr.p, c->obs_cam.p, c->pt_rank.p);
-        }
+        if (c->mode == kModeMotStr && c->ntiles > 0)
+            ARGUS_CUDA_CHECK(cudaMemsetAsync(c->pt_rank.p, 0xFF, (size_t)c->ntiles * kTilePts * c->rank_mp, s));
         if (c->ntiles > 0)
             k_build_tile_index<<<c->ntiles, 256, 0, s>>>(m, c->tile_pt.p, c->tile_o.p, c->obs_ptr.p, c->obs_cam.p, c->obs_lpt.p, c->corder.p,
-                                                         c->cstart.p);
+                                                         c->cstart.p, ncon, c->rank_mp, c->mode == kModeMotStr ? c->pt_rank.p : nullptr);
         ARGUS_CUDA_CHECK(cudaGetLastError());
     }
     ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));      // host staging vectors go out of scope
