@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(256) k_build_tile_index(int m, const int32_t *
     }
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // 32-byte global store (sm_100: st.global.v4.f64): one full sector per store instruction
 __device__ __forceinline__ void st_global_v4(double *p, double a, double b, double c, double d)
 {
@@ -198,9 +200,15 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
 
     long long tk = clock64();
 #define LIN_TICK(ph) do { if (out.dbg && tid == 0) { const long long t1_ = clock64(); atomicAdd(out.dbg + (ph), (unsigned long long)(t1_ - tk)); tk = t1_; } } while (0)
+    // tile bounds are loaded one tile ahead (they end up in uniform registers), and the next tile's index data / measurements /
+    // points are pulled into L2 while this tile computes: the dependent loads at the top of a tile then see L2, not DRAM, latency
+    int nx_p0 = 0, nx_p1 = 0, nx_o0 = 0, nx_o1 = 0;
+    if ((int)blockIdx.x < tp.ntiles) { nx_p0 = tp.tile_pt[blockIdx.x]; nx_p1 = tp.tile_pt[blockIdx.x + 1]; nx_o0 = tp.tile_o[blockIdx.x]; nx_o1 = tp.tile_o[blockIdx.x + 1]; }
     for (int tile = blockIdx.x; tile < tp.ntiles; tile += gridDim.x) {
-        const int p0 = tp.tile_pt[tile], npts = tp.tile_pt[tile + 1] - p0;
-        const int o0 = tp.tile_o[tile], nobs_t = tp.tile_o[tile + 1] - o0;
+        const int p0 = nx_p0, npts = nx_p1 - nx_p0;
+        const int o0 = nx_o0, nobs_t = nx_o1 - nx_o0;
+        const int ntile = tile + gridDim.x;
+        if (ntile < tp.ntiles) { nx_p0 = tp.tile_pt[ntile]; nx_p1 = tp.tile_pt[ntile + 1]; nx_o0 = tp.tile_o[ntile]; nx_o1 = tp.tile_o[ntile + 1]; }
         // the tile's index data and points -> shared memory (the previous tile ended with a barrier)
         double2 z = make_double2(0.0, 0.0); int my_cam = 0, my_lp = 0;
         if (tid < nobs_t) {
@@ -245,6 +253,15 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                 *reinterpret_cast<double2 *>(b + 4) = make_double2(0.0, 0.0);
             }
             *reinterpret_cast<double2 *>(b + 6) = make_double2(e0, e1);
+        }
+        if (ntile < tp.ntiles) {      // L2 prefetch of the next tile's inputs (one request per 128-byte line)
+            const int no = nx_o1 - nx_o0, np = nx_p1 - nx_p0;
+            if ((tid & 7) == 0 && tid < no) prefetch_l2(pb.obs_uv + nx_o0 + tid);
+            if (tid < 3 && tid * 128 < no + 127) {
+                prefetch_l2(pb.obs_cam + nx_o0 + tid * 128); prefetch_l2(lp.obs_lpt + nx_o0 + tid * 128); prefetch_l2(lp.corder + nx_o0 + tid * 128);
+            }
+            if (tid >= 32 && tid < 40 && (tid - 32) * 16 < 3 * np + 15) prefetch_l2(pts + 3 * (int64_t)nx_p0 + (tid - 32) * 16);
+            if (tid == 64) { prefetch_l2(pb.obs_ptr + nx_p0); prefetch_l2(pb.obs_ptr + nx_p0 + 31); prefetch_l2(lp.cstart + (size_t)ntile * (pb.m + 1)); }
         }
         __syncthreads();
         LIN_TICK(1);
