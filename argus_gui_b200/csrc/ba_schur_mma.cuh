@@ -70,7 +70,16 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 
 // Bridge from the generation-1 linearisation (W, V, eb resident): per point damp + LDL^T, Z = W L^-T |D|^-1/2, sign mask,
 // V*^-1 (for the back-substitution) and c_i = V*^-1 eb_i; E_j partials as in k_prepare.  One thread per point.
-__global__ void __launch_bounds__(128) k_make_z(BaProblem pb, double mu, int use_state, int write_state,
+// Z in HBM: per tile of points one block of 48 * nobs_t doubles, chunk-major inside the block: the 12 four-double chunks of an
+// observation's 16 x 3 row (chunk = zperm / 4) live in 12 planes of nobs_t chunks each, so that the one-thread-per-observation
+// producer writes consecutive 32-byte chunks (coalesced) and the Schur kernel copies a tile plane by plane.
+//   element e (= zperm(r, c)) of local observation lk of a tile starting at observation o0:
+__host__ __device__ __forceinline__ int64_t z_index(int64_t o0, int nobs_t, int lk, int e)
+{
+    return 48 * o0 + ((int64_t)(e >> 2) * nobs_t + lk) * 4 + (e & 3);
+}
+
+__global__ void __launch_bounds__(128) k_make_z(BaProblem pb, TilePlan tp, double mu, int use_state, int write_state,
                                                 const double *__restrict__ V, const double *__restrict__ eb,
                                                 double *__restrict__ vstate, const double *__restrict__ W, double *__restrict__ Z,
                                                 uint8_t *__restrict__ zsign, double *__restrict__ Vinv, double *__restrict__ Epart,
@@ -105,21 +114,23 @@ __global__ void __launch_bounds__(128) k_make_z(BaProblem pb, double mu, int use
         const double s0 = sqrt(fabs(di[0])), s1 = sqrt(fabs(di[1])), s2 = sqrt(fabs(di[2]));
         zsign[i] = (uint8_t)((di[0] < 0.0 ? 1 : 0) | (di[1] < 0.0 ? 2 : 0) | (di[2] < 0.0 ? 4 : 0));
         const int k1 = pb.obs_ptr[i + 1];
+        int tl = 0, th = tp.ntiles - 1;                    // the tile of point i (tile_pt is ascending)
+        while (tl < th) { const int tm = (tl + th + 1) >> 1; if (tp.tile_pt[tm] <= i) tl = tm; else th = tm - 1; }
+        const int o0 = tp.tile_o[tl], nobs_t = tp.tile_o[tl + 1] - o0;
         for (int k = pb.obs_ptr[i]; k < k1; ++k) {
             const int j = pb.obs_cam[k];
-            double *Zk = Z + 48 * (int64_t)k;
             if (j < pb.mcon) {
 #pragma unroll
-                for (int t = 0; t < 48; ++t) Zk[t] = 0.0;
+                for (int t = 0; t < 48; ++t) Z[z_index(o0, nobs_t, k - o0, t)] = 0.0;
                 continue;
             }
             const double *Wk = W + 48 * (int64_t)k;
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const double w0 = Wk[3 * r], w1 = Wk[3 * r + 1], w2 = Wk[3 * r + 2];
-                Zk[zperm(r, 0)] = w0 * s0;
-                Zk[zperm(r, 1)] = (li[0] * w0 + w1) * s1;
-                Zk[zperm(r, 2)] = (li[1] * w0 + li[2] * w1 + w2) * s2;
+                Z[z_index(o0, nobs_t, k - o0, zperm(r, 0))] = w0 * s0;
+                Z[z_index(o0, nobs_t, k - o0, zperm(r, 1))] = (li[0] * w0 + w1) * s1;
+                Z[z_index(o0, nobs_t, k - o0, zperm(r, 2))] = (li[1] * w0 + li[2] * w1 + w2) * s2;
                 const double s = w0 * c0 + w1 * c1 + w2 * c2;
                 if (s != 0.0) atomicAdd(Es + 16 * j + r, s);
             }
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(128) k_make_z(BaProblem pb, double mu, int use
 
 // The Schur kernel.  grid = (nchunk, G); NW consumer warps, each owning NB blocks; the copy producer is lane 0 of warp 0
 // (PROD = 0) or a dedicated extra warp (PROD = 1).
-// Dynamic shared memory: 2 x [Z tile: TO x 48 doubles | rank tile: 32 x mp bytes], then one Z row (384 B) of zeros.
+// Dynamic shared memory: 2 x [Z tile: 12 chunk planes of (TO + 1) x 32 bytes | rank tile: mp x 32 bytes], then 384 B of zeros.
 // Spart[chunk][pair][256]: per-chunk partial sums in fragment order (lane * 8 + q), q = (ri*2 + ci)*2 + e for the
 // 8x8 sub-tile (ri, ci) of the block: element (row = ri*8 + lane>>2, col = ci*8 + 2*(lane&3) + e).
 //
@@ -161,7 +172,8 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
                                                                  int mp, double *__restrict__ Spart)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t zbytes = (uint32_t)tp.tile_obs * 384u;
+    const uint32_t plane = (uint32_t)tp.tile_obs * 32u + 32u;                   // one chunk plane (+32 B: consecutive planes start 8 banks apart)
+    const uint32_t zbytes = 12u * plane;
     const uint32_t stage = zbytes + (uint32_t)kTilePts * (uint32_t)mp;          // multiple of 16
     unsigned char *zero_blk = smem_raw + 2 * stage;
     __shared__ __align__(8) uint64_t mfull[2], mempty[2];
@@ -190,7 +202,8 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
             unsigned char *dst = smem_raw + (size_t)b * stage;
             const char *src = reinterpret_cast<const char *>(Z + 48 * (int64_t)o0);
             mbar_expect_tx(&mfull[b], zb + rb);
-            for (uint32_t off = 0; off < zb; off += 8192u) bulk_g2s(dst + off, src + off, (zb - off < 8192u) ? (zb - off) : 8192u, &mfull[b]);
+            const uint32_t pl = (uint32_t)(o1 - o0) * 32u;                     // bytes of one chunk plane of this tile
+            if (pl) for (uint32_t q = 0; q < 12u; ++q) bulk_g2s(dst + q * plane, src + (size_t)q * pl, pl, &mfull[b]);
             bulk_g2s(dst + zbytes, pt_rank + (size_t)t * rb, rb, &mfull[b]);
         }
         __syncwarp();
@@ -216,12 +229,13 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
     const uint32_t smem_base = smem_u32(smem_raw);
     uint2 *hl = hitlist[warp];
     const uint32_t zero_addr = smem_base + 2u * stage;
-    const uint32_t lane_off = (uint32_t)g8 * 48u + (uint32_t)kk * 16u;
+    // byte offset of 16-byte element x = g8 * 3 + component of a row, relative to the row's chunk slot in plane 0
+    auto elem_off = [&](int x) { return (uint32_t)(x >> 1) * plane + (uint32_t)(x & 1) * 16u; };
+    const uint32_t lane_off = elem_off(g8 * 3 + (kk < 3 ? kk : 0));
     // (hit-in-group, component) of this k-lane in the three steps of a full 4-hit group
     const int gh0 = (kk == 3) ? 1 : 0, gh1 = (kk == 0 || kk == 1) ? 1 : 2, gh2 = (kk == 0) ? 2 : 3;
     const int gc0 = (kk == 3) ? 0 : kk, gc1 = (kk == 0) ? 1 : (kk == 1) ? 2 : (kk == 2) ? 0 : 1, gc2 = (kk == 0) ? 2 : kk - 1;
-    const uint32_t goff0 = (uint32_t)g8 * 48u + (uint32_t)gc0 * 16u, goff1 = (uint32_t)g8 * 48u + (uint32_t)gc1 * 16u,
-                   goff2 = (uint32_t)g8 * 48u + (uint32_t)gc2 * 16u;
+    const uint32_t goff0 = elem_off(g8 * 3 + gc0), goff1 = elem_off(g8 * 3 + gc1), goff2 = elem_off(g8 * 3 + gc2);
 
     // per-lane metadata of the point this lane represents in a tile: local observation base and the sign bits of D.
     // Two-level prefetch so no load waits on another: tile bounds two tiles ahead, per-point data one tile ahead.
@@ -264,7 +278,7 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
             if (hit) {
                 const int pos = __popc(bal & ((1u << lane) - 1u));
                 // shared-memory byte addresses of the two Z rows of this hit; bits 28..30 of .x carry the sign bits of D
-                const uint32_t aj = zbase + (uint32_t)(ob + (int)rj) * 384u, ak = zbase + (uint32_t)(ob + (int)rkk) * 384u;
+                const uint32_t aj = zbase + (uint32_t)(ob + (int)rj) * 32u, ak = zbase + (uint32_t)(ob + (int)rkk) * 32u;
                 hl[pos] = make_uint2(aj | (sg << 28), ak);
             }
             __syncwarp();

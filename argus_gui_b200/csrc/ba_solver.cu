@@ -269,13 +269,13 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
         } else {
             ProfScope ps(c, P_PREPARE);
             k_make_z<<<c->grid_pts128, 128, (size_t)m * 16 * sizeof(double), c->stream>>>(
-                c->problem(), mu, use_state, write_state, c->V.p, c->eb.p, c->vstate.p, c->W.p, c->Z.p, c->zsign.p, c->Vinv.p,
+                c->problem(), c->tile_plan(), mu, use_state, write_state, c->V.p, c->eb.p, c->vstate.p, c->W.p, c->Z.p, c->zsign.p, c->Vinv.p,
                 c->Epart.p, c->flags.p);
         }
         {
             ProfScope ps(c, P_SCHUR);
             dim3 grid(c->schur_nchunk, c->schur_G);
-            const size_t sm = (size_t)2 * ((size_t)c->tile_obs * 384 + (size_t)kTilePts * c->rank_mp) + 384;
+            const size_t sm = (size_t)2 * ((size_t)c->tile_obs * 384 + 384 + (size_t)kTilePts * c->rank_mp) + 384;
 #define SCHUR_LAUNCH(NB_, NW_, PR_) k_schur_mma<NB_, NW_, PR_><<<grid, (NW_ + PR_) * 32, sm, c->stream>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, \
                                                                                        c->zsign.p, c->pt_rank.p, c->rank_mp, c->Spart.p)
             switch (c->schur_NB * 100 + c->schur_NW) {
@@ -554,7 +554,7 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
     ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, 214000));
     if (const char *e = getenv("ARGUS_BA_GEN")) c->gen = atoi(e);
     {
-        const int smx = 2 * (256 * 384 + 32 * 64) + 384;
+        const int smx = 2 * (256 * 384 + 384 + 32 * 64) + 384;
         ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
         ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<3, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
         ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<5, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
