@@ -235,8 +235,10 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             if (my_cam >= pb.mcon) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    *reinterpret_cast<double2 *>(g + r * 2) = make_double2(A[r], A[r + 8]);
-                    *reinterpret_cast<double2 *>(g + 16 + r * 2) = make_double2(A[16 + r], A[24 + r]);
+                    // row layout [r (8)][component u / v][parameter r, r + 8]: the four 16-byte elements a quarter-warp of the
+                    // Gram phase reads from one observation (2 rows x 2 components) are 64 contiguous bytes
+                    *reinterpret_cast<double2 *>(g + r * 4) = make_double2(A[r], A[r + 8]);
+                    *reinterpret_cast<double2 *>(g + r * 4 + 2) = make_double2(A[16 + r], A[24 + r]);
                 }
             } else {
 #pragma unroll
@@ -356,8 +358,8 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                 double zz[12];
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    const double2 a0 = *reinterpret_cast<const double2 *>(g + (r + rr) * 2);          // du/da_r, du/da_{r+8}
-                    const double2 a1 = *reinterpret_cast<const double2 *>(g + 16 + (r + rr) * 2);     // dv/da_r, dv/da_{r+8}
+                    const double2 a0 = *reinterpret_cast<const double2 *>(g + (r + rr) * 4);          // du/da_r, du/da_{r+8}
+                    const double2 a1 = *reinterpret_cast<const double2 *>(g + (r + rr) * 4 + 2);      // dv/da_r, dv/da_{r+8}
                     const double wl0 = a0.x * B0 + a1.x * B3, wl1 = a0.x * B1 + a1.x * B4, wl2 = a0.x * B2 + a1.x * B5;   // row r
                     const double wh0 = a0.y * B0 + a1.y * B3, wh1 = a0.y * B1 + a1.y * B4, wh2 = a0.y * B2 + a1.y * B5;   // row r + 8
                     // layout ((r%8)*3 + c)*2 + r/8
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                         const bool valid = idx < njq[q];
                         const int o = s_cord[c0q[q] + (valid ? idx : 0)];
                         const double *g = Ga + (size_t)o * kGa;
-                        double2 a = *reinterpret_cast<const double2 *>(g + comp * 16 + g8 * 2);
+                        double2 a = *reinterpret_cast<const double2 *>(g + g8 * 4 + comp * 2);
                         double ax = (g8 < 2) ? g[32 + comp * 2 + g8] : 0.0;
                         if (!valid) { a.x = 0.0; a.y = 0.0; ax = 0.0; }
                         dmma884(uacc[q][0], uacc[q][1], a.x, a.x);
