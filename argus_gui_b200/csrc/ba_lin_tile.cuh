@@ -387,13 +387,17 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                 smax = max(smax, njq[q]);
             }
             const int comp = kk & 1;
+            int onx[MC];                                   // observation index of the NEXT step (one shared-memory latency off the chain)
+#pragma unroll
+            for (int q = 0; q < MC; ++q) onx[q] = s_cord[c0q[q] + (((kk >> 1) < njq[q]) ? (kk >> 1) : 0)];
             for (int s = 0; s < smax; s += 2) {
 #pragma unroll
                 for (int q = 0; q < MC; ++q) {
                     if (s < njq[q]) {
                         const int idx = s + (kk >> 1);
                         const bool valid = idx < njq[q];
-                        const int o = s_cord[c0q[q] + (valid ? idx : 0)];
+                        const int o = onx[q];
+                        onx[q] = s_cord[c0q[q] + ((idx + 2 < njq[q]) ? idx + 2 : 0)];
                         const double *g = Ga + (size_t)o * kGa;
                         double2 a = *reinterpret_cast<const double2 *>(g + g8 * 4 + comp * 2);
                         double ax = (g8 < 2) ? g[32 + comp * 2 + g8] : 0.0;
