@@ -177,7 +177,7 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
     const uint32_t stage = zbytes + (uint32_t)kTilePts * (uint32_t)mp;          // multiple of 16
     unsigned char *zero_blk = smem_raw + 2 * stage;
     __shared__ __align__(8) uint64_t mfull[2], mempty[2];
-    __shared__ uint2 hitlist[NW][kTilePts + 1];
+    __shared__ uint2 hitlist[NW][kTilePts + 4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g8 = lane >> 2, kk = lane & 3;
@@ -185,6 +185,9 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
     const int ntl = (tp.ntiles > chunk) ? (tp.ntiles - chunk + sp.nchunk - 1) / sp.nchunk : 0;   // tiles of this chunk
 
     if (threadIdx.x < 96) reinterpret_cast<uint32_t *>(zero_blk)[threadIdx.x] = 0u;        // a whole Z row of zeros (384 B)
+    // the pad slot (index TO) of every chunk plane of both stages is never written by the copies: it is the all-zero row
+    for (int t = threadIdx.x; t < 2 * 12 * 8; t += blockDim.x)
+        reinterpret_cast<uint32_t *>(smem_raw + (size_t)(t / 96) * stage + (size_t)((t % 96) / 8) * plane + (size_t)tp.tile_obs * 32u)[t % 8] = 0u;
     if (threadIdx.x == 0) { mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1); mbar_init(&mempty[0], NW); mbar_init(&mempty[1], NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -228,7 +231,6 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
 
     const uint32_t smem_base = smem_u32(smem_raw);
     uint2 *hl = hitlist[warp];
-    const uint32_t zero_addr = smem_base + 2u * stage;
     // byte offset of 16-byte element x = g8 * 3 + component of a row, relative to the row's chunk slot in plane 0
     auto elem_off = [&](int x) { return (uint32_t)(x >> 1) * plane + (uint32_t)(x & 1) * 16u; };
     const uint32_t lane_off = elem_off(g8 * 3 + (kk < 3 ? kk : 0));
@@ -263,6 +265,7 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
         mbar_wait(&mfull[sb], (uint32_t)((it >> 1) & 1));
         const uint32_t zoff = (uint32_t)sb * stage;                           // byte offset of this stage from smem_base
         const uint32_t zbase = smem_base + zoff;
+        const uint32_t zrow_addr = zbase + (uint32_t)tp.tile_obs * 32u;       // plane-0 address of the all-zero row of this stage
         const unsigned char *rk = smem_raw + zoff + zbytes + lane;          // rank tile is camera-major: [cam][32 points]
         const bool anyneg = __any_sync(0xffffffffu, sg != 0);
 
@@ -281,11 +284,15 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
                 const uint32_t aj = zbase + (uint32_t)(ob + (int)rj) * 32u, ak = zbase + (uint32_t)(ob + (int)rkk) * 32u;
                 hl[pos] = make_uint2(aj | (sg << 28), ak);
             }
+            if (lane < 3) hl[nh + lane] = make_uint2(zrow_addr, zrow_addr);     // missing hits of the last group -> the zero slot
             __syncwarp();
             // K packing.  Full groups of 4 hits fill 3 DMMA steps completely (12 K-slots): k-lane kk handles the (hit, component)
             // pairs  kk0: (0,0)(1,1)(2,2)  kk1: (0,1)(1,2)(3,0)  kk2: (0,2)(2,0)(3,1)  kk3: (1,0)(2,1)(3,2)  of the group in steps
             // 0,1,2.  The remaining 1..3 hits take one step each (k-lanes 0..2 = the three components, k-lane 3 reads zeros).
-            const int nfull = nh & ~3;
+            // Every group of up to 4 hits goes through the same three packed steps; the slots of a last, partial group that have no
+            // hit read the all-zero pad slot of the chunk planes (hit-list entries nh .. nh + 2 point there), and steps that would
+            // only multiply zeros are skipped (a group of r hits needs min(r, 3) steps).
+            const int nfull = nh & ~3, rem = nh - nfull;
             if (j == k) {
                 for (int q = 0; q < nfull; q += 4) {
                     const uint2 e0 = hl[q + gh0], e1 = hl[q + gh1], e2 = hl[q + gh2];
@@ -301,12 +308,21 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
                     dmma884(acc[b][0], acc[b][1], s1.x, a1.x); dmma884(acc[b][2], acc[b][3], s1.x, a1.y); dmma884(acc[b][6], acc[b][7], s1.y, a1.y);
                     dmma884(acc[b][0], acc[b][1], s2.x, a2.x); dmma884(acc[b][2], acc[b][3], s2.x, a2.y); dmma884(acc[b][6], acc[b][7], s2.y, a2.y);
                 }
-                for (int h = nfull; h < nh; ++h) {
-                    const uint2 ent = hl[h];
-                    const double2 a = lds_f64x2(kk < 3 ? (ent.x & 0x0FFFFFFFu) + lane_off : zero_addr);
-                    double2 sa = a;
-                    if (anyneg) { const uint32_t bit = ((ent.x >> 28) >> kk) & 1u; sa.x = flip_sign(sa.x, bit); sa.y = flip_sign(sa.y, bit); }
-                    dmma884(acc[b][0], acc[b][1], sa.x, a.x); dmma884(acc[b][2], acc[b][3], sa.x, a.y); dmma884(acc[b][6], acc[b][7], sa.y, a.y);
+                if (rem) {          // last, partial group: same packed steps, all loads issued before the first DMMA
+                    const uint2 e0 = hl[nfull + gh0];
+                    uint2 e1 = e0, e2 = e0;
+                    double2 a0 = lds_f64x2((e0.x & 0x0FFFFFFFu) + goff0), a1 = a0, a2 = a0;
+                    if (rem >= 2) { e1 = hl[nfull + gh1]; a1 = lds_f64x2((e1.x & 0x0FFFFFFFu) + goff1); }
+                    if (rem >= 3) { e2 = hl[nfull + gh2]; a2 = lds_f64x2((e2.x & 0x0FFFFFFFu) + goff2); }
+                    double2 s0 = a0, s1 = a1, s2 = a2;
+                    if (anyneg) {
+                        const uint32_t b0 = ((e0.x >> 28) >> gc0) & 1u, b1 = ((e1.x >> 28) >> gc1) & 1u, b2 = ((e2.x >> 28) >> gc2) & 1u;
+                        s0.x = flip_sign(s0.x, b0); s0.y = flip_sign(s0.y, b0); s1.x = flip_sign(s1.x, b1); s1.y = flip_sign(s1.y, b1);
+                        s2.x = flip_sign(s2.x, b2); s2.y = flip_sign(s2.y, b2);
+                    }
+                    dmma884(acc[b][0], acc[b][1], s0.x, a0.x); dmma884(acc[b][2], acc[b][3], s0.x, a0.y); dmma884(acc[b][6], acc[b][7], s0.y, a0.y);
+                    if (rem >= 2) { dmma884(acc[b][0], acc[b][1], s1.x, a1.x); dmma884(acc[b][2], acc[b][3], s1.x, a1.y); dmma884(acc[b][6], acc[b][7], s1.y, a1.y); }
+                    if (rem >= 3) { dmma884(acc[b][0], acc[b][1], s2.x, a2.x); dmma884(acc[b][2], acc[b][3], s2.x, a2.y); dmma884(acc[b][6], acc[b][7], s2.y, a2.y); }
                 }
             } else {
                 for (int q = 0; q < nfull; q += 4) {
@@ -326,13 +342,28 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
                     dmma884(acc[b][0], acc[b][1], a2.x, b2.x); dmma884(acc[b][2], acc[b][3], a2.x, b2.y);
                     dmma884(acc[b][4], acc[b][5], a2.y, b2.x); dmma884(acc[b][6], acc[b][7], a2.y, b2.y);
                 }
-                for (int h = nfull; h < nh; ++h) {
-                    const uint2 ent = hl[h];
-                    double2 a = lds_f64x2(kk < 3 ? (ent.x & 0x0FFFFFFFu) + lane_off : zero_addr);
-                    const double2 bb = lds_f64x2(kk < 3 ? ent.y + lane_off : zero_addr);
-                    if (anyneg) { const uint32_t bit = ((ent.x >> 28) >> kk) & 1u; a.x = flip_sign(a.x, bit); a.y = flip_sign(a.y, bit); }
-                    dmma884(acc[b][0], acc[b][1], a.x, bb.x); dmma884(acc[b][2], acc[b][3], a.x, bb.y);
-                    dmma884(acc[b][4], acc[b][5], a.y, bb.x); dmma884(acc[b][6], acc[b][7], a.y, bb.y);
+                if (rem) {          // last, partial group: same packed steps, all loads issued before the first DMMA
+                    const uint2 e0 = hl[nfull + gh0];
+                    uint2 e1 = e0, e2 = e0;
+                    double2 a0 = lds_f64x2((e0.x & 0x0FFFFFFFu) + goff0), a1 = a0, a2 = a0;
+                    double2 b0 = lds_f64x2(e0.y + goff0), b1 = b0, b2 = b0;
+                    if (rem >= 2) { e1 = hl[nfull + gh1]; a1 = lds_f64x2((e1.x & 0x0FFFFFFFu) + goff1); b1 = lds_f64x2(e1.y + goff1); }
+                    if (rem >= 3) { e2 = hl[nfull + gh2]; a2 = lds_f64x2((e2.x & 0x0FFFFFFFu) + goff2); b2 = lds_f64x2(e2.y + goff2); }
+                    if (anyneg) {
+                        const uint32_t t0 = ((e0.x >> 28) >> gc0) & 1u, t1 = ((e1.x >> 28) >> gc1) & 1u, t2 = ((e2.x >> 28) >> gc2) & 1u;
+                        a0.x = flip_sign(a0.x, t0); a0.y = flip_sign(a0.y, t0); a1.x = flip_sign(a1.x, t1); a1.y = flip_sign(a1.y, t1);
+                        a2.x = flip_sign(a2.x, t2); a2.y = flip_sign(a2.y, t2);
+                    }
+                    dmma884(acc[b][0], acc[b][1], a0.x, b0.x); dmma884(acc[b][2], acc[b][3], a0.x, b0.y);
+                    dmma884(acc[b][4], acc[b][5], a0.y, b0.x); dmma884(acc[b][6], acc[b][7], a0.y, b0.y);
+                    if (rem >= 2) {
+                        dmma884(acc[b][0], acc[b][1], a1.x, b1.x); dmma884(acc[b][2], acc[b][3], a1.x, b1.y);
+                        dmma884(acc[b][4], acc[b][5], a1.y, b1.x); dmma884(acc[b][6], acc[b][7], a1.y, b1.y);
+                    }
+                    if (rem >= 3) {
+                        dmma884(acc[b][0], acc[b][1], a2.x, b2.x); dmma884(acc[b][2], acc[b][3], a2.x, b2.y);
+                        dmma884(acc[b][4], acc[b][5], a2.y, b2.x); dmma884(acc[b][6], acc[b][7], a2.y, b2.y);
+                    }
                 }
             }
             __syncwarp();
