@@ -8,12 +8,14 @@
 //
 // Work decomposition.  The upper-triangular 16x16 camera blocks (j <= k) are dealt to G groups x 8 warps x NB slots.
 // A CTA = (chunk of point tiles, group); each warp keeps its NB blocks as DMMA accumulators (8 doubles per lane per
-// block) for the whole chunk.  Per tile (<= 32 points, <= TO observations) the CTA's Z rows arrive by cp.async.bulk
-// into a double-buffered shared-memory tile; per block the warp ballots the points that see both cameras, compacts
-// them into a hit list and feeds the K dimension (3 per hit, 4 per DMMA step) without padding.
+// block) for the whole chunk.  Per tile (<= 32 points, <= TO observations) the CTA's Z block arrives by cp.async.bulk,
+// one copy per chunk plane (z_index), into a double-buffered shared-memory stage; per block the warp ballots the points that
+// see both cameras, compacts them into a hit list and feeds the K dimension (3 per hit, 4 per DMMA step) without padding
+// (groups of 4 hits fill 3 steps; a last partial group runs through the same steps with its missing slots on a zero row).
 // Fragment layout of mma.m8n8k4.f64: A: lane -> (row = lane>>2, k = lane&3); B: (k = lane&3, col = lane>>2);
-// C: (row = lane>>2, cols 2*(lane&3), +1).  The Z rows of an observation are stored as ((r%8)*3 + c)*2 + r/8 so one
-// 16-byte load gives a lane the (row, row+8) pair of its fragment - the same load serves the A and the B operand.
+// C: (row = lane>>2, cols 2*(lane&3), +1).  The 48 values of an observation are ordered ((r%8)*3 + c)*2 + r/8 so one
+// 16-byte load gives a lane the (row, row+8) pair of its fragment - the same load serves the A and the B operand;
+// consecutive 32-byte chunks of that order live in consecutive chunk planes of the tile (coalesced producer stores).
 #pragma once
 #include "ba_common.cuh"
 

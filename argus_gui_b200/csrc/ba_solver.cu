@@ -666,7 +666,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         c->schur_nchunk = nch;
     }
     c->rank_mp = (m + 15) & ~15;
-    // obs_lpt, corder, cstart and pt_rank are derived on the device from obs_ptr / obs_cam / tile_pt (k_build_*_index)
+    // obs_lpt, corder, cstart and pt_rank are derived on the device from obs_ptr / obs_cam / tile_pt (k_index_*, k_build_tile_index)
     c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)c->tile_obs * (kGa + kBs) * sizeof(double) +
                   (size_t)kTilePts * kPs * sizeof(double);
     {
@@ -761,7 +761,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));      // host staging vectors go out of scope
     c->h2d_bytes += (size_t)n * m + nobs * sizeof(double2) + (4 + 16) * m * sizeof(double) + 3 * n * sizeof(double) +
                     2 * tiles.size() * sizeof(int32_t);
-    if (timing) fprintf(stderr, "argus_b200 upload: host index build %.1f ms, device alloc %.1f ms, H2D %.1f ms\n", 1e3 * (t_index - t_start), 1e3 * (t_alloc - t_index), 1e3 * (tnow() - t_alloc));
+    if (timing) fprintf(stderr, "argus_b200 upload: host counting + tile plan %.1f ms, device alloc %.1f ms, H2D + device index build %.1f ms\n", 1e3 * (t_index - t_start), 1e3 * (t_alloc - t_index), 1e3 * (tnow() - t_alloc));
     return argus_ba_reset(c);
 }
 
