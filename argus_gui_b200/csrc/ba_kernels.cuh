@@ -153,18 +153,23 @@ __global__ void k_reduce_lin_scalars(const double *__restrict__ scpart, int npar
 __global__ void k_lin_finalize(const double *__restrict__ Ured, const double *__restrict__ cam, int m, int mcon,
                                const double *__restrict__ sum2, const double *__restrict__ max2, double *__restrict__ scal)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double inf = max2[0], dmax = 2.2250738585072014e-308 /* DBL_MIN, sba_levmar.c:982 */, psq = sum2[1];
-        for (int j = mcon; j < m; ++j) {
-            const double *Uj = Ured + j * kU;
-            for (int r = 0; r < 16; ++r) {
-                inf = fmax(inf, fabs(Uj[136 + r]));
-                dmax = fmax(dmax, Uj[tri16(r, r)]);
-            }
-        }
-        dmax = fmax(dmax, max2[1]);
-        for (int t = 0; t < 16 * m; ++t) psq += cam[t] * cam[t];
-        scal[0] = sum2[0]; scal[1] = inf; scal[2] = psq; scal[3] = dmax;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    double inf = 0.0, dmax = 2.2250738585072014e-308 /* DBL_MIN, sba_levmar.c:982 */, psq = 0.0;
+    for (int t = mcon * 16 + lane; t < m * 16; t += 32) {           // one (camera, parameter) per lane and pass
+        const int j = t >> 4, r = t & 15;
+        const double *Uj = Ured + j * kU;
+        inf = fmax(inf, fabs(Uj[136 + r]));
+        dmax = fmax(dmax, Uj[tri16(r, r)]);
+    }
+    for (int t = lane; t < 16 * m; t += 32) psq += cam[t] * cam[t];
+    for (int o = 16; o > 0; o >>= 1) {                               // fixed-order butterflies
+        inf = fmax(inf, __shfl_xor_sync(0xffffffffu, inf, o));
+        dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        psq += __shfl_xor_sync(0xffffffffu, psq, o);
+    }
+    if (lane == 0) {
+        scal[0] = sum2[0]; scal[1] = fmax(inf, max2[0]); scal[2] = psq + sum2[1]; scal[3] = fmax(dmax, max2[1]);
     }
 }
 
