@@ -1,4 +1,4 @@
-"""Small end-to-end run of every entry point, meant to be run under compute-sanitizer (memcheck / racecheck)."""
+"""Small end-to-end run of every entry point, a quick health check of the built library on a GPU box."""
 import sys; sys.path.insert(0, '/root/repo')
 import numpy as np
 from argus_gui_b200 import scenes, ba, dlt, triangulate
