@@ -304,7 +304,7 @@ def bench_dlt(torch, device, stream, steps, warmup, rank, world, hbm_peak):
            "ms_triangulate": tri_ms, "ms_reproj_error": err_ms, "ms_fused_reconstruct": fused_ms,
            "roofline_fused": {"bound": "hbm", "achieved": fused_bytes / (fused_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                               "frac": fused_bytes / (fused_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                              "note": "fp64-instruction bound: 5 correctly-rounded divisions per camera (float32-faithful undistortion)"},
+                              "note": "fp64-instruction bound (ncu: fp64 pipe 71-77 % of peak, issue slots 63-65 %, DRAM 13-17 %: profiles/r01_final_ncu_full_dlt.txt): 5 undistortion iterations with a correctly rounded division each, no FMA contraction (bit-exact float32 output)"},
            "roofline_triangulate": {"bound": "hbm", "achieved": tri_bytes / (tri_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                     "frac": tri_bytes / (tri_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
            "roofline_reproj_error": {"bound": "hbm", "achieved": err_bytes / (err_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
