@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <chrono>
 #include <thread>
+#include <mutex>
 #include <functional>
 #include "../../include/argus_b200.h"
 #include "ba_kernels.cuh"
@@ -70,6 +71,22 @@ void parallel_for(int64_t n, const std::function<void(int64_t, int64_t)> &fn)
     for (int q = 0; q < T; ++q) th.emplace_back([&, q] { fn(n * q / T, n * (q + 1) / T); });
     for (auto &x : th) x.join();
 }
+
+// process-wide bits that are expensive to set up per context (a one-shot call creates and destroys a context):
+// kernel attributes already applied per device, and a free list of 128-byte pinned scratch blocks for the scalar read-backs
+std::mutex g_once_mutex;
+unsigned long long g_attr_done = 0;
+std::vector<double *> g_pinned_free;
+double *pinned_take()
+{
+    {
+        std::lock_guard<std::mutex> lk(g_once_mutex);
+        if (!g_pinned_free.empty()) { double *p = g_pinned_free.back(); g_pinned_free.pop_back(); return p; }
+    }
+    double *p = nullptr;
+    return cudaMallocHost(&p, 16 * sizeof(double)) == cudaSuccess ? p : nullptr;
+}
+void pinned_give(double *p) { std::lock_guard<std::mutex> lk(g_once_mutex); g_pinned_free.push_back(p); }
 
 }  // namespace
 
@@ -542,25 +559,27 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
     c->device = device;
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else { ARGUS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-    cudaDeviceProp prop;
-    ARGUS_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    c->sms = prop.multiProcessorCount;
-    ARGUS_CUDA_CHECK(cudaMallocHost(&c->h_pinned, 16 * sizeof(double)));
+    ARGUS_CUDA_CHECK(cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device));
+    c->h_pinned = pinned_take();
+    if (!c->h_pinned) { delete c; return ARGUS_E_CUDA; }
     memset(c->prof_ms, 0, sizeof(c->prof_ms)); memset(c->prof_n, 0, sizeof(c->prof_n));
-    // opt in to large dynamic shared memory where needed
-    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve_t<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
-    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve_t<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
-    ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, 214000));
     if (const char *e = getenv("ARGUS_BA_GEN")) c->gen = atoi(e);
-    {
-        const int smx = 2 * (256 * 384 + 384 + 32 * 64) + 384;
-        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
-        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<3, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
-        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<5, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
-        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<9, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
-        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<6, 12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
-        ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<7, 11, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+    {   // opt in to large dynamic shared memory where needed: once per device and process
+        std::lock_guard<std::mutex> lk(g_once_mutex);
+        if (device < 64 && !(g_attr_done & (1ull << device))) {
+            const int smx = 2 * (256 * 384 + 384 + 32 * 64) + 384;
+            ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_linearize, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve_t<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
+            ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve_t<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 223000));
+            ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_chol_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, 214000));
+            ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+            ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<3, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+            ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<5, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+            ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<9, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+            ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<6, 12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+            ARGUS_CUDA_CHECK(cudaFuncSetAttribute(k_schur_mma<7, 11, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx));
+            g_attr_done |= 1ull << device;
+        }
     }
     if (const char *e = getenv("ARGUS_SCHUR_NW")) c->schur_nw_pref = atoi(e);
     if (getenv("ARGUS_LIN_DEBUG")) { ARGUS_CUDA_CHECK(cudaMalloc(&c->lin_dbg, 8 * sizeof(unsigned long long))); ARGUS_CUDA_CHECK(cudaMemset(c->lin_dbg, 0, 8 * sizeof(unsigned long long))); }
@@ -587,7 +606,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
     c->flags.release(); c->tile_pt.release(); c->tile_o.release(); c->blk_jk.release(); c->blk_pair.release(); c->zsign.release(); c->Z.release();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->arena.base) cudaFree(c->arena.base);
-    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_pinned) pinned_give(c->h_pinned);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
