@@ -727,7 +727,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     PLAN_ENS(c->Upart, (int64_t)c->grid_pts128 * m * kU); PLAN_ENS(c->scpart, 4 * std::max(c->grid_pts128, c->grid_lin)); PLAN_ENS(c->red1, m * kU + 2); PLAN_ENS(c->max2, 2);
     PLAN_ENS(c->Epart, (int64_t)c->grid_pts128 * m * 16); PLAN_ENS(c->Spart, (int64_t)std::max(c->nchunks, c->schur_nchunk) * c->npairs * 256);
     PLAN_ENS(c->red2, (int64_t)c->npairs * 256 + m * 16); PLAN_ENS(c->S, (int64_t)N * N); PLAN_ENS(c->E, N); PLAN_ENS(c->da_free, N); PLAN_ENS(c->da_full, 16 * m);
-    PLAN_ENS(c->part3, 3 * c->grid_pts128); PLAN_ENS(c->red3, 4); PLAN_ENS(c->cam2, 2); PLAN_ENS(c->scal, 8); PLAN_ENS(c->att, 8); PLAN_ENS(c->respart, c->grid_pts256);
+    PLAN_ENS(c->part3, 3 * c->grid_pts128); PLAN_ENS(c->red3, 4); PLAN_ENS(c->cam2, 2); PLAN_ENS(c->scal, 16); c->att.p = c->scal.p + 8; c->att.cap = 8; c->att.owned = false; PLAN_ENS(c->respart, c->grid_pts256);
     PLAN_CHECK(c->flags.ensure(2));
 #undef PLAN_ENS
 #undef PLAN_CHECK
@@ -944,15 +944,17 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
 
     for (itno = 0; itno < itmax && !stop; ++itno) {
         // generation 3: once mu is known the tile kernel linearises AND prepares the first attempt (Z, E) in one pass
-        bool z_valid = false;
-        if (c->gen >= 3 && itno > 0) { rc = run_lin_tile(c, 1, mu, 0, compat ? 1 : 0); z_valid = true; }
+        bool z_valid = false, deferred = false;
+        if (c->gen >= 3 && itno > 0) { rc = run_lin_tile(c, 1, mu, 0, compat ? 1 : 0); z_valid = true; deferred = true; }
         else rc = run_linearize(c);
         if (rc) return rc;
         ++njev;
-        if ((rc = read_back(c, c->scal.p, 4, h))) return rc;
-        eab_inf = h[1]; p_L2 = h[2]; dmax = h[3];
-        if (eab_inf <= eps1) { dp_L2 = 0.0; stop = 1; break; }
-        if (itno == 0) mu = tau * dmax;
+        if (!deferred) {
+            if ((rc = read_back(c, c->scal.p, 4, h))) return rc;
+            eab_inf = h[1]; p_L2 = h[2]; dmax = h[3];
+            if (eab_inf <= eps1) { dp_L2 = 0.0; stop = 1; break; }
+            if (itno == 0) mu = tau * dmax;
+        }
         double mu_u = 0.0;          // damping accumulated on U's diagonal within this iteration (compat: not restored)
         bool first = true;
         while (1) {
@@ -960,7 +962,17 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
             // generation 3: Z / E depend on mu, so the tile linearisation runs once per attempt with the damping applied
             if ((rc = run_attempt(c, mu, mu_u, compat && !first, compat, nullptr, !z_valid))) return rc;
             z_valid = false;
-            if ((rc = read_back(c, c->att.p, 5, h))) return rc;
+            if (deferred) {
+                // mu was known, so the first attempt was launched behind the linearisation without a host round trip; the
+                // linearisation's scalars arrive with the attempt's (scal and att are one buffer).  When the gradient test
+                // stops the iteration here, the attempt's results are simply never looked at.
+                double hh[16];
+                if ((rc = read_back(c, c->scal.p, 16, hh))) return rc;
+                deferred = false;
+                eab_inf = hh[1]; p_L2 = hh[2]; dmax = hh[3];
+                if (eab_inf <= eps1) { dp_L2 = 0.0; stop = 1; break; }
+                for (int q = 0; q < 8; ++q) h[q] = hh[8 + q];
+            } else if ((rc = read_back(c, c->att.p, 5, h))) return rc;
             first = false;
             const bool singular = h[4] != 0.0;
             if (singular) fprintf(stderr, "argus_b200: singular matrix V*_i, increasing damping\n");
@@ -1007,6 +1019,7 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
             }
             nu = nu2;
         }
+        if (stop == 1) break;       // gradient test (deferred read-back): leaves the outer loop like the reference's break (:977-981)
         if (p_eL2 <= eps3_sq) stop = 5;
     }
     if (itno >= itmax) stop = 3;

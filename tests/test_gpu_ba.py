@@ -367,3 +367,27 @@ def test_almost_everything_fixed(ncon, mcon):
     assert ro == rg and list(io[5:]) == list(ig[5:]) and abs(io[1] - ig[1]) <= 1e-9 * io[1]
     assert rel_blocks(pg, po, m) < 1e-7
     assert np.array_equal(pg[:16 * mcon], p0[:16 * mcon]) and np.array_equal(pg[16 * m:16 * m + 3 * ncon], p0[16 * m:16 * m + 3 * ncon])
+
+
+@pytest.mark.parametrize("stop_at", [0, 2, 4])
+def test_gradient_stop_matches_oracle(golden_ba, stop_at):
+    """Stop reason 1 (||J^T e||_inf <= eps1, sba_levmar.c:977-981) at the first linearisation and at later ones - where the
+    solver has already queued the first damping attempt behind the linearisation and must discard it: iteration count,
+    function / Jacobian evaluations and linear systems must be the reference's (no extra attempt counted)."""
+    g = golden_ba
+    args = (g["G1_p0"], g["G1_x"], g["G1_vmask"], g["G1_rot0"], 2, 3)
+    # gradient norm the oracle sees at the linearisation of iteration `stop_at` = info[2] of a run stopped by itmax there
+    _, iprobe, _ = ba_port.port_motstr(*args, itmax=stop_at + 1)
+    if stop_at == 0:
+        eps1 = 1e30
+    else:
+        _, ia, _ = ba_port.port_motstr(*args, itmax=stop_at)          # info[2]: gradient at the last linearisation done
+        _, ib, _ = ba_port.port_motstr(*args, itmax=stop_at + 1)
+        assert ib[2] < ia[2]
+        eps1 = 0.5 * (ia[2] + ib[2])                                   # iteration stop_at's linearisation is the first below it
+    opts = [1e-3, eps1, 1e-12, 1e-12, 0.0]
+    po, io, ro = ba_port.port_motstr(*args, itmax=50, opts=opts)
+    assert int(io[6]) == 1
+    pg, ig, rg = ba.solve_motstr(g["G1_vmask"], g["G1_p0"], g["G1_rot0"], g["G1_x"], 2, 3, itmax=50, opts=opts)
+    assert rg == ro and list(ig[5:]) == list(io[5:]) and abs(ig[1] - io[1]) <= 1e-10 * io[1] and abs(ig[2] - io[2]) <= 1e-6 * io[2]
+    assert rel_blocks(pg, po, 4) < 1e-8
