@@ -13,9 +13,19 @@
  *                                 adata = struct globs_ {rot0params, nccalib, ncdist, cnp=16, pnp=3, mnp=2}
  *                                 (sbaprojs.h:123-156); call site R/argus_gui/sbaDriver.py:292 through
  *                                 python-sba's sba.SparseBundleAdjust.
+ *   argus_ba_mot_kdrts         <- sba_mot_levmar_x              SBA/sba.h:119-123, SBA/sba_levmar.c:1437-1980
+ *                                 with img_projsKDRT_x / _jac_x (sbaprojs.c:1261-1370), globs_.ptparams
+ *   argus_ba_str_kdrts         <- sba_str_levmar_x              SBA/sba.h:126-130, SBA/sba_levmar.c:1987-2540
+ *                                 with img_projsKDS_x / _jac_x (sbaprojs.c:1375-1445), globs_.camparams
  *   argus_dlt_triangulate      <- uv_to_xyz                     R/argus_gui/tools.py:296-337
  *   argus_dlt_reproj_error     <- get_repo_errors               R/argus_gui/tools.py:360-423
+ *   argus_dlt_reconstruct      <- both of the above in one pass (call sites argus-click:3283-3305, utils/DLCbatch.py:646-666)
  *   argus_undistort_points     <- undistort_pts (pinhole)       R/argus_gui/tools.py:129-148
+ *   argus_dlt_bootstrap        <- bootstrapXYZs, the 250-iteration loop      R/argus_gui/tools.py:448-544 (:513-527)
+ *   argus_dlt_fit              <- solve_dlt / OutlierWindow.getCoefficients   tools.py:220-280, sbaDriver.py:1027-1079
+ *   argus_pair_triangulate     <- Triangulator.triangulate      R/argus_gui/triangulate.py:27-212
+ *   argus_ba_create ... argus_ba_normal_equations: the resident-data form of the three LM drivers (no counterpart in the
+ *                                 reference, which re-allocates everything per call) and parity hooks for the tests
  *
  * Ownership: the caller owns every array; outputs are written into caller-allocated memory.  No entry point
  * calls exit(); errors are negative return codes (ARGUS_E_*).  There is no CPU fallback: without a CUDA
