@@ -20,6 +20,7 @@
 #include "ba_schur_mma.cuh"
 #include "ba_lin_tile.cuh"
 #include "ba_blockdiag.cuh"
+#include "ba_chol_coop.cuh"
 
 using namespace argus;
 
@@ -112,6 +113,7 @@ struct argus_ba_ctx {
     int gen = 3;
     int mode = kModeMotStr;   // which half of the parameters moves (argus_ba_set_mode)
     int schur_nw_pref = 12;
+    bool chol_coop = true;     // multi-SM Cholesky (ARGUS_CHOL_COOP=0 falls back to the single-CTA kernels)
     DevBuf<int32_t> tile_pt, tile_o; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
     DevBuf<uint8_t> obs_lpt, corder, pt_rank, vmask_dev; DevBuf<int32_t> idx_btot; int rank_mp = 16;
     DevBuf<uint8_t> cam_fix; bool cam_fix_on = false; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect, cholwork;
@@ -341,7 +343,16 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
         size_t rows = (size_t)(N > nbw ? N - nbw : 1);
         size_t sm = rows * (nbw + 1) * sizeof(double);
         if (sm < (size_t)N * sizeof(double)) sm = (size_t)N * sizeof(double);
-        if (c->gen >= 3 && N <= 832) k_chol_solve2<<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->cholwork.p, c->flags.p + 1);
+        if (c->gen >= 3 && c->chol_coop && N >= 320) {
+            // multi-SM factorisation (cooperative grid): the single-CTA kernels below are latency bound
+            ARGUS_CUDA_CHECK(cudaMemsetAsync(c->flags.p + 2, 0, sizeof(int), c->stream));
+            double *Sp = c->S.p, *xp = c->da_free.p, *wp = c->cholwork.p; const double *Ep = c->E.p; int Nn = N;
+            int *st = c->flags.p + 1, *fl = c->flags.p + 2;
+            void *args[] = {&Sp, &Ep, &xp, &Nn, &wp, &st, &fl};
+            const int nblk = (N + 31) / 32;
+            int grid = std::min(c->sms, std::max(2, (nblk - 1) * nblk / 2));
+            ARGUS_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)k_chol_coop, dim3(grid), dim3(kCoopThreads), args, 0, c->stream));
+        } else if (c->gen >= 3 && N <= 832) k_chol_solve2<<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->cholwork.p, c->flags.p + 1);
         else if (nbw == 32) k_chol_solve_t<32><<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->flags.p + 1);
         else k_chol_solve_t<16><<<1, kCholThreads, sm, c->stream>>>(c->S.p, c->E.p, c->da_free.p, N, c->flags.p + 1);
     }
@@ -582,6 +593,8 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
         }
     }
     if (const char *e = getenv("ARGUS_SCHUR_NW")) c->schur_nw_pref = atoi(e);
+    if (const char *e = getenv("ARGUS_CHOL_COOP")) c->chol_coop = atoi(e) != 0;
+    { int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device); if (!coop) c->chol_coop = false; }
     if (getenv("ARGUS_LIN_DEBUG")) { ARGUS_CUDA_CHECK(cudaMalloc(&c->lin_dbg, 8 * sizeof(unsigned long long))); ARGUS_CUDA_CHECK(cudaMemset(c->lin_dbg, 0, 8 * sizeof(unsigned long long))); }
     *out = c;
     return ARGUS_OK;
@@ -715,7 +728,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     PLAN_CHECK(c->tile_pt.ensure(tiles.size())); PLAN_CHECK(c->tile_o.ensure(tiles.size())); PLAN_CHECK(c->blk_jk.ensure(hjk.size())); PLAN_CHECK(c->blk_pair.ensure(hpair.size()));
     PLAN_CHECK(c->zsign.ensure((size_t)n)); if (c->gen >= 2 && c->mode == kModeMotStr) { PLAN_ENS(c->Z, 48 * nobs); }
     PLAN_CHECK(c->obs_lpt.ensure((size_t)nobs)); PLAN_CHECK(c->corder.ensure((size_t)nobs)); PLAN_CHECK(c->cstart.ensure((size_t)c->ntiles * (m + 1)));
-    PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1024);
+    PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1024 + N + 32);
     PLAN_CHECK(c->pt_rank.ensure(c->mode == kModeMotStr ? (size_t)c->ntiles * kTilePts * c->rank_mp : 1));
     PLAN_ENS(c->vmask_dev, n * m); PLAN_ENS(c->idx_btot, (n + kIdxPts - 1) / kIdxPts + 1);
     PLAN_ENS(c->obs_ptr, n + 1); PLAN_ENS(c->obs_cam, nobs); PLAN_ENS(c->obs_uv, nobs); PLAN_ENS(c->pt_mask, n);
@@ -728,7 +741,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     PLAN_ENS(c->Epart, (int64_t)c->grid_pts128 * m * 16); PLAN_ENS(c->Spart, (int64_t)std::max(c->nchunks, c->schur_nchunk) * c->npairs * 256);
     PLAN_ENS(c->red2, (int64_t)c->npairs * 256 + m * 16); PLAN_ENS(c->S, (int64_t)N * N); PLAN_ENS(c->E, N); PLAN_ENS(c->da_free, N); PLAN_ENS(c->da_full, 16 * m);
     PLAN_ENS(c->part3, 3 * c->grid_pts128); PLAN_ENS(c->red3, 4); PLAN_ENS(c->cam2, 2); PLAN_ENS(c->scal, 16); c->att.p = c->scal.p + 8; c->att.cap = 8; c->att.owned = false; PLAN_ENS(c->respart, c->grid_pts256);
-    PLAN_CHECK(c->flags.ensure(2));
+    PLAN_CHECK(c->flags.ensure(4));
 #undef PLAN_ENS
 #undef PLAN_CHECK
         return cudaSuccess;
