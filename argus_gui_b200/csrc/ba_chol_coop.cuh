@@ -18,44 +18,61 @@ namespace argus {
 
 constexpr int kCoopThreads = 256;
 
-// factor the 32 x 32 diagonal block at kb (lower triangle of S) in shared memory, write L back, its inverse to Dinv (global)
+// factor the 32 x 32 diagonal block at kb (lower triangle of S), write L back and its inverse to Dinv (global).
+// The factorisation and the inversion are the serial part of every panel, so they run in ONE warp without block barriers:
+// lane i keeps row i of the block in registers, the pivot row travels by shuffles (right-looking Cholesky, 1/sqrt(pivot) from
+// rsqrt); then lane c forms column c of L^-1 by forward substitution with L read from shared memory (broadcast loads).
 __device__ void coop_factor_diag(double *__restrict__ S, int N, int kb, double *__restrict__ Dinv, int *fail,
                                  double (*D)[33], double (*Di)[33])
 {
+    __shared__ double s_rinv[32];
+    __shared__ int s_fail;
     const int tid = threadIdx.x, nb = min(32, N - kb);
     for (int t = tid; t < 32 * 32; t += blockDim.x) {
         const int r = t >> 5, c = t & 31;
         D[r][c] = (r < nb && c < nb && c <= r) ? S[(int64_t)(kb + r) * N + kb + c] : ((r == c) ? 1.0 : 0.0);
     }
-    __syncthreads();
-    __shared__ int s_fail;
     if (tid == 0) s_fail = 0;
     __syncthreads();
-    for (int j = 0; j < nb; ++j) {
-        if (tid == 0) { const double d = D[j][j]; if (!(d > 0.0)) s_fail = 1; else D[j][j] = sqrt(d); }
-        __syncthreads();
-        if (s_fail) break;
-        const double ljj = D[j][j];
-        if (tid > j && tid < nb) D[tid][j] /= ljj;
-        __syncthreads();
-        const int w = nb - 1 - j;
-        for (int t = tid; t < w * w; t += blockDim.x) {
-            const int r = j + 1 + t / w, c = j + 1 + t % w;
-            if (c <= r) D[r][c] -= D[r][j] * D[c][j];
-        }
-        __syncthreads();
-    }
-    if (s_fail) { if (tid == 0) { *(volatile int *)fail = 1; __threadfence(); } __syncthreads(); return; }
-    // inverse of the lower-triangular factor: column c by forward substitution, one column per thread
     if (tid < 32) {
-        const int c = tid;
-        for (int r = 0; r < 32; ++r) {
-            double s = (r == c) ? 1.0 : 0.0;
-            for (int q = c; q < r; ++q) s -= D[r][q] * Di[q][c];
-            Di[r][c] = (r >= c) ? s / D[r][r] : 0.0;
+        const int lane = tid;
+        double a[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) a[c] = D[lane][c];
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const double piv = __shfl_sync(0xffffffffu, a[j], j);
+            if (!(piv > 0.0)) bad = true;
+            const double ri = rsqrt(piv);
+            const double lij = a[j] * ri;                       // lane j: sqrt(pivot); lanes below: l_ij
+            a[j] = lij;
+            if (lane == j) s_rinv[j] = ri;
+#pragma unroll
+            for (int c = j + 1; c < 32; ++c) {
+                const double lc = __shfl_sync(0xffffffffu, lij, c);
+                a[c] -= lij * lc;                                // meaningful for c <= lane
+            }
         }
+        if (bad) { if (lane == 0) s_fail = 1; }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) D[lane][c] = (c <= lane) ? a[c] : 0.0;
+        __syncwarp();
+        // column `lane` of L^-1: x_r = (delta_r,lane - sum_{q<r} L[r][q] x_q) / L[r][r]   (x_q = 0 for q < lane)
+        double x[32];
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+            double s0 = (r == lane) ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+            for (int q = 0; q + 1 < r; q += 2) { s0 -= D[r][q] * x[q]; s1 -= D[r][q + 1] * x[q + 1]; }
+            if (r & 1) s0 -= D[r][r - 1] * x[r - 1];
+            x[r] = (r >= lane) ? (s0 + s1) * s_rinv[r] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 32; ++r) Di[r][lane] = x[r];
     }
     __syncthreads();
+    if (s_fail) { if (tid == 0) { *(volatile int *)fail = 1; __threadfence(); } __syncthreads(); return; }
     for (int t = tid; t < 32 * 32; t += blockDim.x) {
         const int r = t >> 5, c = t & 31;
         Dinv[t] = Di[r][c];

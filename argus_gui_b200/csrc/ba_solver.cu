@@ -114,6 +114,7 @@ struct argus_ba_ctx {
     int mode = kModeMotStr;   // which half of the parameters moves (argus_ba_set_mode)
     int schur_nw_pref = 12;
     bool chol_coop = true;     // multi-SM Cholesky (ARGUS_CHOL_COOP=0 falls back to the single-CTA kernels)
+    int chol_coop_min = 192;   // smallest reduced system that goes to it (ARGUS_CHOL_COOP_MIN)
     DevBuf<int32_t> tile_pt, tile_o; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
     DevBuf<uint8_t> obs_lpt, corder, pt_rank, vmask_dev; DevBuf<int32_t> idx_btot; int rank_mp = 16;
     DevBuf<uint8_t> cam_fix; bool cam_fix_on = false; DevBuf<uint16_t> cstart; DevBuf<double> Upart2, Edirect, cholwork;
@@ -343,7 +344,7 @@ int run_attempt(argus_ba_ctx *c, double mu, double mu_u, int use_state, int writ
         size_t rows = (size_t)(N > nbw ? N - nbw : 1);
         size_t sm = rows * (nbw + 1) * sizeof(double);
         if (sm < (size_t)N * sizeof(double)) sm = (size_t)N * sizeof(double);
-        if (c->gen >= 3 && c->chol_coop && N >= 320) {
+        if (c->gen >= 3 && c->chol_coop && N >= c->chol_coop_min) {
             // multi-SM factorisation (cooperative grid): the single-CTA kernels below are latency bound
             ARGUS_CUDA_CHECK(cudaMemsetAsync(c->flags.p + 2, 0, sizeof(int), c->stream));
             double *Sp = c->S.p, *xp = c->da_free.p, *wp = c->cholwork.p; const double *Ep = c->E.p; int Nn = N;
@@ -594,6 +595,7 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
     }
     if (const char *e = getenv("ARGUS_SCHUR_NW")) c->schur_nw_pref = atoi(e);
     if (const char *e = getenv("ARGUS_CHOL_COOP")) c->chol_coop = atoi(e) != 0;
+    if (const char *e = getenv("ARGUS_CHOL_COOP_MIN")) c->chol_coop_min = atoi(e);
     { int coop = 0; cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device); if (!coop) c->chol_coop = false; }
     if (getenv("ARGUS_LIN_DEBUG")) { ARGUS_CUDA_CHECK(cudaMalloc(&c->lin_dbg, 8 * sizeof(unsigned long long))); ARGUS_CUDA_CHECK(cudaMemset(c->lin_dbg, 0, 8 * sizeof(unsigned long long))); }
     *out = c;

@@ -2,7 +2,7 @@ import sys, os; sys.path.insert(0, '/root/repo')
 if len(sys.argv) > 1: os.environ["ARGUS_CHOL_COOP"] = sys.argv[1]
 import bench
 from argus_gui_b200 import ba, scenes
-for (m, n, v) in ((24, 100_000, 12), (32, 100_000, 12), (40, 100_000, 12), (54, 100_000, 12), (64, 100_000, 12)):
+for (m, n, v) in ((8, 100_000, 6), (16, 100_000, 10), (24, 100_000, 12), (32, 100_000, 12), (54, 100_000, 12), (64, 100_000, 12)):
     s = scenes.make_ba_scene(m, n, v, seed=m)
     p0, rot0 = scenes.pack_ba_problem(s["cams0"], s["pts0"])
     B = ba.BundleAdjuster().upload(s["vmask"], p0, rot0, s["x"], 0, 0)
