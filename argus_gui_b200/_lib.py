@@ -42,6 +42,11 @@ SIGNATURES = {
     "argus_ba_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_void_p]),
     "argus_ba_destroy": (None, [ctypes.c_void_p]),
     "argus_ba_set_comm": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ALLREDUCE_FN, ctypes.c_void_p]),
+    "argus_set_default_device": (ctypes.c_int, [ctypes.c_int]),
+    "argus_nccl_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "argus_ba_comm_init_nccl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "argus_ba_set_comm_nccl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "argus_ba_set_graph": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "argus_ba_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "argus_ba_set_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
@@ -96,5 +101,5 @@ def check(rc, what):
     if rc == ARGUS_E_ARG:
         raise ValueError("%s: invalid argument" % what)
     if rc == ARGUS_E_COMM:
-        raise RuntimeError("%s: all-reduce hook failed" % what)
+        raise RuntimeError("%s: the all-reduce (NCCL or hook) failed" % what)
     return rc

@@ -3,8 +3,9 @@
 ``solve_motstr`` is the one-shot drop-in for ``sba_motstr_levmar_x`` + ``img_projsKDRTS_x/_jac_x``
 (sba-1.6p/sba_levmar.c:449-1428); ``BundleAdjuster`` keeps the problem resident in HBM (bench, parity hooks,
 multi-GPU).  Multi-GPU is one process per GPU: points (with all their observations) are block-partitioned over
-the ranks by ``shard_points`` and the only exchange is the all-reduce hook the C solver calls
-(``torch.distributed.all_reduce`` on NCCL).
+the ranks by ``shard_points`` and the only exchange are the two all-reduces per damping attempt, which the C solver
+issues through NCCL itself (``BundleAdjuster.init_nccl``: the communicator is created inside the library, torch.distributed
+only carries the 128-byte NCCL id from rank 0 to the others) or through a caller-supplied hook (``set_comm``).
 """
 import ctypes
 import numpy as np
@@ -55,6 +56,7 @@ class BundleAdjuster:
         self.h = h
         _lib.check(self.lib.argus_ba_set_mode(self.h, self.MODES[mode]), "argus_ba_set_mode")
         self.n = self.m = 0
+        self.device = int(device)
         self._cb = None
         self._keep = None
 
@@ -80,6 +82,23 @@ class BundleAdjuster:
                 return 1
         self._cb = _lib.ALLREDUCE_FN(_cb)
         _lib.check(self.lib.argus_ba_set_comm(self.h, int(rank), int(world), self._cb, None), "argus_ba_set_comm")
+
+    def init_nccl(self, rank, world, group=None):
+        """Create this rank's NCCL communicator inside the library (collective over the ranks).  ``torch.distributed`` (any
+        backend) is only used to hand rank 0's ncclUniqueId to the other ranks."""
+        import torch
+        import torch.distributed as dist
+        uid = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            _lib.check(self.lib.argus_nccl_unique_id(_ptr(uid)), "argus_nccl_unique_id")
+        box = [uid.tobytes()]
+        dist.broadcast_object_list(box, src=0, group=group)
+        uid = np.frombuffer(box[0], dtype=np.uint8).copy()
+        _lib.check(self.lib.argus_ba_comm_init_nccl(self.h, int(rank), int(world), _ptr(uid)), "argus_ba_comm_init_nccl")
+        return self
+
+    def set_graph(self, on):
+        _lib.check(self.lib.argus_ba_set_graph(self.h, 1 if on else 0), "argus_ba_set_graph")
 
     def upload(self, vmask, p, rot0, x, nccalib=0, ncdist=0, ncon=0, mcon=0):
         vmask = _as_mask(vmask)
@@ -118,8 +137,16 @@ class BundleAdjuster:
             _lib.check(ret, "argus_ba_solve")
         return ret, info
 
-    def download(self):
-        p = np.zeros(16 * self.m + 3 * self.n)
+    def download(self, out=None):
+        """Current parameter vector [16 m | 3 n]; ``out``: a C-contiguous float64 array to fill in place (a pinned one makes
+        the copy run at full PCIe speed)."""
+        size = 16 * self.m + 3 * self.n
+        if out is None:
+            p = np.empty(size)
+        else:
+            if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous and out.size == size):
+                raise ValueError("out must be a C-contiguous float64 array of 16 m + 3 n entries")
+            p = out.reshape(-1)
         _lib.check(self.lib.argus_ba_download(self.h, _ptr(p)), "argus_ba_download")
         return p
 
@@ -171,6 +198,8 @@ def solve_motstr(vmask, p, rot0, x, nccalib=0, ncdist=0, itmax=DEFAULT_ITMAX, op
         p = np.array(p, dtype=np.float64, copy=True).ravel()
     rot0 = np.ascontiguousarray(rot0, dtype=np.float64).ravel()
     x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    if p.size != 16 * m + 3 * n or rot0.size != 4 * m or x.size != 2 * int(np.count_nonzero(vmask)):
+        raise ValueError("inconsistent BA problem sizes")
     opts = np.ascontiguousarray(opts, dtype=np.float64)
     info = np.zeros(10)
     ret = lib.argus_ba_motstr_kdrts(n, int(ncon), m, int(mcon), _ptr(vmask), _ptr(p), _ptr(rot0), _ptr(x), int(nccalib), int(ncdist),
@@ -250,14 +279,15 @@ def shard_problem(vmask, p, x, m, world, rank, balance_observations=False):
     return vmask[lo:hi], p_loc, x[rowptr[lo]:rowptr[hi]], (lo, hi)
 
 
-def torch_allreduce_hook(group=None):
-    """All-reduce hook backed by ``torch.distributed`` (NCCL on GPUs).  The C solver hands a device pointer; it is
-    wrapped without a copy and reduced on the solver's stream."""
+def torch_allreduce_hook(group=None, device=None):
+    """All-reduce hook backed by ``torch.distributed`` (NCCL on GPUs), the alternative to ``BundleAdjuster.init_nccl``.  The C
+    solver hands a device pointer; it is wrapped without a copy and reduced on the solver's stream.  ``device``: the CUDA
+    device index of the BundleAdjuster this hook serves (default: torch's current device when the hook is created)."""
     import torch
     import torch.distributed as dist
+    dev = torch.cuda.current_device() if device is None else int(device)
 
     def hook(ptr, count, op, stream):
-        dev = torch.cuda.current_device()
         # zero-copy view of the solver's device buffer
         iface = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False), "version": 3, "strides": None}
 

@@ -13,10 +13,11 @@ enum { kModeMotStr = 0, kModeMot = 1, kModeStr = 2 };
 
 // scalars of one linearisation (:1774-1812 / :2319-2357): scal = {cost, ||J^T e||_inf, ||p||^2, max diagonal}, each over the
 // moving half only (p is the camera vector for motion-only, the point vector for structure-only)
-__global__ void k_bd_finalize(int mode, const double *__restrict__ Ured, const double *__restrict__ cam, int m, int mcon,
+__global__ void k_bd_finalize(int mode, const double *__restrict__ Ured, ParamBufs pbuf, const LmState *__restrict__ st, int m, int mcon,
                               const double *__restrict__ sum2, const double *__restrict__ max2, double *__restrict__ scal)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (threadIdx.x != 0 || blockIdx.x != 0 || st->done) return;
+    const double *cam = pbuf.cam[st->cur_cam];
     double inf = 0.0, dmax = 2.2250738585072014e-308 /* DBL_MIN */, psq = 0.0;
     if (mode == kModeMot) {
         for (int j = mcon; j < m; ++j) {
@@ -34,10 +35,13 @@ __global__ void k_bd_finalize(int mode, const double *__restrict__ Ured, const d
 // copy, then dpotrs), trial cameras, ||da||^2 and dL = sum da (mu da + ea) (:1858-1895).  mu_diag is the damping that sits
 // on the diagonal (it accumulates over rejected attempts in sba-1.6 compatibility mode), mu the current damping.
 //   out2 = {||da||^2, dL}; flags[1] = 1 when every system was positive definite.
-__global__ void __launch_bounds__(64) k_mot_solve(int m, int mcon, const double *__restrict__ Ured, double mu_diag, double mu,
-                                                  const double *__restrict__ cam, double *__restrict__ cam_new,
-                                                  double *__restrict__ out2, int *__restrict__ flags)
+__global__ void __launch_bounds__(64) k_mot_solve(int m, int mcon, const double *__restrict__ Ured, ParamBufs pbuf,
+                                                  const LmState *__restrict__ st, double *__restrict__ out2, int *__restrict__ flags)
 {
+    if (st->done) return;
+    const double mu_diag = st->mu_u, mu = st->mu;
+    const double *cam = pbuf.cam[st->cur_cam];
+    double *cam_new = pbuf.cam[st->cur_cam ^ 1];
     __shared__ double s_d2[ARGUS_BA_MAX_CAMS], s_dl[ARGUS_BA_MAX_CAMS];
     __shared__ int s_ok[ARGUS_BA_MAX_CAMS];
     const int j = threadIdx.x;
@@ -94,11 +98,12 @@ __global__ void __launch_bounds__(64) k_mot_solve(int m, int mcon, const double 
 
 // one thread per point: inverse of V_i + mu_diag I through LDL^T; a pivot that is not positive is what makes the reference's
 // 3x3 dpotrf fail (-> the attempt is rejected, :2398).  Vinv feeds k_backsub_recompute with da = 0: db_i = Vinv_i eb_i.
-__global__ void __launch_bounds__(256) k_str_invert(int64_t n, int64_t ncon, double mu_diag, const double *__restrict__ V,
+__global__ void __launch_bounds__(256) k_str_invert(int64_t n, int64_t ncon, const LmState *__restrict__ st, const double *__restrict__ V,
                                                     double *__restrict__ Vinv, int *__restrict__ flags)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || i < ncon) return;
+    if (i >= n || i < ncon || st->done) return;
+    const double mu_diag = st->mu_u;
     double vv[6], li[3], di[3];
     for (int t = 0; t < 6; ++t) vv[t] = V[6 * i + t];
     vv[0] += mu_diag; vv[3] += mu_diag; vv[5] += mu_diag;

@@ -83,8 +83,10 @@ __device__ void coop_factor_diag(double *__restrict__ S, int N, int kb, double *
 
 __global__ void __launch_bounds__(kCoopThreads) k_chol_coop(double *__restrict__ S, const double *__restrict__ E, double *__restrict__ x,
                                                             int N, double *__restrict__ work, int *__restrict__ status,
-                                                            int *fail /* zeroed by the host; written by the CTA that factors a diagonal block */)
+                                                            int *fail /* zero on entry (the controller clears it); written by the CTA that factors a diagonal block */,
+                                                            const int *__restrict__ done)
 {
+    if (*done) return;
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ double A[32][33], B[32][33];

@@ -25,6 +25,36 @@ struct BaProblem {
     const double   *rot0;     // 4m
 };
 
+// ---- Levenberg-Marquardt state, resident on the device ------------------------------------------------
+// The damping loop of sba_motstr_levmar_x / sba_mot_levmar_x / sba_str_levmar_x (sba_levmar.c:791-1357, :1694-1950,
+// :2239-2495) runs as a single-thread controller kernel at the end of every damping attempt (ba_lm_controller.cuh); every
+// other kernel of an attempt reads what it needs (damping, which parameter buffer is current, "the loop has ended") from
+// this block.  The host therefore never sits between two attempts: it queues attempts (a CUDA graph each) ahead of the
+// device and only looks at asynchronous snapshots of this block to know when to stop queueing.
+struct LmState {
+    // inputs of the next attempt
+    double mu;            // damping term
+    double mu_u;          // what the attempt adds to U's (and, block-diagonal drivers, V's) diagonal: mu, or in sba-1.6 mode
+                          // the sum of the dampings of the attempts rejected in this iteration (diagonals never restored)
+    int use_state;        // sba-1.6 mode retry: V's diagonal is what the previous inversion left behind
+    int write_state;
+    int cur_cam, cur_pts; // which buffer of each parameter pair holds the current estimate
+    int done;             // the loop has ended: every queued kernel returns immediately
+    int fresh;            // the next attempt linearises at a new point (counts as a Jacobian evaluation, gradient stop test)
+    // controller
+    int mode, compat, itmax, itno, stop, nu, nfev, njev, err, nsingular, nlog, logcap;
+    double nlss, nblocks;
+    double tau, eps1, eps2, eps2_sq, eps3_sq, eps4_sq;
+    double p_eL2, init_p_eL2, eab_inf, p_L2, dmax, dp_L2;
+    double *lmlog;        // optional per-attempt log (verbose > 1), kLmLogDoubles per entry
+};
+
+// the two copies of the parameter vector (current estimate / trial point); LmState::cur_* says which is which
+struct ParamBufs {
+    double *cam[2];
+    double *pts[2];
+};
+
 constexpr int kU = 152;       // per camera: 136 upper-triangle entries of U_j + 16 of ea_j
 
 // index of (r,c), r<=c, in the packed upper triangle of a 16x16 symmetric block

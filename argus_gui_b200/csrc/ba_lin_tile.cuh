@@ -38,7 +38,6 @@ struct LinTileOut {
     double *Upart;               // grid x m x 320
     double *scpart;              // grid x 4: cost, max|eb|, max diag V, sum pts^2
     int *flag;
-    unsigned long long *dbg;     // optional per-phase clock counters (nullptr in production)
 };
 
 // ---- static index construction (once per upload; visibility never changes during a solve) ----
@@ -171,10 +170,14 @@ __device__ __forceinline__ void st_global_v4(double *p, double a, double b, doub
 }
 
 template <int MC>
-__global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem pb, TilePlan tp, LinTilePlan lp, const double *__restrict__ cam,
-                                                  const double *__restrict__ pts, int mode, double mu, int use_state, int write_state,
-                                                  LinTileOut out)
+__global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem pb, TilePlan tp, LinTilePlan lp, ParamBufs pbuf,
+                                                  const LmState *__restrict__ st, int mode, LinTileOut out)
 {
+    if (st->done) return;
+    const double *__restrict__ cam = pbuf.cam[st->cur_cam];
+    const double *__restrict__ pts = pbuf.pts[st->cur_pts];
+    const double mu = st->mu;
+    const int use_state = st->use_state, write_state = st->write_state;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);
     double *Ga = reinterpret_cast<double *>(smem_raw + (((size_t)pb.m * sizeof(CamConst) + 15) & ~(size_t)15));   // TO x 36 (16-byte aligned)
@@ -198,8 +201,6 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
 
     double cost = 0.0, ebmax = 0.0, vdmax = -1.79769313486231570e308, ptsq = 0.0;
 
-    long long tk = clock64();
-#define LIN_TICK(ph) do { if (out.dbg && tid == 0) { const long long t1_ = clock64(); atomicAdd(out.dbg + (ph), (unsigned long long)(t1_ - tk)); tk = t1_; } } while (0)
     // tile bounds are loaded one tile ahead (they end up in uniform registers), and the next tile's index data / measurements /
     // points are pulled into L2 while this tile computes: the dependent loads at the top of a tile then see L2, not DRAM, latency
     int nx_p0 = 0, nx_p1 = 0, nx_o0 = 0, nx_o1 = 0;
@@ -220,7 +221,6 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
         if (tid < npts) { const int64_t i = p0 + tid; s_M[3 * tid] = pts[3 * i]; s_M[3 * tid + 1] = pts[3 * i + 1]; s_M[3 * tid + 2] = pts[3 * i + 2]; }
         if (tid <= pb.m) s_cst[tid] = lp.cstart[(size_t)tile * (pb.m + 1) + tid];
         __syncthreads();
-        LIN_TICK(0);
 
         // ---- P1: one thread per observation ----
         if (tid < nobs_t) {
@@ -266,7 +266,6 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             if (tid == 64) { prefetch_l2(pb.obs_ptr + nx_p0); prefetch_l2(pb.obs_ptr + nx_p0 + 31); prefetch_l2(lp.cstart + (size_t)ntile * (pb.m + 1)); }
         }
         __syncthreads();
-        LIN_TICK(1);
 
         // ---- P2: 8 threads per point ----
         {
@@ -337,7 +336,6 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             }
         }
         __syncthreads();
-        LIN_TICK(2);
 
         // ---- P3: per observation: e' and Z ----
         if (mode != 0 && tid < nobs_t) {
@@ -374,7 +372,6 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             }
         }
         __syncthreads();
-        LIN_TICK(3);
 
         // ---- P4: Gram per camera on the tensor pipe (the cameras a warp owns advance together: independent DMMA chains) ----
         {
@@ -412,9 +409,7 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             }
         }
         __syncthreads();
-        LIN_TICK(4);
     }
-#undef LIN_TICK
 
     {   // per-CTA Gram fragments; cameras nobody owns (fixed ones) are written as zeros
         double *up = out.Upart + (size_t)blockIdx.x * pb.m * kUfrag;
@@ -440,9 +435,10 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
 // Also reduces the scalar partials: sum2 = {cost, sum pts^2}, max2 = {max|eb|, max diag V}.  grid = m blocks of 192.
 __global__ void __launch_bounds__(192) k_lin_tile_reduce(int m, int nparts, const double *__restrict__ Upart, const double *__restrict__ scpart,
                                                          double *__restrict__ Ured, double *__restrict__ Eout, double *__restrict__ sum2,
-                                                         double *__restrict__ max2)
+                                                         double *__restrict__ max2, const int *__restrict__ done)
 {
     const int j = blockIdx.x, t = threadIdx.x;
+    if (*done) return;
     if (t < 168) {
         // element -> (tile, row, col) of the 24-column Gram matrix
         int r, c;
@@ -475,12 +471,18 @@ __global__ void __launch_bounds__(192) k_lin_tile_reduce(int m, int nparts, cons
 // HBM except the measurement: the Jacobian is re-evaluated (about 6x cheaper than streaming 384 B of W per observation).
 //   db_i = V*_i^-1 (eb_i - sum_j B_ij^T (A_ij da_j))      (sba_levmar.c:1215-1256, W_ij^T da_j = B_ij^T A_ij da_j)
 //   trial point, cost at (cam_new, pts_new)                 (sba_levmar.c:1261-1288)
-__global__ void __launch_bounds__(128) k_backsub_recompute(BaProblem pb, double mu, const double *__restrict__ cam,
-                                                           const double *__restrict__ cam_new, const double *__restrict__ da,
-                                                           const double *__restrict__ pts, const double *__restrict__ Vinv,
-                                                           const double *__restrict__ eb, double *__restrict__ pts_new,
-                                                           double *__restrict__ dbout, double *__restrict__ part)
+//   cam_moves = 0: the structure-only driver (trial cameras = current cameras, da = 0)
+__global__ void __launch_bounds__(128) k_backsub_recompute(BaProblem pb, ParamBufs pbuf, const LmState *__restrict__ st, int cam_moves,
+                                                           const double *__restrict__ da, const double *__restrict__ Vinv,
+                                                           const double *__restrict__ eb, double *__restrict__ dbout,
+                                                           double *__restrict__ part)
 {
+    if (st->done) return;
+    const double mu = st->mu;
+    const double *__restrict__ cam = pbuf.cam[st->cur_cam];
+    const double *__restrict__ cam_new = pbuf.cam[st->cur_cam ^ (cam_moves ? 1 : 0)];
+    const double *__restrict__ pts = pbuf.pts[st->cur_pts];
+    double *__restrict__ pts_new = pbuf.pts[st->cur_pts ^ 1];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);          // old cameras
     CamConst *sn = sc + pb.m;                                        // trial cameras

@@ -70,8 +70,6 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// Bridge from the generation-1 linearisation (W, V, eb resident): per point damp + LDL^T, Z = W L^-T |D|^-1/2, sign mask,
-// V*^-1 (for the back-substitution) and c_i = V*^-1 eb_i; E_j partials as in k_prepare.  One thread per point.
 // Z in HBM: per tile of points one block of 48 * nobs_t doubles, chunk-major inside the block: the 12 four-double chunks of an
 // observation's 16 x 3 row (chunk = zperm / 4) live in 12 planes of nobs_t chunks each, so that the one-thread-per-observation
 // producer writes consecutive 32-byte chunks (coalesced) and the Schur kernel copies a tile plane by plane.
@@ -79,67 +77,6 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 __host__ __device__ __forceinline__ int64_t z_index(int64_t o0, int nobs_t, int lk, int e)
 {
     return 48 * o0 + ((int64_t)(e >> 2) * nobs_t + lk) * 4 + (e & 3);
-}
-
-__global__ void __launch_bounds__(128) k_make_z(BaProblem pb, TilePlan tp, double mu, int use_state, int write_state,
-                                                const double *__restrict__ V, const double *__restrict__ eb,
-                                                double *__restrict__ vstate, const double *__restrict__ W, double *__restrict__ Z,
-                                                uint8_t *__restrict__ zsign, double *__restrict__ Vinv, double *__restrict__ Epart,
-                                                int *__restrict__ flag)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *Es = reinterpret_cast<double *>(smem_raw);      // m x 16
-    for (int t = threadIdx.x; t < pb.m * 16; t += blockDim.x) Es[t] = 0.0;
-    __syncthreads();
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < pb.n; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = base + threadIdx.x;
-        if (i >= pb.n) continue;
-        if (i < pb.ncon) { zsign[i] = 0; continue; }
-        double v[6];
-#pragma unroll
-        for (int t = 0; t < 6; ++t) v[t] = V[6 * i + t];
-        if (use_state) { v[0] = vstate[3 * i]; v[3] = vstate[3 * i + 1]; v[5] = vstate[3 * i + 2]; }
-        v[0] += mu; v[3] += mu; v[5] += mu;
-        double li[3], di[3];
-        if (!sym3_ldl_inv(v, li, di)) { atomicOr(flag, 1); zsign[i] = 0; continue; }
-        const double n00 = di[0] + li[0] * li[0] * di[1] + li[1] * li[1] * di[2];
-        const double n01 = li[0] * di[1] + li[1] * li[2] * di[2];
-        const double n02 = li[1] * di[2];
-        const double n11 = di[1] + li[2] * li[2] * di[2];
-        const double n12 = li[2] * di[2];
-        const double n22 = di[2];
-        double *Ni = Vinv + 6 * i;
-        Ni[0] = n00; Ni[1] = n01; Ni[2] = n02; Ni[3] = n11; Ni[4] = n12; Ni[5] = n22;
-        if (write_state) { vstate[3 * i] = n00; vstate[3 * i + 1] = n11; vstate[3 * i + 2] = n22; }
-        const double b0 = eb[3 * i], b1 = eb[3 * i + 1], b2 = eb[3 * i + 2];
-        const double c0 = n00 * b0 + n01 * b1 + n02 * b2, c1 = n01 * b0 + n11 * b1 + n12 * b2, c2 = n02 * b0 + n12 * b1 + n22 * b2;
-        const double s0 = sqrt(fabs(di[0])), s1 = sqrt(fabs(di[1])), s2 = sqrt(fabs(di[2]));
-        zsign[i] = (uint8_t)((di[0] < 0.0 ? 1 : 0) | (di[1] < 0.0 ? 2 : 0) | (di[2] < 0.0 ? 4 : 0));
-        const int k1 = pb.obs_ptr[i + 1];
-        int tl = 0, th = tp.ntiles - 1;                    // the tile of point i (tile_pt is ascending)
-        while (tl < th) { const int tm = (tl + th + 1) >> 1; if (tp.tile_pt[tm] <= i) tl = tm; else th = tm - 1; }
-        const int o0 = tp.tile_o[tl], nobs_t = tp.tile_o[tl + 1] - o0;
-        for (int k = pb.obs_ptr[i]; k < k1; ++k) {
-            const int j = pb.obs_cam[k];
-            if (j < pb.mcon) {
-#pragma unroll
-                for (int t = 0; t < 48; ++t) Z[z_index(o0, nobs_t, k - o0, t)] = 0.0;
-                continue;
-            }
-            const double *Wk = W + 48 * (int64_t)k;
-#pragma unroll
-            for (int r = 0; r < 16; ++r) {
-                const double w0 = Wk[3 * r], w1 = Wk[3 * r + 1], w2 = Wk[3 * r + 2];
-                Z[z_index(o0, nobs_t, k - o0, zperm(r, 0))] = w0 * s0;
-                Z[z_index(o0, nobs_t, k - o0, zperm(r, 1))] = (li[0] * w0 + w1) * s1;
-                Z[z_index(o0, nobs_t, k - o0, zperm(r, 2))] = (li[1] * w0 + li[2] * w1 + w2) * s2;
-                const double s = w0 * c0 + w1 * c1 + w2 * c2;
-                if (s != 0.0) atomicAdd(Es + 16 * j + r, s);
-            }
-        }
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < pb.m * 16; t += blockDim.x) Epart[(int64_t)blockIdx.x * pb.m * 16 + t] = Es[t];
 }
 
 // The Schur kernel.  grid = (nchunk, G); NW consumer warps, each owning NB blocks; the copy producer is lane 0 of warp 0
@@ -171,8 +108,9 @@ __device__ __forceinline__ double flip_sign(double v, uint32_t bit)      // bit 
 template <int NB, int NW, int PROD>
 __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb, TilePlan tp, SchurPlan sp, const double *__restrict__ Z,
                                                                  const uint8_t *__restrict__ zsign, const uint8_t *__restrict__ pt_rank,
-                                                                 int mp, double *__restrict__ Spart)
+                                                                 int mp, double *__restrict__ Spart, const int *__restrict__ done)
 {
+    if (*done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t plane = (uint32_t)tp.tile_obs * 32u + 32u;                   // one chunk plane (+32 B: consecutive planes start 8 banks apart)
     const uint32_t zbytes = 12u * plane;
@@ -385,11 +323,13 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
 }
 
 // Assemble S, E from fragment-ordered Schur sums (see k_schur_mma) and the reduced U / ea:
-//   S_jk = delta_jk (U_j + mu_u I) - P_jk,  E_j = ea_j - Ered_j (or Ered_j itself when the tile kernel produced E directly); the lower block triangle (and the (hi,lo) sub-tile of the
+//   S_jk = delta_jk (U_j + mu_u I) - P_jk,  E_j = Ered_j (the tile lineariser produces E = sum A^T e' directly); the lower block triangle (and the (hi,lo) sub-tile of the
 //   diagonal blocks, which the MMA kernel skips) is mirrored.
 __global__ void k_assemble_mma(int m, int mcon, const double *__restrict__ Ured, const double *__restrict__ Sred,
-                               const double *__restrict__ Ered, double mu_u, double *__restrict__ S, double *__restrict__ E, bool e_direct)
+                               const double *__restrict__ Ered, const LmState *__restrict__ st, double *__restrict__ S, double *__restrict__ E)
 {
+    if (st->done) return;
+    const double mu_u = st->mu_u;
     const int mf = m - mcon, N = 16 * mf;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < (int64_t)N * N) {
@@ -409,7 +349,7 @@ __global__ void k_assemble_mma(int m, int mcon, const double *__restrict__ Ured,
     }
     if (t < N) {
         const int j = mcon + (int)(t >> 4), r = (int)(t & 15);
-        E[t] = e_direct ? Ered[j * 16 + r] : Ured[j * kU + 136 + r] - Ered[j * 16 + r];
+        E[t] = Ered[j * 16 + r];
     }
 }
 

@@ -26,6 +26,9 @@
  *   argus_pair_triangulate     <- Triangulator.triangulate      R/argus_gui/triangulate.py:27-212
  *   argus_ba_create ... argus_ba_normal_equations: the resident-data form of the three LM drivers (no counterpart in the
  *                                 reference, which re-allocates everything per call) and parity hooks for the tests
+ *   argus_ba_comm_init_nccl / argus_ba_set_comm_nccl / argus_nccl_unique_id: the multi-GPU exchange (one all-reduce of the
+ *                                 reduced camera system + one of four scalars per damping attempt) through NCCL, which the
+ *                                 library binds at run time; the reference is single-process and has no counterpart
  *
  * Ownership: the caller owns every array; outputs are written into caller-allocated memory.  No entry point
  * calls exit(); errors are negative return codes (ARGUS_E_*).  There is no CPU fallback: without a CUDA
@@ -92,11 +95,25 @@ int argus_ba_str_kdrts(int64_t n, int64_t ncon, int m, const char *vmask, double
                        const double *rot0, const double *x,
                        int itmax, int verbose, const double opts[5], double info[10], int flags);
 
+/* CUDA device the one-shot calls above run on (default 0) */
+int argus_set_default_device(int device);
+
 /* ---- resident-data interface (what the one-shot call is built from; used by bench.py and the multi-GPU host) ---- */
 int  argus_ba_create(argus_ba_ctx **ctx, int device, void *stream /* cudaStream_t or NULL */);
 void argus_ba_destroy(argus_ba_ctx *ctx);
-/* rank/world and the hook; world == 1 (default) needs no hook.  ncon/mcon passed to upload are LOCAL counts. */
+/* Multi-GPU (one context per GPU, points sharded, cameras replicated; ncon/mcon passed to upload are LOCAL counts).
+ * Preferred: NCCL inside the library.  argus_nccl_unique_id writes the 128-byte ncclUniqueId the ranks must share (rank 0
+ * creates it, the host distributes it by whatever means it has); argus_ba_comm_init_nccl creates this rank's communicator
+ * from it (collective over the ranks: ncclCommInitRank) on the context's device; argus_ba_set_comm_nccl adopts a
+ * communicator the caller owns (an ncclComm_t).  With NCCL a damping attempt is one CUDA graph including its two
+ * collectives.  Alternative: argus_ba_set_comm with a caller-supplied all-reduce hook (used by the CPU / single-GPU tests
+ * of the plumbing).  world == 1 (default) needs neither. */
+int  argus_nccl_unique_id(void *out128);
+int  argus_ba_comm_init_nccl(argus_ba_ctx *ctx, int rank, int world, const void *unique_id128);
+int  argus_ba_set_comm_nccl(argus_ba_ctx *ctx, int rank, int world, void *nccl_comm);
 int  argus_ba_set_comm(argus_ba_ctx *ctx, int rank, int world, argus_allreduce_fn fn, void *user);
+/* a damping attempt is replayed as a CUDA graph from the first solve after an upload (default on); 0 launches kernel by kernel */
+int  argus_ba_set_graph(argus_ba_ctx *ctx, int on);
 /* copy a problem (or this rank's shard of the points, with all cameras) to the device and build the indices */
 int  argus_ba_upload(argus_ba_ctx *ctx, int64_t n, int64_t ncon, int m, int mcon, const char *vmask,
                      const double *p, const double *rot0, const double *x, int nccalib, int ncdist);

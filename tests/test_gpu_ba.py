@@ -305,19 +305,6 @@ def test_config5_shape_per_camera_fixed_intrinsics_and_outliers():
     assert np.abs(cg[16:, 0] - c0[16:, 0]).min() > 0            # free cameras: refined
 
 
-@pytest.mark.parametrize("gen", ["1", "2"])
-def test_earlier_kernel_generations_still_agree(gen, golden_ba, monkeypatch):
-    """The generation-1 (straight) and generation-2 (MMA Schur + bridge) kernel sets stay selectable (ARGUS_BA_GEN) and give the
-    same trajectories: an A/B check of the current kernels against independently written ones."""
-    g = golden_ba
-    monkeypatch.setenv("ARGUS_BA_GEN", gen)
-    p, info, ret = ba.solve_motstr(g["G1_vmask"], g["G1_p0"], g["G1_rot0"], g["G1_x"], 2, 3, itmax=8)
-    rinfo = g["G1_info_it8"]
-    assert list(info[5:]) == list(rinfo[5:]) and abs(info[1] - rinfo[1]) <= 1e-10 * rinfo[1]
-    p2, info2, _ = ba.solve_motstr(g["G2_vmask"], g["G2_p0"], g["G2_rot0"], g["G2_x"], 0, 0, itmax=6, opts=g["G2_opts"], mcon=1)
-    assert list(info2[5:]) == list(g["G2_info_it6"][5:])
-
-
 def _subset(s, keep):
     """Scene restricted to the visibility entries where ``keep`` is non-zero: (vmask, x)."""
     vm = s["vmask"]

@@ -1,5 +1,4 @@
 import sys, os; sys.path.insert(0, '/root/repo')
-if len(sys.argv) > 1: os.environ["ARGUS_CHOL_COOP"] = sys.argv[1]
 import bench
 from argus_gui_b200 import ba, scenes
 for (m, n, v) in ((8, 100_000, 6), (16, 100_000, 10), (24, 100_000, 12), (32, 100_000, 12), (54, 100_000, 12), (64, 100_000, 12)):
@@ -9,5 +8,5 @@ for (m, n, v) in ((8, 100_000, 6), (16, 100_000, 10), (24, 100_000, 12), (32, 10
     B.solve(itmax=2, opts=bench.OPTS_FIXED_WORK); B.reset()
     ret, info = B.solve(itmax=4, opts=bench.OPTS_FIXED_WORK, profile=True)
     pr = B.profile()
-    print("coop=%s m=%d N=%d: chol %.3f ms, iteration %.3f ms" % (os.environ.get("ARGUS_CHOL_COOP", "default"), m, 16 * m, pr["chol_solve"][0] / pr["chol_solve"][1], sum(v_[0] for v_ in pr.values()) / 4))
+    print("m=%d N=%d: chol %.3f ms, iteration %.3f ms" % (m, 16 * m, pr["chol_solve"][0] / pr["chol_solve"][1], sum(v_[0] for v_ in pr.values()) / 4))
     B.close()
