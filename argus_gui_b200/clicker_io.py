@@ -81,7 +81,10 @@ def save_tracks(prefix, pts, camera_profile=None, dlt_coefficients=None, track_n
     res = {}
     m = len(camera_profile) if camera_profile is not None else None
     if m is not None and dlt_coefficients is not None:
-        res = reconstruct_tracks(pts, camera_profile, dlt_coefficients, bootstrap=bootstrap, bs_iter=bs_iter, seed=seed)
+        # the bootstrap's sub-frame search shifts its input in place (tools.bootstrapXYZs, as the reference's does); the Clicker
+        # builds the -xypts table BEFORE it bootstraps (argus-click:3280 vs :3311), so the file holds the digitised points
+        work = pts.copy() if bootstrap else pts
+        res = reconstruct_tracks(work, camera_profile, dlt_coefficients, bootstrap=bootstrap, bs_iter=bs_iter, seed=seed)
     k = pts.shape[1] // (2 * m) if m else None
     names = list(track_names) if track_names is not None else (['Track %d' % (t + 1) for t in range(k)] if k else None)
     if sparse:

@@ -912,6 +912,7 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
     if (graph && !c->graph_exec) capture_attempt_graph(c);
     int queued = 0, confirmed = 0;
     bool done = false;
+    std::vector<size_t> ev_mark;          // profiling: first event of each attempt (attempts queued behind the end are dropped)
     while (!done) {
         while (queued - confirmed > kDepth) {
             ARGUS_CUDA_CHECK(cudaEventSynchronize(c->snap_ev[confirmed % kSnap]));
@@ -922,7 +923,10 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
         if (graph && c->graph_exec) {
             ARGUS_CUDA_CHECK(cudaGraphLaunch(c->graph_exec, s));
             c->launches += c->graph_launches; c->n_allreduce += c->graph_allreduces;
-        } else if ((rc = enqueue_attempt(c))) return rc;
+        } else {
+            if (c->profiling) ev_mark.push_back(c->evs.size());
+            if ((rc = enqueue_attempt(c))) return rc;
+        }
         ARGUS_CUDA_CHECK(cudaMemcpyAsync(&c->h_snap[queued % kSnap], c->st.p, sizeof(LmState), cudaMemcpyDeviceToHost, s));
         ARGUS_CUDA_CHECK(cudaEventRecord(c->snap_ev[queued % kSnap], s));
         c->d2h_bytes += sizeof(LmState);
@@ -931,7 +935,14 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
     ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));
     const LmState fin = c->h_snap[(queued - 1) % kSnap];
     c->cur_cam = fin.cur_cam; c->cur_pts = fin.cur_pts;
-    if (c->profiling) prof_collect(c);
+    if (c->profiling) {
+        // `confirmed` is the attempt that ended the loop; the ones queued behind it did nothing
+        if ((size_t)confirmed + 1 < ev_mark.size()) {
+            for (size_t q = ev_mark[confirmed + 1]; q < c->evs.size(); ++q) { c->ev_pool.push_back(c->evs[q].a); c->ev_pool.push_back(c->evs[q].b); }
+            c->evs.resize(ev_mark[confirmed + 1]);
+        }
+        prof_collect(c);
+    }
 
     const double nvis = gc[0];
     const char *tag = (mode == kModeMot) ? "mot" : (mode == kModeStr) ? "str" : "motstr";

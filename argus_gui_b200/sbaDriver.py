@@ -11,9 +11,9 @@ unpaired tracks] (``getPointsAndExtArray``, :165-257), the initial structure / e
 
 The Qt / OpenGL viewer (``OutlierWindow`` is a QWidget in the reference) is out of scope; its numerical part
 (``buildData`` :676-789, ``getCoefficients`` :1027-1165, ``pairedIsomorphism`` :988-1009, ``WandOutputter``
-output.py:29-66) is provided by ``WandResults`` without any GUI toolkit.  Alignment to user reference points
-(``transform`` :828-985: axis / gravity / plane modes) is not reproduced: with reference points the cloud is scaled and
-translated to the first reference point only, and a warning is printed.
+output.py:29-66) is provided by ``WandResults`` without any GUI toolkit, including the alignment of the scaled cloud to
+user reference points (``transform`` :828-985: 1- to 4-point axis references, gravity, horizontal plane) and the sign change of
+the z-related DLT coefficients the reference applies for axis references (:767-773).
 """
 from __future__ import print_function
 
@@ -27,10 +27,100 @@ import pandas
 
 from . import sba
 from . import dlt as _dlt
-from .tools import undistort_pts
+from .tools import undistort_pts, redistort_pts
 from .triangulate import multiTriangulator
 
-__all__ = ["sbaArgusDriver", "WandResults"]
+__all__ = ["sbaArgusDriver", "WandResults", "align_to_reference"]
+
+
+def _rotation_between(a, b):
+    """Rotation that turns direction ``a`` into direction ``b`` (Rodrigues' formula in its cross-product-matrix form; the
+    reference's ``rotation`` helper, sbaDriver.py:1232-1248)."""
+    a = a / np.linalg.norm(a)
+    b = b / np.linalg.norm(b)
+    v = np.cross(a, b)
+    K = np.array([[0.0, -v[2], v[1]], [v[2], 0.0, -v[0]], [-v[1], v[0], 0.0]])
+    return np.eye(3) + K + (K @ K) * ((1.0 - np.dot(a, b)) / np.dot(v, v))
+
+
+def _kabsch(A, B):
+    """Least-squares rotation taking the centred point set A onto B (the reference's ``rigid_transform_3D``,
+    sbaDriver.py:1271-1299, which flips the last right singular vector when the solution is a reflection)."""
+    Ac = A - A.mean(axis=0)
+    Bc = B - B.mean(axis=0)
+    U, _, Vt = np.linalg.svd(Ac.T @ Bc)
+    R = Vt.T @ U.T
+    if np.linalg.det(R) < 0:
+        print('Reflection detected - correcting to ensure proper right-handed coordinate system')
+        Vt[2, :] *= -1
+        R = Vt.T @ U.T
+    return R
+
+
+def align_to_reference(xyzs, nref, reference_type='Axis points', recording_frequency=100):
+    """The reference's ``OutlierWindow.transform`` (sbaDriver.py:828-985): move / rotate the scaled cloud ``xyzs`` (whose first
+    ``nref`` rows are the reference points) into the user's frame.
+
+    * 'Axis points': 1 point = origin; 2 = origin, +z; 3 = origin, +x, +y (z = -(x cross y), as the reference has it);
+      4 = origin, +x, +y, +z.  Any other count only moves the origin.
+    * 'Gravity': the reference rows are a free-fall track; a quadratic per coordinate gives the acceleration, which is turned
+      onto -z.
+    * 'Plane': the reference rows lie in a horizontal plane; principal axes from an SVD, +z towards the bulk of the data, origin
+      at the centre of the reference points.
+    """
+    xyzs = np.asarray(xyzs, dtype=np.float64)
+    ref = xyzs[:nref]
+    origin = ref[0].copy()
+    out = xyzs - origin
+    ref = ref - origin
+    k = ref.shape[0]
+    if reference_type == 'Axis points' and k == 1:
+        print('Using 1-point (origin) reference axes')
+    elif reference_type == 'Axis points' and k == 2:
+        print('Using 2-point (origin,+Z) reference axes')
+        out = out @ _rotation_between(ref[1], np.array([0.0, 0.0, 1.0])).T
+    elif reference_type == 'Axis points' and k in (3, 4):
+        if k == 3:
+            print('Using 3-point (origin,+x,+y) reference axes')
+            z = -np.cross(ref[1], ref[2])
+            A = np.vstack((ref, z / np.linalg.norm(z)))
+            lz = 1.0
+        else:
+            print('Using 4-point (origin,+x,+y,+z) reference axes')
+            A = ref
+            lz = np.linalg.norm(A[3])
+        B = np.diag([np.linalg.norm(A[1]), np.linalg.norm(A[2]), lz])
+        out = out @ _kabsch(A, np.vstack((np.zeros(3), B))).T
+    elif reference_type == 'Gravity':
+        print('Using gravity alignment, +Z will point anti-parallel to gravity')
+        f = float(recording_frequency)
+        t = np.arange(k)
+        ok = np.isfinite(ref[:, 0])
+        acc = np.array([np.mean(np.diff(np.polyval(np.polyfit(t[ok], ref[ok, a], 2), t), n=2)) for a in range(3)]) * f * f
+        g = acc / np.linalg.norm(acc)
+        down = np.array([0.0, 0.0, -1.0])
+        axis = np.cross(g, down)
+        axis = axis / np.linalg.norm(axis)
+        ang = np.arccos(np.dot(g, down))
+        K = np.array([[0.0, -axis[2], axis[1]], [axis[2], 0.0, -axis[0]], [-axis[1], axis[0], 0.0]])
+        R = np.eye(3) + np.sin(ang) * K + (1.0 - np.cos(ang)) * (K @ K)
+        out = out @ R.T
+        print('Gravity measured with {:.2f}% accuracy!'.format(np.linalg.norm(acc) / 9.81 * 100))
+    elif reference_type == 'Plane':
+        print('Aligning to horizontal plane reference points')
+        avg = ref.mean(axis=0)
+        basis = np.linalg.svd(ref - avg, full_matrices=True)[2].T
+        if np.linalg.det(basis) == -1:
+            basis = -basis
+        # the reference centres the UNSHIFTED cloud on the mean of the shifted reference points here (sbaDriver.py:953); the
+        # final re-centring on the reference points makes the difference a pure translation that cancels
+        centred = xyzs - avg
+        out = centred @ basis
+        if out[:, 2].mean() < 0:
+            basis = basis @ np.diag([1.0, -1.0, -1.0])
+            out = centred @ basis
+        out = out - out[:k].mean(axis=0)
+    return out
 
 
 class sbaArgusDriver(object):
@@ -187,7 +277,8 @@ class sbaArgusDriver(object):
         uvs = [undistort_pts(np.ascontiguousarray(self.pts[:, 3 + 2 * k:3 + 2 * (k + 1)]), self.cams[k]) for k in range(self.ncams)]
         nRef = self.ref.shape[0] if self.ref is not None else 0
         self.grapher = WandResults(newpoints.B, newcameras.arr, self.nppts, self.nuppts, self.scale, self.ref is not None, self.indices,
-                                   self.ncams, npframes, nupframes, self.name, uvs, nRef, self.order, self.cams)
+                                   self.ncams, npframes, nupframes, self.name, uvs, nRef, self.order, self.cams,
+                                   self.reference_type, self.recording_frequency)
         self.outliers = self.grapher.outliers
         if self.outputCameraProfiles:
             nps = np.loadtxt(self.name + '-sba-profile.txt', ndmin=2)
@@ -233,11 +324,16 @@ class WandResults(object):
     """Numerical part of the reference's OutlierWindow (no GUI): wand scale and score, centring, per-camera 11-parameter
     DLT fit with reprojection RMSE and 3-sigma outliers, output files."""
 
-    def __init__(self, xyzs, cam, nppts, nuppts, scale, refBool, indices, ncams, npframes, nupframes, name, uvs, nRef, order, cams):
+    def __init__(self, xyzs, cam, nppts, nuppts, scale, refBool, indices, ncams, npframes, nupframes, name, uvs, nRef, order, cams,
+                 reference_type='Axis points', recording_frequency=100):
         self.nppts, self.nuppts, self.scale, self.refBool = nppts, nuppts, scale, refBool
         self.indices, self.ncams, self.npframes, self.nupframes = indices, ncams, npframes, nupframes
-        self.name, self.uvs, self.nRef, self.order, self.cams = name, uvs, nRef, order, cams
+        self.name, self.uvs, self.nRef, self.order = name, uvs, nRef, order
+        self.reference_type, self.recording_frequency = reference_type, recording_frequency
+        # 8-value pinhole profiles [f, cx, cy, k1, k2, p1, p2, k3] for the outlier report (sbaDriver.py:511-513)
+        self.cams = [[c[u] for u in (0, 1, 2, 5, 6, 7, 8, 9)] for c in cams]
         self.cam = cam
+        self.ref = None
         self.outliers, self.index = self.buildData(np.array(xyzs, dtype=np.float64, copy=True))
 
     def isVisible(self):
@@ -267,8 +363,9 @@ class WandResults(object):
             factor = self.scale / dist
         xyzs = xyzs * factor
         if self.refBool:
-            print('Using reference points (B200 backend: scale + translation to the first reference point only)')
-            xyzs = xyzs - xyzs[0]
+            print('Using reference points')
+            xyzs = align_to_reference(xyzs, self.nRef, self.reference_type, self.recording_frequency)
+            self.ref = xyzs[:self.nRef, :]
         else:
             print('No reference points available - centering the calibration on the mean point location.')
             xyzs = xyzs - np.mean(xyzs, axis=0)
@@ -285,6 +382,8 @@ class WandResults(object):
             dlts.append(cos); errs.append(error)
         self.dlts = np.asarray(dlts)
         self.dlterrors = np.asarray(errs)
+        if self.refBool and self.reference_type == 'Axis points':
+            self.dlts[:, [2, 6, 10]] *= -1.0          # the z-related coefficients change sign with axis references (sbaDriver.py:767-773)
         self.outputDLT(self.dlts, self.dlterrors)
         if self.nppts != 0:
             self.wandscore = 100. * (std / dist)
@@ -320,7 +419,8 @@ class WandResults(object):
             i = int(idx[k])
             if i >= self.nRef and i not in ptsi:
                 ptsi.append(i)
-            base = {'uv': uv[i], 'error': float(errors[k]), 'camera': camera_number}
+            base = {'uv': redistort_pts(np.array([uv[i]], dtype=np.float64), self.cams[cam_index])[0], 'error': float(errors[k]),
+                    'camera': camera_number}
             if self.nRef - 1 < i < pb_1 + self.nRef:
                 outliers.append(dict(base, frame=self.indices['paired'][0][i - self.nRef] + 1, kind='paired', paired_point=1, unpaired_track=None))
             elif pb_1 + self.nRef <= i < self.nppts + self.nRef:

@@ -4,6 +4,7 @@ the per-frame Python loops of the reference are replaced by the batched CUDA ker
     uv_to_xyz(pts, profs, dlt)            tools.py:296-337   -> argus_dlt_triangulate
     get_repo_errors(xyzs, pts, prof, dlt) tools.py:360-423   -> argus_dlt_reproj_error
     undistort_pts(pts, prof)              tools.py:129-148   -> argus_undistort_points   (pinhole profiles)
+    redistort_pts(pts, prof)              tools.py:160-183   (host numpy: only used for the handful of reported outliers)
     solve_dlt(xyz, uv)                    tools.py:220-280   -> argus_dlt_fit
     reconstruct_uv(L, xyz), dlt_inverse(L, xyz), normalize(pts, prof)   (host numpy, not hot)
 
@@ -13,7 +14,7 @@ import numpy as np
 
 from . import dlt as _dlt
 
-__all__ = ["ArgusError", "dlt_inverse", "reconstruct_uv", "undistort_pts", "normalize", "solve_dlt", "uv_to_xyz",
+__all__ = ["ArgusError", "dlt_inverse", "reconstruct_uv", "undistort_pts", "redistort_pts", "normalize", "solve_dlt", "uv_to_xyz",
            "get_repo_errors", "uv_to_xyz_and_errors", "bootstrapXYZs"]
 
 
@@ -77,6 +78,25 @@ def normalize(pts, prof):
     return pts
 
 
+def redistort_pts(pts, prof):
+    """Nx2 undistorted pixel coordinates -> Nx2 distorted pixel coordinates: the forward camera model applied to the normalised
+    coordinates (the reference projects (x, y, 1) with cv2.projectPoints, identity pose; tools.py:160-183).  ``pts`` is
+    normalised in place, as the reference does."""
+    if not _is_pinhole(prof):
+        raise ArgusError("only pinhole distortion profiles are supported by the B200 backend")
+    prof = np.asarray(prof, dtype=np.float64)
+    if len(prof) != 8:
+        raise ArgusError('pinhole distortion profile must contain exactly 8 coefficients')
+    q = normalize(pts, prof)
+    x, y = q[:, 0], q[:, 1]
+    k1, k2, p1, p2, k3 = prof[3:8]
+    r2 = x * x + y * y
+    rad = 1.0 + r2 * (k1 + r2 * (k2 + r2 * k3))
+    xd = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x)
+    yd = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y
+    return np.stack([prof[0] * xd + prof[1], prof[0] * yd + prof[2]], axis=1)
+
+
 def solve_dlt(xyz, uv):
     """11-parameter DLT fit (tools.py:220-280) on the GPU (argus_dlt_fit): returns (L (11 x 1), mean reprojection distance)."""
     if type(xyz) != np.ndarray or type(uv) != np.ndarray:
@@ -127,62 +147,78 @@ def uv_to_xyz_and_errors(pts, profs, dlt):
     return _dlt.reconstruct(pts, profs, np.asarray(dlt, dtype=np.float64))
 
 
+_SUBFRAME_STEPS = np.linspace(-1, 1, 21)
+
+
+def _subframe_offsets(pts, prof, dlt, numcams, numpts):
+    """Sub-frame synchronisation search of bootstrapXYZs (tools.py:455-510): for every camera but the first, the track of
+    that camera is re-sampled at 21 time offsets in [-1, 1] frames (linear interpolation), re-triangulated together with the
+    first camera and one other camera, and the offset with the smallest median (over tracks) of the median reprojection
+    error wins; a non-zero winner is written back into ``pts`` (in place).  All 21 x tracks candidate point sets of a camera
+    go through ONE fused GPU triangulation + reprojection call.  Returns True when ``pts`` changed.
+
+    Two details of the reference are kept because its outputs depend on them: a track whose finite rows are exactly [0] is
+    skipped (``np.any(fin)``), and the write-back of every track uses the finite rows of the LAST track (tools.py:497-498)."""
+    from scipy import interpolate
+    nstep = len(_SUBFRAME_STEPS)
+    col = lambda k, cam: slice(2 * (numcams * k + cam), 2 * (numcams * k + cam) + 2)
+    # values of a track (given on the frames `rows`) at rows + shift; `shift` may be a column of offsets -> (offsets, rows, 2)
+    resample = lambda rows, vals, shift: interpolate.interp1d(rows, vals, axis=0, kind='linear', fill_value='extrapolate')(rows + shift)
+    changed = False
+    for c in range(1, numcams):
+        partner = 1 if c > 1 else 2
+        trio_prof = np.vstack([prof[0], prof[partner], prof[c]])
+        trio_dlt = np.vstack([dlt[0], dlt[partner], dlt[c]])
+        blocks, sizes, rows_last = [], np.zeros((nstep, numpts), dtype=np.int64), None
+        for k in range(numpts):
+            track_c = pts[:, col(k, c)]
+            rows_last = np.where(np.isfinite(track_c[:, 0]))[0]
+            if not np.any(rows_last):
+                continue
+            cand = np.repeat(np.hstack([pts[:, col(k, 0)], pts[:, col(k, partner)], track_c])[None], nstep, axis=0)   # steps x frames x 6
+            cand[:, rows_last, 4:6] = resample(rows_last, track_c[rows_last], _SUBFRAME_STEPS[:, None])
+            usable = np.isfinite(cand).sum(axis=2) > 4
+            sizes[:, k] = usable.sum(axis=1)
+            blocks.append((k, cand, usable))
+        med = np.full((nstep, numpts), np.nan)
+        if blocks:
+            stacked = np.ascontiguousarray(np.vstack([cand[i][usable[i]] for (_, cand, usable) in blocks for i in range(nstep)]))
+            err = _dlt.reconstruct(stacked, trio_prof, trio_dlt)[1].ravel() if stacked.shape[0] else np.zeros(0)
+            at = 0
+            import warnings
+            with warnings.catch_warnings(), np.errstate(all='ignore'):
+                warnings.simplefilter('ignore', category=RuntimeWarning)
+                for (k, _, _) in blocks:
+                    for i in range(nstep):
+                        med[i, k] = np.nanmedian(err[at:at + sizes[i, k]])
+                        at += sizes[i, k]
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', category=RuntimeWarning)
+            best = _SUBFRAME_STEPS[np.nanargmin(np.nanmedian(med, axis=1))]
+        if best != 0:
+            changed = True
+            print('partial offset of {} frames found for cam {}, remaking pts'.format(best, c + 1))
+            for k in range(numpts):
+                track_c = pts[:, col(k, c)]
+                track_c[rows_last] = resample(rows_last, track_c[rows_last], best)
+                pts[:, col(k, c)] = track_c
+    return changed
+
+
 def bootstrapXYZs(pts, rmses, prof, dlt, bsIter=250, display_progress=False, subframeinterp=True, seed=None, noise=None):
     """95 % confidence intervals of the triangulated points by bootstrapping (tools.py:448-544): same arguments and return
     values (CIs N x 3k, spline weights, tolerances) as the reference.  The ``bsIter`` perturbed re-triangulations per track run
     as ONE kernel (argus_dlt_bootstrap: on-device Philox noise, Welford standard deviation); the optional sub-frame offset
-    search (21 candidate offsets per camera, tools.py:455-510) keeps the reference's host logic with the GPU
-    triangulation / reprojection calls inside.  ``seed`` / ``noise`` (extension): reproducible device noise, or explicit
+    search (21 candidate offsets per camera, tools.py:455-510) is one fused GPU call per camera (``_subframe_offsets``);
+    like the reference it shifts ``pts`` in place when it finds an offset.  ``seed`` / ``noise`` (extension): reproducible device noise, or explicit
     standard-normal numbers of shape (tracks, bsIter, frames, 2 * cameras) in the reference's draw order."""
     from scipy import interpolate
     numcams = len(prof)
     numpts = int(pts.shape[1] / (2 * numcams))
     dlt = np.asarray(dlt, dtype=np.float64)
-    if subframeinterp and numcams > 2:
-        print('Checking subframe interpolation')
-        redormse = False
-        step = list(np.linspace(-1, 1, 21))
-        for c in range(1, numcams):
-            steprmses = np.zeros((21, numpts)) * np.nan
-            ocam = 1 if c > 1 else 2
-            for k in range(numpts):
-                base = k * 2 * numcams
-                c1pts = pts[:, base:base + 2]
-                cpts_clean = pts[:, base + c * 2:base + c * 2 + 2]
-                ocpts = pts[:, base + ocam * 2:base + ocam * 2 + 2]
-                fin = np.where(np.isfinite(cpts_clean[:, 0]))[0]
-                if not np.any(fin):
-                    continue
-                sprof = np.vstack([prof[0], prof[ocam], prof[c]])
-                sdlt = np.vstack([dlt[0], dlt[ocam], dlt[c]])
-                f = interpolate.interp1d(fin, cpts_clean[fin], axis=0, kind='linear', fill_value='extrapolate')
-                for i, s in enumerate(step):
-                    cpts = cpts_clean.copy()
-                    cpts[fin] = f(fin + s)
-                    spts = np.hstack([c1pts, ocpts, cpts])
-                    spts = np.ascontiguousarray(spts[np.where(np.sum(np.isfinite(spts), axis=1) > 4)[0]])
-                    sxyzs, srms = _dlt.reconstruct(spts, sprof, sdlt)
-                    with np.errstate(all='ignore'):
-                        import warnings
-                        with warnings.catch_warnings():
-                            warnings.simplefilter('ignore', category=RuntimeWarning)
-                            steprmses[i, k] = np.nanmedian(srms)
-            import warnings
-            with warnings.catch_warnings():
-                warnings.simplefilter('ignore', category=RuntimeWarning)
-                poff = step[np.nanargmin(np.nanmedian(steprmses, axis=1))]
-            if poff != 0:
-                redormse = True
-                print('partial offset of {} frames found for cam {}, remaking pts'.format(poff, c + 1))
-                for k in range(numpts):
-                    sl = slice(k * 2 * numcams + c * 2, k * 2 * numcams + c * 2 + 2)
-                    cpts = pts[:, sl]
-                    # NOTE: the reference indexes with the `fin` of the LAST track's clean points here (tools.py:497-498); kept
-                    cpts[fin] = interpolate.interp1d(fin, cpts[fin], axis=0, kind='linear', fill_value='extrapolate')(fin + poff)
-                    pts[:, sl] = cpts
-        if redormse:
-            xyzs, err = _dlt.reconstruct(np.ascontiguousarray(pts), prof, dlt)
-            rmses = err.T
+    if subframeinterp and numcams > 2 and _subframe_offsets(pts, prof, dlt, numcams, numpts):
+        rmses = _dlt.reconstruct(np.ascontiguousarray(pts), prof, dlt)[1].T
     if seed is None and noise is None:
         seed = int(np.random.randint(0, 2 ** 31 - 1))
     ret = _dlt.bootstrap_sd(np.ascontiguousarray(pts), np.asarray(rmses, dtype=np.float64)[:, :numpts], prof, dlt, bs_iter=bsIter, noise=noise, seed=seed or 0)

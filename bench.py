@@ -378,7 +378,7 @@ def main():
     with torch.cuda.stream(stream):
         B = ba.BundleAdjuster(device=local, stream=stream.cuda_stream)
         if world > 1:
-            B.set_comm(rank, world, ba.torch_allreduce_hook())
+            B.init_nccl(rank, world)
         B.upload(s["vmask"], p0, rot0, s["x"], nk, nd)
         if args.workload == "c5":
             B.set_camera_fix([5] * 16 + [0] * 16, [5] * 16 + [0] * 16)
@@ -430,7 +430,7 @@ def main():
             else:
                 with torch.cuda.stream(stream):
                     Be = ba.BundleAdjuster(device=local, stream=stream.cuda_stream)
-                    Be.set_comm(rank, world, ba.torch_allreduce_hook())
+                    Be.init_nccl(rank, world)
                     Be.upload(hv, hp, rot0, hx, nk, nd)
                     re_, ie = Be.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
                     pe = Be.download(); Be.close()

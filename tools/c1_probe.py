@@ -12,6 +12,14 @@ B = ba.BundleAdjuster().upload(s["vmask"], p0, rot0, s["x"], 5, 4)
 B.solve(itmax=150); B.reset()
 t = time.perf_counter(); ret, info = B.solve(itmax=150); dt = time.perf_counter() - t
 print("gpu resident: %d iterations, %.2f ms, %.3f ms/iteration" % (ret, 1e3 * dt, 1e3 * dt / max(ret, 1)))
+import time as _t
+st = {}
+for rep in range(3):
+    t0 = _t.perf_counter(); B2 = ba.BundleAdjuster(); B2.set_graph(False); t1 = _t.perf_counter()
+    B2.upload(s["vmask"], p0, rot0, s["x"], 5, 4); t2 = _t.perf_counter()
+    B2.solve(itmax=150); t3 = _t.perf_counter(); B2.download(); t4 = _t.perf_counter(); B2.close(); t5 = _t.perf_counter()
+    st = {"create": t1 - t0, "upload": t2 - t1, "solve": t3 - t2, "download": t4 - t3, "destroy": t5 - t4}
+print("stages of a one-shot call (ms):", {k: round(1e3 * v, 3) for k, v in st.items()})
 try:
     from oracle import sba_ref
     if sba_ref.available():
