@@ -26,6 +26,7 @@ _lib = None
 # name -> (restype, argtypes); also the list of symbols include/argus_b200.h declares (tests check every one)
 SIGNATURES = {
     "argus_b200_version": (ctypes.c_char_p, []),
+    "argus_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_double, c_double_p, c_double_p]),
     "argus_ba_motstr_kdrts": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libargus_b200.so")
-SOURCES = ["ba_solver.cu", "dlt_kernels.cu", "pair_kernels.cu", "fit_kernels.cu"]
+SOURCES = ["ba_solver.cu", "dlt_kernels.cu", "pair_kernels.cu", "fit_kernels.cu", "microbench.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
 

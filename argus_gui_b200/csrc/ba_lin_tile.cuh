@@ -26,10 +26,12 @@ struct LinTilePlan {
     const uint8_t *obs_lpt;      // nobs: local point index of each observation inside its tile
     const uint8_t *corder;       // nobs: per tile, local observation indices sorted by camera
     const uint16_t *cstart;      // ntiles x (m+1): start of each camera's run in corder (local)
+    const uint8_t *row_obs;      // Z rows: local observation index held by each row of a tile's Z block, 0xFF = unused row
 };
 
 struct LinTileOut {
-    double *Z;                   // nobs x 48 (permuted, see zperm)
+    double *Z;                   // Z rows x 48 (permuted, see zperm; chunk-major tile blocks, z_index)
+    uint8_t *zs;                 // ntiles x 256: sign bits of D of the point behind every Z row (what the Schur kernel reads)
     uint8_t *zsign;              // n
     double *Vinv;                // n x 6
     double *V;                   // n x 6 (undamped, for the parity hook)
@@ -124,13 +126,14 @@ __global__ void __launch_bounds__(256) k_index_fill(int64_t n, const uint64_t *_
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) obs_ptr[n] = k;     // last thread of the last block ends at the grand total
 }
 
-// per tile: local point index of every observation, camera-sorted (stable) observation order, the camera run starts, and the
-// rank table of the Schur kernel: pt_rank[tile][cam][local point] = position of cam in that point's observation list (the table
-// is pre-filled with 0xFF: camera not seen, or point fixed; camera-major so that a warp reads 32 consecutive bytes)
+// per tile: local point index of every observation, camera-sorted (stable) observation order, the camera run starts, and which
+// observation every row of the tile's Z block holds: the observation of rank r of a point sits in row pt_slot0[point] + 4 r
+// (ba_schur_mma.cuh: four classes of points, rows 4 i + class); row_obs is pre-filled with 0xFF (unused row)
 __global__ void __launch_bounds__(256) k_build_tile_index(int m, const int32_t *__restrict__ tile_pt, const int32_t *__restrict__ tile_o,
-                                                          const int32_t *__restrict__ obs_ptr, const uint8_t *__restrict__ obs_cam,
-                                                          uint8_t *__restrict__ obs_lpt, uint8_t *__restrict__ corder, uint16_t *__restrict__ cstart,
-                                                          int64_t ncon, int mp, uint8_t *__restrict__ pt_rank /* may be nullptr */)
+                                                          const int32_t *__restrict__ tile_r, const int32_t *__restrict__ obs_ptr,
+                                                          const uint8_t *__restrict__ obs_cam, const uint8_t *__restrict__ pt_slot0,
+                                                          uint8_t *__restrict__ obs_lpt, uint8_t *__restrict__ corder,
+                                                          uint16_t *__restrict__ cstart, uint8_t *__restrict__ row_obs)
 {
     __shared__ int s_pofs[kTilePts + 1];
     __shared__ uint8_t s_cam[256];
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(256) k_build_tile_index(int m, const int32_t *
         int lp = 0;
         while (lp + 1 < npts && tid >= s_pofs[lp + 1]) ++lp;
         obs_lpt[o0 + tid] = (uint8_t)lp;
-        if (pt_rank && (int64_t)p0 + lp >= ncon) pt_rank[((size_t)tile * mp + s_cam[tid]) * kTilePts + lp] = (uint8_t)(tid - s_pofs[lp]);
+        row_obs[(size_t)tile_r[tile] + pt_slot0[p0 + lp] + 4 * (tid - s_pofs[lp])] = (uint8_t)tid;
         atomicAdd(&s_cnt[s_cam[tid] + 1], 1);               // integer histogram: order-independent
     }
     __syncthreads();
@@ -181,8 +184,8 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);
     double *Ga = reinterpret_cast<double *>(smem_raw + (((size_t)pb.m * sizeof(CamConst) + 15) & ~(size_t)15));   // TO x 36 (16-byte aligned)
-    double *Bs = Ga + (size_t)tp.tile_obs * kGa;                    // TO x kBs
-    double *Ps = Bs + (size_t)tp.tile_obs * kBs;                    // 32 x 16
+    double *Bs = Ga + (size_t)kTileRows * kGa;                      // 256 x kBs
+    double *Ps = Bs + (size_t)kTileRows * kBs;                      // 32 x 16
     __shared__ double red[32];
     __shared__ double s_M[kTilePts * 3];          // the tile's points
     __shared__ int s_pofs[kTilePts + 1];          // local observation offset of each point
@@ -203,27 +206,38 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
 
     // tile bounds are loaded one tile ahead (they end up in uniform registers), and the next tile's index data / measurements /
     // points are pulled into L2 while this tile computes: the dependent loads at the top of a tile then see L2, not DRAM, latency
-    int nx_p0 = 0, nx_p1 = 0, nx_o0 = 0, nx_o1 = 0;
-    if ((int)blockIdx.x < tp.ntiles) { nx_p0 = tp.tile_pt[blockIdx.x]; nx_p1 = tp.tile_pt[blockIdx.x + 1]; nx_o0 = tp.tile_o[blockIdx.x]; nx_o1 = tp.tile_o[blockIdx.x + 1]; }
+    int nx_p0 = 0, nx_p1 = 0, nx_o0 = 0, nx_o1 = 0, nx_r0 = 0, nx_r1 = 0;
+    if ((int)blockIdx.x < tp.ntiles) {
+        nx_p0 = tp.tile_pt[blockIdx.x]; nx_p1 = tp.tile_pt[blockIdx.x + 1]; nx_o0 = tp.tile_o[blockIdx.x]; nx_o1 = tp.tile_o[blockIdx.x + 1];
+        nx_r0 = tp.tile_r[blockIdx.x]; nx_r1 = tp.tile_r[blockIdx.x + 1];
+    }
     for (int tile = blockIdx.x; tile < tp.ntiles; tile += gridDim.x) {
         const int p0 = nx_p0, npts = nx_p1 - nx_p0;
         const int o0 = nx_o0, nobs_t = nx_o1 - nx_o0;
+        const int r0 = nx_r0, nrows_t = nx_r1 - nx_r0;
         const int ntile = tile + gridDim.x;
-        if (ntile < tp.ntiles) { nx_p0 = tp.tile_pt[ntile]; nx_p1 = tp.tile_pt[ntile + 1]; nx_o0 = tp.tile_o[ntile]; nx_o1 = tp.tile_o[ntile + 1]; }
-        // the tile's index data and points -> shared memory (the previous tile ended with a barrier)
-        double2 z = make_double2(0.0, 0.0); int my_cam = 0, my_lp = 0;
-        if (tid < nobs_t) {
-            const int k = o0 + tid;
-            z = pb.obs_uv[k]; my_cam = pb.obs_cam[k]; my_lp = lp.obs_lpt[k];
-            s_cord[tid] = lp.corder[k];
+        if (ntile < tp.ntiles) {
+            nx_p0 = tp.tile_pt[ntile]; nx_p1 = tp.tile_pt[ntile + 1]; nx_o0 = tp.tile_o[ntile]; nx_o1 = tp.tile_o[ntile + 1];
+            nx_r0 = tp.tile_r[ntile]; nx_r1 = tp.tile_r[ntile + 1];
         }
+        // the tile's index data and points -> shared memory (the previous tile ended with a barrier).  In the per-observation
+        // phases P1 and P3 a thread is a ROW of the tile's Z block (so that the Z stores of a warp are consecutive 32-byte
+        // chunks); li is the observation that row holds - the index everything in shared memory is keyed by
+        double2 z = make_double2(0.0, 0.0); int my_cam = 0, my_lp = 0, li = 0xFF;
+        if (tid < nrows_t) li = lp.row_obs[(size_t)r0 + tid];
+        const bool act = li != 0xFF;
+        if (act) {
+            const int k = o0 + li;
+            z = pb.obs_uv[k]; my_cam = pb.obs_cam[k]; my_lp = lp.obs_lpt[k];
+        }
+        if (tid < nobs_t) s_cord[tid] = lp.corder[o0 + tid];
         if (tid <= npts) s_pofs[tid] = pb.obs_ptr[p0 + tid] - o0;
         if (tid < npts) { const int64_t i = p0 + tid; s_M[3 * tid] = pts[3 * i]; s_M[3 * tid + 1] = pts[3 * i + 1]; s_M[3 * tid + 2] = pts[3 * i + 2]; }
         if (tid <= pb.m) s_cst[tid] = lp.cstart[(size_t)tile * (pb.m + 1) + tid];
         __syncthreads();
 
         // ---- P1: one thread per observation ----
-        if (tid < nobs_t) {
+        if (act) {
             const int64_t i = p0 + my_lp;
             const double M0 = s_M[3 * my_lp], M1 = s_M[3 * my_lp + 1], M2 = s_M[3 * my_lp + 2];
             double u, v, A[32], B[6];
@@ -231,7 +245,7 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             cam_project_jac(sc[my_cam], M0, M1, M2, nfk, nfd, u, v, A, B);
             const double e0 = z.x - u, e1 = z.y - v;
             cost += e0 * e0 + e1 * e1;
-            double *g = Ga + (size_t)tid * kGa;
+            double *g = Ga + (size_t)li * kGa;
             if (my_cam >= pb.mcon) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
@@ -246,7 +260,7 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             }
             *reinterpret_cast<double2 *>(g + 32) = make_double2(e0, 0.0);      // [comp][{e, e'}]
             *reinterpret_cast<double2 *>(g + 34) = make_double2(e1, 0.0);
-            double *b = Bs + (size_t)tid * kBs;
+            double *b = Bs + (size_t)li * kBs;
             if (i >= pb.ncon) {
                 *reinterpret_cast<double2 *>(b) = make_double2(B[0], B[1]); *reinterpret_cast<double2 *>(b + 2) = make_double2(B[2], B[3]);
                 *reinterpret_cast<double2 *>(b + 4) = make_double2(B[4], B[5]);
@@ -261,6 +275,7 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             if ((tid & 7) == 0 && tid < no) prefetch_l2(pb.obs_uv + nx_o0 + tid);
             if (tid < 3 && tid * 128 < no + 127) {
                 prefetch_l2(pb.obs_cam + nx_o0 + tid * 128); prefetch_l2(lp.obs_lpt + nx_o0 + tid * 128); prefetch_l2(lp.corder + nx_o0 + tid * 128);
+                prefetch_l2(lp.row_obs + nx_r0 + tid * 128);
             }
             if (tid >= 32 && tid < 40 && (tid - 32) * 16 < 3 * np + 15) prefetch_l2(pts + 3 * (int64_t)nx_p0 + (tid - 32) * 16);
             if (tid == 64) { prefetch_l2(pb.obs_ptr + nx_p0); prefetch_l2(pb.obs_ptr + nx_p0 + 31); prefetch_l2(lp.cstart + (size_t)ntile * (pb.m + 1)); }
@@ -327,7 +342,9 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                             P[0] = li[0]; P[1] = li[1]; P[2] = li[2];
                             P[3] = rs[0]; P[4] = rs[1]; P[5] = rs[2];
                             P[6] = n00 * b0 + n01 * b1 + n02 * b2; P[7] = n01 * b0 + n11 * b1 + n12 * b2; P[8] = n02 * b0 + n12 * b1 + n22 * b2;
-                            out.zsign[i] = (uint8_t)((di[0] < 0.0 ? 1 : 0) | (di[1] < 0.0 ? 2 : 0) | (di[2] < 0.0 ? 4 : 0));
+                            const int sgn = (di[0] < 0.0 ? 1 : 0) | (di[1] < 0.0 ? 2 : 0) | (di[2] < 0.0 ? 4 : 0);
+                            out.zsign[i] = (uint8_t)sgn;
+                            P[9] = (double)sgn;
                         }
                     }
                 } else if (mode != 0) {
@@ -338,18 +355,19 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
         __syncthreads();
 
         // ---- P3: per observation: e' and Z ----
-        if (mode != 0 && tid < nobs_t) {
+        if (mode != 0) out.zs[(size_t)tile * 256 + tid] = act ? (uint8_t)(int)Ps[my_lp * kPs + 9] : (uint8_t)0;
+        if (mode != 0 && act) {
             const double *P = Ps + my_lp * kPs;
-            const double *b = Bs + (size_t)tid * kBs;
+            const double *b = Bs + (size_t)li * kBs;
             const double2 t0 = *reinterpret_cast<const double2 *>(b), t1 = *reinterpret_cast<const double2 *>(b + 2),
                           t2 = *reinterpret_cast<const double2 *>(b + 4), t3 = *reinterpret_cast<const double2 *>(b + 6);
             const double B0 = t0.x, B1 = t0.y, B2 = t1.x, B3 = t1.y, B4 = t2.x, B5 = t2.y;
-            double *g = Ga + (size_t)tid * kGa;
+            double *g = Ga + (size_t)li * kGa;
             const double c0 = P[6], c1 = P[7], c2 = P[8];
             g[33] = t3.x - (B0 * c0 + B1 * c1 + B2 * c2);
             g[35] = t3.y - (B3 * c0 + B4 * c1 + B5 * c2);
             const double l0 = P[0], l1 = P[1], l2 = P[2], s0 = P[3], s1 = P[4], s2 = P[5];
-            double *Zt = out.Z + 48 * (int64_t)o0 + 4 * (int64_t)tid;     // chunk-major tile block (z_index): chunk c of this observation at Zt + c * nobs_t * 4
+            double *Zt = out.Z + 48 * (int64_t)r0 + 4 * (int64_t)tid;     // chunk-major tile block (z_index): chunk c of this row at Zt + c * nrows_t * 4
             // two rows (r, r+1) x three components x (lo, hi) = 12 doubles = three 32-byte stores (full sectors)
 #pragma unroll
             for (int r = 0; r < 8; r += 2) {
@@ -365,10 +383,10 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                     zz[rr * 6 + 2] = (l0 * wl0 + wl1) * s1; zz[rr * 6 + 3] = (l0 * wh0 + wh1) * s1;
                     zz[rr * 6 + 4] = (l1 * wl0 + l2 * wl1 + wl2) * s2; zz[rr * 6 + 5] = (l1 * wh0 + l2 * wh1 + wh2) * s2;
                 }
-                double *zp = Zt + (size_t)((r >> 1) * 3) * (size_t)nobs_t * 4;       // chunks 3 r/2 .. 3 r/2 + 2: consecutive lanes write consecutive chunks
+                double *zp = Zt + (size_t)((r >> 1) * 3) * (size_t)nrows_t * 4;       // chunks 3 r/2 .. 3 r/2 + 2: consecutive lanes write consecutive chunks
                 st_global_v4(zp, zz[0], zz[1], zz[2], zz[3]);
-                st_global_v4(zp + (size_t)nobs_t * 4, zz[4], zz[5], zz[6], zz[7]);
-                st_global_v4(zp + (size_t)nobs_t * 8, zz[8], zz[9], zz[10], zz[11]);
+                st_global_v4(zp + (size_t)nrows_t * 4, zz[4], zz[5], zz[6], zz[7]);
+                st_global_v4(zp + (size_t)nrows_t * 8, zz[8], zz[9], zz[10], zz[11]);
             }
         }
         __syncthreads();

@@ -1,17 +1,28 @@
-// Generation-2 Schur-complement kernel: fp64 tensor-pipe (DMMA m8n8k4) rank-3 updates with S-blocks stationary in
-// registers, operands streamed through shared memory by bulk-async (TMA) copies.
+// Schur-complement kernel: fp64 tensor-pipe (DMMA m8n8k4) rank-3 updates with the S blocks stationary in registers, operands
+// streamed through shared memory by bulk-async (TMA) copies, and STATIC hit lists.
 //
 // Math.  With V*_i = L_i D_i L_i^T (3x3, per point) and  Z_ij = W_ij L_i^-T |D_i|^-1/2  (16x3, per observation),
 //     sum_i Y_ij W_ik^T = sum_i Z_ij diag(sign D_i) Z_ik^T            (sba_levmar.c:1075-1114 computes the left side)
 // so the whole Schur complement is a sum of signed rank-3 outer products of ONE operand array Z (384 B per
 // observation) instead of two (Y and W).  For a damped, positive-definite V* all signs are +.
 //
-// Work decomposition.  The upper-triangular 16x16 camera blocks (j <= k) are dealt to G groups x 8 warps x NB slots.
-// A CTA = (chunk of point tiles, group); each warp keeps its NB blocks as DMMA accumulators (8 doubles per lane per
-// block) for the whole chunk.  Per tile (<= 32 points, <= TO observations) the CTA's Z block arrives by cp.async.bulk,
-// one copy per chunk plane (z_index), into a double-buffered shared-memory stage; per block the warp ballots the points that
-// see both cameras, compacts them into a hit list and feeds the K dimension (3 per hit, 4 per DMMA step) without padding
-// (groups of 4 hits fill 3 steps; a last partial group runs through the same steps with its missing slots on a zero row).
+// Work decomposition.  The upper-triangular 16x16 camera blocks (j <= k) are dealt to G groups x NW warps x NB slots.
+// A CTA = (chunk of point tiles, group); each warp keeps its NB blocks as DMMA accumulators (8 doubles per lane per block)
+// for the whole chunk.  Per tile (<= 32 points, <= 256 rows) the CTA's Z block arrives by cp.async.bulk, one copy per chunk
+// plane, into a double-buffered shared-memory stage, together with the tile's slice of the static index.
+//
+// Static index (built once per upload, visibility never changes during a solve; k_hits_*): for every (tile, block) the list of
+// "hits" - points of the tile that see both cameras of the block - as (row of Z_ij, row of Z_ik) byte pairs, plus a table
+// (offset, count) per block.  The kernel does no visibility test at all: it walks lists.
+//
+// Rows, classes and bank conflicts.  A tile's Z block has one 32-byte slot per row and chunk plane, so the shared-memory bank
+// group (16 bytes) of element x = 3 (row pair g) + component of row s is (x + 2 s) mod 8.  Rows are not the tile's
+// observations in order: every point is given one of four CLASSES and its observations occupy rows 4 i + class.  A group of
+// four hits of four different classes is processed in three DMMA steps, step t = component t of all four hits, k-lane = hit:
+// the eight lanes of a quarter warp then read eight different bank groups - conflict free - and the K dimension of the
+// DMMA is full (4 hits x 3 components = 3 steps x 4).  The index build orders every list so that its groups of four mix the
+// classes as far as the list allows; the 1-3 hits left over take one step each (k-lanes 0-2 = the three components of one
+// hit, six consecutive elements per quarter warp: conflict free by construction).
 // Fragment layout of mma.m8n8k4.f64: A: lane -> (row = lane>>2, k = lane&3); B: (k = lane&3, col = lane>>2);
 // C: (row = lane>>2, cols 2*(lane&3), +1).  The 48 values of an observation are ordered ((r%8)*3 + c)*2 + r/8 so one
 // 16-byte load gives a lane the (row, row+8) pair of its fragment - the same load serves the A and the B operand;
@@ -21,24 +32,30 @@
 
 namespace argus {
 
-constexpr int kTilePts = 32;        // points per tile (one ballot)
+constexpr int kTilePts = 32;        // points per tile
+constexpr int kTileRows = 256;      // Z rows per tile: 4 classes x 64
+constexpr int kClassCap = 64;       // observations per class and tile
 constexpr int kSchurWarps = 8;
 
 __host__ __device__ __forceinline__ int zperm(int r, int c) { return ((r & 7) * 3 + c) * 2 + (r >> 3); }
 
 struct TilePlan {
     int ntiles;
-    int tile_obs;                   // TO: max observations per tile
     const int32_t *tile_pt;         // ntiles + 1: first point of each tile
     const int32_t *tile_o;          // ntiles + 1: first observation of each tile
+    const int32_t *tile_r;          // ntiles + 1: first Z row of each tile (a tile has 4 * max class fill rows)
 };
 
 struct SchurPlan {
     int G;                          // block groups
     int nchunk;                     // point-tile chunks (grid.x)
     int npairs;                     // upper-triangular camera pairs among the free cameras
-    const uint16_t *blk_jk;         // [G][8][NB]: j | k << 8 (absolute camera ids), 0xFFFF = empty slot
-    const int32_t *blk_pair;        // [G][8][NB]: pair index (row-major upper triangle over free cameras) or -1
+    int nslots;                     // NW * NB block slots per group
+    const uint16_t *blk_jk;         // [G][NW][NB]: j | k << 8 (absolute camera ids), 0xFFFF = empty slot
+    const int32_t *blk_pair;        // [G][NW][NB]: pair index (row-major upper triangle over free cameras) or -1
+    const uint32_t *hit_tab;        // [ntiles][G][nslots]: offset of the block's list inside the (tile, group) entry block | hits << 16 | diagonal block << 31
+    const uint16_t *hit_ent;        // entries: row of Z_ij | row of Z_ik << 8
+    const int32_t *hit_ptr;         // [ntiles * G + 1]: first entry of every (tile, group) block (multiples of 8 entries)
 };
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) ----
@@ -60,6 +77,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
                      : "=r"(done) : "r"(a), "r"(parity) : "memory");
     }
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -69,100 +90,258 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-
-// Z in HBM: per tile of points one block of 48 * nobs_t doubles, chunk-major inside the block: the 12 four-double chunks of an
-// observation's 16 x 3 row (chunk = zperm / 4) live in 12 planes of nobs_t chunks each, so that the one-thread-per-observation
-// producer writes consecutive 32-byte chunks (coalesced) and the Schur kernel copies a tile plane by plane.
-//   element e (= zperm(r, c)) of local observation lk of a tile starting at observation o0:
-__host__ __device__ __forceinline__ int64_t z_index(int64_t o0, int nobs_t, int lk, int e)
-{
-    return 48 * o0 + ((int64_t)(e >> 2) * nobs_t + lk) * 4 + (e & 3);
-}
-
-// The Schur kernel.  grid = (nchunk, G); NW consumer warps, each owning NB blocks; the copy producer is lane 0 of warp 0
-// (PROD = 0) or a dedicated extra warp (PROD = 1).
-// Dynamic shared memory: 2 x [Z tile: 12 chunk planes of (TO + 1) x 32 bytes | rank tile: mp x 32 bytes], then 384 B of zeros.
-// Spart[chunk][pair][256]: per-chunk partial sums in fragment order (lane * 8 + q), q = (ri*2 + ci)*2 + e for the
-// 8x8 sub-tile (ri, ci) of the block: element (row = ri*8 + lane>>2, col = ci*8 + 2*(lane&3) + e).
-//
-// pt_rank[tile][mp][32] (uint8, static): position of camera j in point i's observation list, 0xFF when i does not see j (or i is
-// a fixed point).  It travels with the Z tile, so finding the points that see both cameras of a block is two byte loads.
-// K mapping: one hit (K = 3, padded to the DMMA's 4) per step; the k-lanes 0..2 of a step read the three components of the
-// same observation at consecutive 16-byte addresses, which is free of shared-memory bank conflicts (a 4-hits-per-3-steps
-// packing was measured slower: its four k-lanes read different observations at the same in-row offset = 4-way conflicts).
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr)
 {
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ double flip_sign(double v, uint32_t bit)      // bit = 0 or 1
 {
     return __hiloint2double(__double2hiint(v) ^ (int)(bit << 31), __double2loint(v));
 }
+__device__ __forceinline__ double2 flip_sign2(double2 v, uint32_t bit) { v.x = flip_sign(v.x, bit); v.y = flip_sign(v.y, bit); return v; }
 
-template <int NB, int NW, int PROD>
-__global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb, TilePlan tp, SchurPlan sp, const double *__restrict__ Z,
-                                                                 const uint8_t *__restrict__ zsign, const uint8_t *__restrict__ pt_rank,
-                                                                 int mp, double *__restrict__ Spart, const int *__restrict__ done)
+// Z in HBM: per tile one block of 48 * nrows doubles, chunk-major inside the block: the 12 four-double chunks of a row
+// (chunk = zperm / 4) live in 12 planes of nrows chunks each, so that the one-thread-per-row producer writes consecutive
+// 32-byte chunks (coalesced) and the Schur kernel copies a tile plane by plane.
+//   element e (= zperm(r, c)) of row `row` of a tile whose first row is r0:
+__host__ __device__ __forceinline__ int64_t z_index(int64_t r0, int nrows, int row, int e)
+{
+    return 48 * r0 + ((int64_t)(e >> 2) * nrows + row) * 4 + (e & 3);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Static hit lists.  One CTA per tile; a warp takes block slots round robin, lane = point of the tile.
+//   pass 0 (k_hits_count): per (tile, group) the number of entries, rounded up to 8 (16-byte granularity of the bulk copies)
+//   scan (k_index_scan of ba_lin_tile.cuh) -> hit_ptr
+//   pass 1 (k_hits_fill): entries in processing order + the (offset, count) table
+// Order of a list of n hits: sorted by class, the classes by ascending population, then dealt round robin to the n / 4 full
+// groups (hit at sorted position q < 4 (n / 4) -> group q mod (n / 4), k-lane q div (n / 4)): a group receives two hits of one
+// class only when that class holds more than n / 4 of the hits; the n mod 4 hits left over come from the most populous class.
+// pt_slot0[p] = 4 * (first row index of point p inside its class) + class;  its observation of rank r sits in row pt_slot0 + 4 r.
+// ---------------------------------------------------------------------------------------------------------------------------
+struct HitCtx {
+    uint64_t mask;      // cameras seeing this lane's point (0 for lanes without a free point)
+    uint32_t slot0;     // pt_slot0 of this lane's point
+};
+__device__ __forceinline__ HitCtx hit_ctx(int lane, int p0, int npts, int64_t ncon, const uint64_t *__restrict__ pt_mask,
+                                          const uint8_t *__restrict__ pt_slot0)
+{
+    HitCtx h; h.mask = 0; h.slot0 = 0;
+    if (lane < npts && (int64_t)p0 + lane >= ncon) { h.mask = pt_mask[p0 + lane]; h.slot0 = pt_slot0[p0 + lane]; }
+    return h;
+}
+
+__global__ void __launch_bounds__(256) k_hits_count(int ntiles, int G, int nslots, const int32_t *__restrict__ tile_pt, int64_t ncon,
+                                                    const uint64_t *__restrict__ pt_mask, const uint8_t *__restrict__ pt_slot0,
+                                                    const uint16_t *__restrict__ blk_jk, int32_t *__restrict__ tg_count)
+{
+    extern __shared__ int s_tot[];       // G
+    const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) s_tot[g] = 0;
+    __syncthreads();
+    const int p0 = tile_pt[tile], npts = tile_pt[tile + 1] - p0;
+    const HitCtx h = hit_ctx(lane, p0, npts, ncon, pt_mask, pt_slot0);
+    for (int q = warp; q < G * nslots; q += 8) {
+        const uint32_t jk = blk_jk[q];
+        if (jk == 0xFFFFu) continue;
+        const int j = jk & 0xFF, k = jk >> 8;
+        const bool hit = ((h.mask >> j) & 1ull) && ((h.mask >> k) & 1ull);
+        const int n = __popc(__ballot_sync(0xffffffffu, hit));
+        if (lane == 0 && n) atomicAdd(&s_tot[q / nslots], n);          // integer: order independent
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) tg_count[(size_t)tile * G + g] = (s_tot[g] + 7) & ~7;
+}
+
+__global__ void __launch_bounds__(256) k_hits_fill(int ntiles, int G, int nslots, const int32_t *__restrict__ tile_pt, int64_t ncon,
+                                                   const uint64_t *__restrict__ pt_mask, const uint8_t *__restrict__ pt_slot0,
+                                                   const uint16_t *__restrict__ blk_jk, const int32_t *__restrict__ hit_ptr,
+                                                   uint32_t *__restrict__ hit_tab, uint16_t *__restrict__ hit_ent)
+{
+    extern __shared__ int s_n[];         // G * nslots: hits per slot, then offsets
+    const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p0 = tile_pt[tile], npts = tile_pt[tile + 1] - p0;
+    const HitCtx h = hit_ctx(lane, p0, npts, ncon, pt_mask, pt_slot0);
+    const int nq = G * nslots;
+    for (int q = warp; q < nq; q += 8) {
+        const uint32_t jk = blk_jk[q];
+        int n = 0;
+        if (jk != 0xFFFFu) {
+            const int j = jk & 0xFF, k = jk >> 8;
+            n = __popc(__ballot_sync(0xffffffffu, ((h.mask >> j) & 1ull) && ((h.mask >> k) & 1ull)));
+        }
+        if (lane == 0) s_n[q] = n;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {          // exclusive offsets inside each (tile, group) block
+        int acc = 0;
+        for (int q = g * nslots; q < (g + 1) * nslots; ++q) {
+            const int n = s_n[q];
+            const uint32_t jk = blk_jk[q];
+            s_n[q] = (int)((uint32_t)acc | ((uint32_t)n << 16) | ((jk != 0xFFFFu && (jk & 0xFF) == (jk >> 8)) ? 0x80000000u : 0u));
+            acc += n;
+        }
+    }
+    __syncthreads();
+    for (int q = warp; q < nq; q += 8) {
+        const uint32_t tb = (uint32_t)s_n[q];
+        if (lane == 0) hit_tab[(size_t)tile * nq + q] = tb;
+        const int n = (int)((tb >> 16) & 0x7FFFu);
+        if (!n) continue;
+        const uint32_t jk = blk_jk[q];
+        const int j = jk & 0xFF, k = jk >> 8;
+        const bool hit = ((h.mask >> j) & 1ull) && ((h.mask >> k) & 1ull);
+        const int cls = (int)(h.slot0 & 3u);
+        // class populations, classes ranked by (population, class id) ascending
+        uint32_t bal[4]; int cnt[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { bal[c] = __ballot_sync(0xffffffffu, hit && cls == c); cnt[c] = __popc(bal[c]); }
+        if (hit) {
+            int before = 0, mine = 0; uint32_t mybal = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (c == cls) { mine = cnt[c]; mybal = bal[c]; }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (cnt[c] < mine || (cnt[c] == mine && c < cls)) before += cnt[c];        // hits of classes ranked before mine
+            const int pos = before + __popc(mybal & ((1u << lane) - 1u));
+            const int F = n >> 2;
+            const int idx = (pos < 4 * F) ? 4 * (pos % F) + pos / F : pos;
+            const uint32_t ra = h.slot0 + 4u * (uint32_t)__popcll(h.mask & ((1ull << j) - 1ull));
+            const uint32_t rb = h.slot0 + 4u * (uint32_t)__popcll(h.mask & ((1ull << k) - 1ull));
+            hit_ent[(size_t)hit_ptr[(size_t)tile * G + q / nslots] + (tb & 0xFFFFu) + idx] = (uint16_t)(ra | (rb << 8));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// The Schur kernel.  grid = (nchunk, G); NW consumer warps, each owning NB blocks; the copy producer is lane 0 of warp 0.
+// Dynamic shared memory: 2 stages of [Z tile: 12 chunk planes of (256 + 1) x 32 bytes | hit entries | hit table | sign bytes].
+// Row 256 of every plane is never written by the copies: it is the all-zero row the fourth k-lane of a left-over step reads.
+// Spart[chunk][pair][256]: per-chunk partial sums in fragment order (lane * 8 + q), q = (ri*2 + ci)*2 + e for the
+// 8x8 sub-tile (ri, ci) of the block: element (row = ri*8 + lane>>2, col = ci*8 + 2*(lane&3) + e).
+// ---------------------------------------------------------------------------------------------------------------------------
+constexpr int kSchurUnroll = 1;      // groups of four hits per trip of the inner loop
+constexpr bool kSchurDiagPath = false;   // a separate 9-DMMA code path for the diagonal blocks (j == k): fewer DMMAs for 16 of 136 blocks, twice the code
+constexpr uint32_t kPlaneBytes = (kTileRows + 1) * 32u;              // 8224: consecutive planes start 8 banks apart
+constexpr uint32_t kZBytes = 12u * kPlaneBytes;
+__host__ __device__ constexpr uint32_t schur_ent_bytes(int nslots) { return (uint32_t)nslots * kTilePts * 2u; }
+__host__ __device__ constexpr uint32_t schur_tab_bytes(int nslots) { return ((uint32_t)nslots * 4u + 15u) & ~15u; }
+__host__ __device__ constexpr uint32_t schur_stage_bytes(int nslots) { return kZBytes + schur_ent_bytes(nslots) + schur_tab_bytes(nslots) + 256u; }
+
+template <bool DIAG, bool SIGNED>
+__device__ __forceinline__ void schur_block(double (&acc)[8], uint32_t ent_addr, int n, uint32_t zbase, uint32_t off0, uint32_t off1,
+                                            uint32_t off2, uint32_t offk, int kk, uint32_t zs_addr)
+{
+    constexpr bool anyneg = SIGNED;
+    const int nfull = n >> 2, rem = n & 3;
+    // ---- groups of four hits: step t = component t of the four hits, k-lane = hit ----
+    uint32_t e = (nfull > 0) ? lds_u16(ent_addr + 2u * (uint32_t)kk) : 0u;
+#pragma unroll kSchurUnroll
+    for (int g = 0; g < nfull; ++g) {
+        const uint32_t ra = zbase + (e & 0xFFu) * 32u, rb = zbase + (e >> 8) * 32u;
+        double2 a0 = lds_f64x2(ra + off0), a1 = lds_f64x2(ra + off1), a2 = lds_f64x2(ra + off2);
+        double2 b0, b1, b2;
+        if (!DIAG) { b0 = lds_f64x2(rb + off0); b1 = lds_f64x2(rb + off1); b2 = lds_f64x2(rb + off2); }
+        else { b0 = a0; b1 = a1; b2 = a2; }
+        if (anyneg) {
+            uint32_t sg;
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sg) : "r"(zs_addr + (e & 0xFFu)));
+            a0 = flip_sign2(a0, sg & 1u); a1 = flip_sign2(a1, (sg >> 1) & 1u); a2 = flip_sign2(a2, (sg >> 2) & 1u);
+        }
+        if (g + 1 < nfull) e = lds_u16(ent_addr + 8u * (uint32_t)(g + 1) + 2u * (uint32_t)kk);      // next group's entry, off the chain
+        dmma884(acc[0], acc[1], a0.x, b0.x); dmma884(acc[2], acc[3], a0.x, b0.y);
+        if (!DIAG) dmma884(acc[4], acc[5], a0.y, b0.x);
+        dmma884(acc[6], acc[7], a0.y, b0.y);
+        dmma884(acc[0], acc[1], a1.x, b1.x); dmma884(acc[2], acc[3], a1.x, b1.y);
+        if (!DIAG) dmma884(acc[4], acc[5], a1.y, b1.x);
+        dmma884(acc[6], acc[7], a1.y, b1.y);
+        dmma884(acc[0], acc[1], a2.x, b2.x); dmma884(acc[2], acc[3], a2.x, b2.y);
+        if (!DIAG) dmma884(acc[4], acc[5], a2.y, b2.x);
+        dmma884(acc[6], acc[7], a2.y, b2.y);
+    }
+    // ---- left-over hits: one step each, k-lanes 0..2 = the three components, k-lane 3 reads the zero row ----
+    if (rem) {
+        double2 av[3], bv[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (r < rem) {
+                const uint32_t er = lds_u16(ent_addr + 8u * (uint32_t)nfull + 2u * (uint32_t)r);
+                av[r] = make_double2(0.0, 0.0); bv[r] = av[r];
+                if (kk < 3) {                                   // the fourth k-lane contributes zeros (no load: nothing to conflict with)
+                    av[r] = lds_f64x2(zbase + (er & 0xFFu) * 32u + offk);
+                    bv[r] = DIAG ? av[r] : lds_f64x2(zbase + (er >> 8) * 32u + offk);
+                }
+                if (anyneg) {
+                    uint32_t sg;
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(sg) : "r"(zs_addr + (er & 0xFFu)));
+                    av[r] = flip_sign2(av[r], (kk < 3) ? ((sg >> kk) & 1u) : 0u);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (r < rem) {
+                dmma884(acc[0], acc[1], av[r].x, bv[r].x); dmma884(acc[2], acc[3], av[r].x, bv[r].y);
+                if (!DIAG) dmma884(acc[4], acc[5], av[r].y, bv[r].x);
+                dmma884(acc[6], acc[7], av[r].y, bv[r].y);
+            }
+        }
+    }
+}
+
+template <int NB, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(TilePlan tp, SchurPlan sp, const double *__restrict__ Z,
+                                                          const uint8_t *__restrict__ zs, double *__restrict__ Spart,
+                                                          const int *__restrict__ done)
 {
     if (*done) return;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const uint32_t plane = (uint32_t)tp.tile_obs * 32u + 32u;                   // one chunk plane (+32 B: consecutive planes start 8 banks apart)
-    const uint32_t zbytes = 12u * plane;
-    const uint32_t stage = zbytes + (uint32_t)kTilePts * (uint32_t)mp;          // multiple of 16
-    unsigned char *zero_blk = smem_raw + 2 * stage;
+    constexpr int kSlots = NW * NB;
+    constexpr uint32_t kEnt = schur_ent_bytes(kSlots), kTab = schur_tab_bytes(kSlots), kStage = schur_stage_bytes(kSlots);
     __shared__ __align__(8) uint64_t mfull[2], mempty[2];
-    __shared__ uint2 hitlist[NW][kTilePts + 4];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g8 = lane >> 2, kk = lane & 3;
     const int chunk = blockIdx.x, grp = blockIdx.y;
     const int ntl = (tp.ntiles > chunk) ? (tp.ntiles - chunk + sp.nchunk - 1) / sp.nchunk : 0;   // tiles of this chunk
 
-    if (threadIdx.x < 96) reinterpret_cast<uint32_t *>(zero_blk)[threadIdx.x] = 0u;        // a whole Z row of zeros (384 B)
-    // the pad slot (index TO) of every chunk plane of both stages is never written by the copies: it is the all-zero row
+    // the zero row (index 256) of every chunk plane of both stages
     for (int t = threadIdx.x; t < 2 * 12 * 8; t += blockDim.x)
-        reinterpret_cast<uint32_t *>(smem_raw + (size_t)(t / 96) * stage + (size_t)((t % 96) / 8) * plane + (size_t)tp.tile_obs * 32u)[t % 8] = 0u;
+        reinterpret_cast<uint32_t *>(smem_raw + (size_t)(t / 96) * kStage + (size_t)((t % 96) / 8) * kPlaneBytes + (size_t)kTileRows * 32u)[t % 8] = 0u;
     if (threadIdx.x == 0) { mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1); mbar_init(&mempty[0], NW); mbar_init(&mempty[1], NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    // producer duty (warp 0, lane 0): bulk-async copies of the Z rows and the rank rows of local tile `it` into stage it & 1,
-    // after every warp has released that stage (mempty)
+    // producer duty (warp 0, lane 0): bulk-async copies of the tile's Z planes, hit entries, hit table and sign bytes into
+    // stage it & 1, after every warp has released that stage (mempty)
     auto produce = [&](int it) {
-        if (warp == (PROD ? NW : 0) && lane == 0) {
+        if (warp == 0 && lane == 0) {
             const int b = it & 1;
             if (it >= 2) mbar_wait(&mempty[b], (uint32_t)(((it >> 1) - 1) & 1));
             const int t = chunk + it * sp.nchunk;
-            const int p0 = tp.tile_pt[t], p1 = tp.tile_pt[t + 1];
-            const int o0 = pb.obs_ptr[p0], o1 = pb.obs_ptr[p1];
-            const uint32_t zb = (uint32_t)(o1 - o0) * 384u, rb = (uint32_t)kTilePts * (uint32_t)mp; (void)p1;
-            unsigned char *dst = smem_raw + (size_t)b * stage;
-            const char *src = reinterpret_cast<const char *>(Z + 48 * (int64_t)o0);
-            mbar_expect_tx(&mfull[b], zb + rb);
-            const uint32_t pl = (uint32_t)(o1 - o0) * 32u;                     // bytes of one chunk plane of this tile
-            if (pl) for (uint32_t q = 0; q < 12u; ++q) bulk_g2s(dst + q * plane, src + (size_t)q * pl, pl, &mfull[b]);
-            bulk_g2s(dst + zbytes, pt_rank + (size_t)t * rb, rb, &mfull[b]);
+            const int r0 = tp.tile_r[t], nrows = tp.tile_r[t + 1] - r0;
+            const int32_t e0 = sp.hit_ptr[(size_t)t * sp.G + grp], e1 = sp.hit_ptr[(size_t)t * sp.G + grp + 1];
+            const uint32_t pl = (uint32_t)nrows * 32u, eb = (uint32_t)(e1 - e0) * 2u;
+            unsigned char *dst = smem_raw + (size_t)b * kStage;
+            mbar_expect_tx(&mfull[b], 12u * pl + eb + kTab + 256u);
+            const char *src = reinterpret_cast<const char *>(Z + 48 * (int64_t)r0);
+            if (pl) for (uint32_t q = 0; q < 12u; ++q) bulk_g2s(dst + q * kPlaneBytes, src + (size_t)q * pl, pl, &mfull[b]);
+            if (eb) bulk_g2s(dst + kZBytes, sp.hit_ent + e0, eb, &mfull[b]);
+            bulk_g2s(dst + kZBytes + kEnt, sp.hit_tab + ((size_t)t * sp.G + grp) * kSlots, kTab, &mfull[b]);
+            bulk_g2s(dst + kZBytes + kEnt + kTab, zs + (size_t)t * 256, 256u, &mfull[b]);
         }
         __syncwarp();
     };
-    if (PROD) {                      // dedicated producer warp: runs ahead of the consumers by up to two stages
-        if (warp == NW) { for (int it = 0; it < ntl; ++it) produce(it); return; }
-    } else if (ntl > 0) produce(0);
+    if (ntl > 0) produce(0);
 
-    // ---------------- consumer warps ----------------
-    int bj[NB], bk[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-        const uint16_t jk = sp.blk_jk[((size_t)grp * NW + warp) * NB + b];
-        bj[b] = (jk == 0xFFFF) ? -1 : (jk & 0xFF);
-        bk[b] = (jk == 0xFFFF) ? -1 : (jk >> 8);
-    }
     double acc[NB][8];
 #pragma unroll
     for (int b = 0; b < NB; ++b)
@@ -170,144 +349,33 @@ __global__ void __launch_bounds__((NW + PROD) * 32, 1) k_schur_mma(BaProblem pb,
         for (int q = 0; q < 8; ++q) acc[b][q] = 0.0;
 
     const uint32_t smem_base = smem_u32(smem_raw);
-    uint2 *hl = hitlist[warp];
-    // byte offset of 16-byte element x = g8 * 3 + component of a row, relative to the row's chunk slot in plane 0
-    auto elem_off = [&](int x) { return (uint32_t)(x >> 1) * plane + (uint32_t)(x & 1) * 16u; };
-    const uint32_t lane_off = elem_off(g8 * 3 + (kk < 3 ? kk : 0));
-    // (hit-in-group, component) of this k-lane in the three steps of a full 4-hit group
-    const int gh0 = (kk == 3) ? 1 : 0, gh1 = (kk == 0 || kk == 1) ? 1 : 2, gh2 = (kk == 0) ? 2 : 3;
-    const int gc0 = (kk == 3) ? 0 : kk, gc1 = (kk == 0) ? 1 : (kk == 1) ? 2 : (kk == 2) ? 0 : 1, gc2 = (kk == 0) ? 2 : kk - 1;
-    const uint32_t goff0 = elem_off(g8 * 3 + gc0), goff1 = elem_off(g8 * 3 + gc1), goff2 = elem_off(g8 * 3 + gc2);
-
-    // per-lane metadata of the point this lane represents in a tile: local observation base and the sign bits of D.
-    // Two-level prefetch so no load waits on another: tile bounds two tiles ahead, per-point data one tile ahead.
-    auto load_bounds = [&](int it, int &p0, int &p1, int &o0) {
-        p0 = 0; p1 = 0; o0 = 0;
-        if (it < ntl) { const int t = chunk + it * sp.nchunk; p0 = tp.tile_pt[t]; p1 = tp.tile_pt[t + 1]; o0 = tp.tile_o[t]; }
-    };
-    auto load_meta = [&](int p0, int p1, int o0, int &ob, uint32_t &sg, bool &have) {
-        ob = 0; sg = 0; have = false;
-        const int p = p0 + lane;
-        if (p < p1) { ob = pb.obs_ptr[p] - o0; sg = zsign[p]; have = true; }
-    };
-    int bp0, bp1, bo0;                       // bounds of tile it + 1 (then it + 2)
-    int ob_n; uint32_t sg_n; bool hv_n;
-    load_bounds(0, bp0, bp1, bo0);
-    load_meta(bp0, bp1, bo0, ob_n, sg_n, hv_n);
-    load_bounds(1, bp0, bp1, bo0);
+    // byte offset of the 16-byte element x = g8 * 3 + component of a row, relative to the row's slot in plane 0
+    auto elem_off = [&](int x) { return (uint32_t)(x >> 1) * kPlaneBytes + (uint32_t)(x & 1) * 16u; };
+    const uint32_t off0 = elem_off(g8 * 3), off1 = elem_off(g8 * 3 + 1), off2 = elem_off(g8 * 3 + 2);
+    const uint32_t offk = (kk == 1) ? off1 : (kk == 2) ? off2 : off0;
 
     for (int it = 0; it < ntl; ++it) {
-        const int ob = ob_n; const uint32_t sg = sg_n; const bool have = hv_n;
-        if (!PROD && it + 1 < ntl) produce(it + 1);
-        load_meta(bp0, bp1, bo0, ob_n, sg_n, hv_n);          // tile it + 1 (bounds arrived during the previous tile)
-        load_bounds(it + 2, bp0, bp1, bo0);
+        if (it + 1 < ntl) produce(it + 1);
         const int sb = it & 1;
         mbar_wait(&mfull[sb], (uint32_t)((it >> 1) & 1));
-        const uint32_t zoff = (uint32_t)sb * stage;                           // byte offset of this stage from smem_base
-        const uint32_t zbase = smem_base + zoff;
-        const uint32_t zrow_addr = zbase + (uint32_t)tp.tile_obs * 32u;       // plane-0 address of the all-zero row of this stage
-        const unsigned char *rk = smem_raw + zoff + zbytes + lane;          // rank tile is camera-major: [cam][32 points]
-        const bool anyneg = __any_sync(0xffffffffu, sg != 0);
-
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            const int j = bj[b], k = bk[b];
-            if (j < 0) continue;
-            const uint32_t rj = have ? rk[j * kTilePts] : 0xFFu, rkk = have ? rk[k * kTilePts] : 0xFFu;
-            const bool hit = (rj | rkk) < 0x80u;
-            const uint32_t bal = __ballot_sync(0xffffffffu, hit);
-            const int nh = __popc(bal);
-            if (nh == 0) continue;
-            if (hit) {
-                const int pos = __popc(bal & ((1u << lane) - 1u));
-                // shared-memory byte addresses of the two Z rows of this hit; bits 28..30 of .x carry the sign bits of D
-                const uint32_t aj = zbase + (uint32_t)(ob + (int)rj) * 32u, ak = zbase + (uint32_t)(ob + (int)rkk) * 32u;
-                hl[pos] = make_uint2(aj | (sg << 28), ak);
-            }
-            if (lane < 3) hl[nh + lane] = make_uint2(zrow_addr, zrow_addr);     // missing hits of the last group -> the zero slot
-            __syncwarp();
-            // K packing.  Full groups of 4 hits fill 3 DMMA steps completely (12 K-slots): k-lane kk handles the (hit, component)
-            // pairs  kk0: (0,0)(1,1)(2,2)  kk1: (0,1)(1,2)(3,0)  kk2: (0,2)(2,0)(3,1)  kk3: (1,0)(2,1)(3,2)  of the group in steps
-            // 0,1,2.  The remaining 1..3 hits take one step each (k-lanes 0..2 = the three components, k-lane 3 reads zeros).
-            // Every group of up to 4 hits goes through the same three packed steps; the slots of a last, partial group that have no
-            // hit read the all-zero pad slot of the chunk planes (hit-list entries nh .. nh + 2 point there), and steps that would
-            // only multiply zeros are skipped (a group of r hits needs min(r, 3) steps).
-            const int nfull = nh & ~3, rem = nh - nfull;
-            if (j == k) {
-                for (int q = 0; q < nfull; q += 4) {
-                    const uint2 e0 = hl[q + gh0], e1 = hl[q + gh1], e2 = hl[q + gh2];
-                    const double2 a0 = lds_f64x2((e0.x & 0x0FFFFFFFu) + goff0), a1 = lds_f64x2((e1.x & 0x0FFFFFFFu) + goff1),
-                                  a2 = lds_f64x2((e2.x & 0x0FFFFFFFu) + goff2);
-                    double2 s0 = a0, s1 = a1, s2 = a2;
-                    if (anyneg) {
-                        const uint32_t b0 = ((e0.x >> 28) >> gc0) & 1u, b1 = ((e1.x >> 28) >> gc1) & 1u, b2 = ((e2.x >> 28) >> gc2) & 1u;
-                        s0.x = flip_sign(s0.x, b0); s0.y = flip_sign(s0.y, b0); s1.x = flip_sign(s1.x, b1); s1.y = flip_sign(s1.y, b1);
-                        s2.x = flip_sign(s2.x, b2); s2.y = flip_sign(s2.y, b2);
-                    }
-                    dmma884(acc[b][0], acc[b][1], s0.x, a0.x); dmma884(acc[b][2], acc[b][3], s0.x, a0.y); dmma884(acc[b][6], acc[b][7], s0.y, a0.y);
-                    dmma884(acc[b][0], acc[b][1], s1.x, a1.x); dmma884(acc[b][2], acc[b][3], s1.x, a1.y); dmma884(acc[b][6], acc[b][7], s1.y, a1.y);
-                    dmma884(acc[b][0], acc[b][1], s2.x, a2.x); dmma884(acc[b][2], acc[b][3], s2.x, a2.y); dmma884(acc[b][6], acc[b][7], s2.y, a2.y);
-                }
-                if (rem) {          // last, partial group: same packed steps, all loads issued before the first DMMA
-                    const uint2 e0 = hl[nfull + gh0];
-                    uint2 e1 = e0, e2 = e0;
-                    double2 a0 = lds_f64x2((e0.x & 0x0FFFFFFFu) + goff0), a1 = a0, a2 = a0;
-                    if (rem >= 2) { e1 = hl[nfull + gh1]; a1 = lds_f64x2((e1.x & 0x0FFFFFFFu) + goff1); }
-                    if (rem >= 3) { e2 = hl[nfull + gh2]; a2 = lds_f64x2((e2.x & 0x0FFFFFFFu) + goff2); }
-                    double2 s0 = a0, s1 = a1, s2 = a2;
-                    if (anyneg) {
-                        const uint32_t b0 = ((e0.x >> 28) >> gc0) & 1u, b1 = ((e1.x >> 28) >> gc1) & 1u, b2 = ((e2.x >> 28) >> gc2) & 1u;
-                        s0.x = flip_sign(s0.x, b0); s0.y = flip_sign(s0.y, b0); s1.x = flip_sign(s1.x, b1); s1.y = flip_sign(s1.y, b1);
-                        s2.x = flip_sign(s2.x, b2); s2.y = flip_sign(s2.y, b2);
-                    }
-                    dmma884(acc[b][0], acc[b][1], s0.x, a0.x); dmma884(acc[b][2], acc[b][3], s0.x, a0.y); dmma884(acc[b][6], acc[b][7], s0.y, a0.y);
-                    if (rem >= 2) { dmma884(acc[b][0], acc[b][1], s1.x, a1.x); dmma884(acc[b][2], acc[b][3], s1.x, a1.y); dmma884(acc[b][6], acc[b][7], s1.y, a1.y); }
-                    if (rem >= 3) { dmma884(acc[b][0], acc[b][1], s2.x, a2.x); dmma884(acc[b][2], acc[b][3], s2.x, a2.y); dmma884(acc[b][6], acc[b][7], s2.y, a2.y); }
-                }
-            } else {
-                for (int q = 0; q < nfull; q += 4) {
-                    const uint2 e0 = hl[q + gh0], e1 = hl[q + gh1], e2 = hl[q + gh2];
-                    double2 a0 = lds_f64x2((e0.x & 0x0FFFFFFFu) + goff0), a1 = lds_f64x2((e1.x & 0x0FFFFFFFu) + goff1),
-                            a2 = lds_f64x2((e2.x & 0x0FFFFFFFu) + goff2);
-                    const double2 b0 = lds_f64x2(e0.y + goff0), b1 = lds_f64x2(e1.y + goff1), b2 = lds_f64x2(e2.y + goff2);
-                    if (anyneg) {
-                        const uint32_t t0 = ((e0.x >> 28) >> gc0) & 1u, t1 = ((e1.x >> 28) >> gc1) & 1u, t2 = ((e2.x >> 28) >> gc2) & 1u;
-                        a0.x = flip_sign(a0.x, t0); a0.y = flip_sign(a0.y, t0); a1.x = flip_sign(a1.x, t1); a1.y = flip_sign(a1.y, t1);
-                        a2.x = flip_sign(a2.x, t2); a2.y = flip_sign(a2.y, t2);
-                    }
-                    dmma884(acc[b][0], acc[b][1], a0.x, b0.x); dmma884(acc[b][2], acc[b][3], a0.x, b0.y);
-                    dmma884(acc[b][4], acc[b][5], a0.y, b0.x); dmma884(acc[b][6], acc[b][7], a0.y, b0.y);
-                    dmma884(acc[b][0], acc[b][1], a1.x, b1.x); dmma884(acc[b][2], acc[b][3], a1.x, b1.y);
-                    dmma884(acc[b][4], acc[b][5], a1.y, b1.x); dmma884(acc[b][6], acc[b][7], a1.y, b1.y);
-                    dmma884(acc[b][0], acc[b][1], a2.x, b2.x); dmma884(acc[b][2], acc[b][3], a2.x, b2.y);
-                    dmma884(acc[b][4], acc[b][5], a2.y, b2.x); dmma884(acc[b][6], acc[b][7], a2.y, b2.y);
-                }
-                if (rem) {          // last, partial group: same packed steps, all loads issued before the first DMMA
-                    const uint2 e0 = hl[nfull + gh0];
-                    uint2 e1 = e0, e2 = e0;
-                    double2 a0 = lds_f64x2((e0.x & 0x0FFFFFFFu) + goff0), a1 = a0, a2 = a0;
-                    double2 b0 = lds_f64x2(e0.y + goff0), b1 = b0, b2 = b0;
-                    if (rem >= 2) { e1 = hl[nfull + gh1]; a1 = lds_f64x2((e1.x & 0x0FFFFFFFu) + goff1); b1 = lds_f64x2(e1.y + goff1); }
-                    if (rem >= 3) { e2 = hl[nfull + gh2]; a2 = lds_f64x2((e2.x & 0x0FFFFFFFu) + goff2); b2 = lds_f64x2(e2.y + goff2); }
-                    if (anyneg) {
-                        const uint32_t t0 = ((e0.x >> 28) >> gc0) & 1u, t1 = ((e1.x >> 28) >> gc1) & 1u, t2 = ((e2.x >> 28) >> gc2) & 1u;
-                        a0.x = flip_sign(a0.x, t0); a0.y = flip_sign(a0.y, t0); a1.x = flip_sign(a1.x, t1); a1.y = flip_sign(a1.y, t1);
-                        a2.x = flip_sign(a2.x, t2); a2.y = flip_sign(a2.y, t2);
-                    }
-                    dmma884(acc[b][0], acc[b][1], a0.x, b0.x); dmma884(acc[b][2], acc[b][3], a0.x, b0.y);
-                    dmma884(acc[b][4], acc[b][5], a0.y, b0.x); dmma884(acc[b][6], acc[b][7], a0.y, b0.y);
-                    if (rem >= 2) {
-                        dmma884(acc[b][0], acc[b][1], a1.x, b1.x); dmma884(acc[b][2], acc[b][3], a1.x, b1.y);
-                        dmma884(acc[b][4], acc[b][5], a1.y, b1.x); dmma884(acc[b][6], acc[b][7], a1.y, b1.y);
-                    }
-                    if (rem >= 3) {
-                        dmma884(acc[b][0], acc[b][1], a2.x, b2.x); dmma884(acc[b][2], acc[b][3], a2.x, b2.y);
-                        dmma884(acc[b][4], acc[b][5], a2.y, b2.x); dmma884(acc[b][6], acc[b][7], a2.y, b2.y);
-                    }
-                }
-            }
-            __syncwarp();
+        const uint32_t zbase = smem_base + (uint32_t)sb * kStage;
+        const uint32_t ent_base = zbase + kZBytes, tab_base = ent_base + kEnt + (uint32_t)(warp * NB) * 4u, zs_addr = ent_base + kEnt + kTab;
+        uint32_t s0, s1;
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(s0), "=r"(s1) : "r"(zs_addr + 8u * (uint32_t)lane));
+        const bool anyneg = __any_sync(0xffffffffu, (s0 | s1) != 0u);
+        // table entry of a block: list offset | hits << 16 | diagonal-block flag << 31 (empty slots have no hits)
+#define ARGUS_SCHUR_TILE(SIGNED_)                                                                                                   \
+        _Pragma("unroll") for (int b = 0; b < NB; ++b) {                                                                            \
+            uint32_t tb;                                                                                                            \
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tb) : "r"(tab_base + 4u * (uint32_t)b));                                  \
+            const int n = (int)((tb >> 16) & 0x7FFFu);                                                                              \
+            if (n == 0) continue;                                                                                                   \
+            const uint32_t ent_addr = ent_base + 2u * (tb & 0xFFFFu);                                                               \
+            if (kSchurDiagPath && (tb >> 31)) schur_block<true, SIGNED_>(acc[b], ent_addr, n, zbase, off0, off1, off2, offk, kk, zs_addr); \
+            else schur_block<false, SIGNED_>(acc[b], ent_addr, n, zbase, off0, off1, off2, offk, kk, zs_addr);                      \
         }
+        if (anyneg) { ARGUS_SCHUR_TILE(true) } else { ARGUS_SCHUR_TILE(false) }
+#undef ARGUS_SCHUR_TILE
         __syncwarp();
         if (lane == 0) mbar_arrive(&mempty[sb]);       // this warp is done with the stage
     }

@@ -136,11 +136,13 @@ struct argus_ba_ctx {
     cudaEvent_t snap_ev[kSnap] = {};
     double *lmlog = nullptr;          // device, verbose > 1 only
     // tile / MMA plan
-    DevBuf<int32_t> tile_pt, tile_o; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign; DevBuf<double> Z;
-    DevBuf<uint8_t> obs_lpt, corder, pt_rank, vmask_dev; DevBuf<int32_t> idx_btot; int rank_mp = 16;
+    DevBuf<int32_t> tile_pt, tile_o, tile_r; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign, zs; DevBuf<double> Z;
+    DevBuf<uint8_t> obs_lpt, corder, row_obs, pt_slot0, vmask_dev; DevBuf<int32_t> idx_btot;
+    DevBuf<uint32_t> hit_tab; DevBuf<uint16_t> hit_ent; DevBuf<int32_t> hit_ptr;     // static hit lists of the Schur kernel
     DevBuf<uint8_t> cam_fix; bool cam_fix_on = false; DevBuf<uint16_t> cstart;
     int grid_lin = 1; size_t lin_smem = 0;
-    int ntiles = 0, tile_obs = 256, schur_G = 1, schur_NB = 1, schur_NW = 8, schur_nchunk = 1;
+    int64_t nrows = 0;                 // Z rows (>= nobs: a tile has 4 * max class fill rows)
+    int ntiles = 0, schur_G = 1, schur_NB = 1, schur_NW = 8, schur_nchunk = 1;
     Arena arena;
     int grid_pts128 = 1, grid_pts256 = 1, npairs = 1;
     // damping attempt as a CUDA graph (captured at the first solve after an upload)
@@ -155,14 +157,15 @@ struct argus_ba_ctx {
     double prof_ms[P_COUNT]; int64_t prof_n[P_COUNT];
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0, n_allreduce = 0;
 
-    TilePlan tile_plan() const { TilePlan tp; tp.ntiles = ntiles; tp.tile_obs = tile_obs; tp.tile_pt = tile_pt.p; tp.tile_o = tile_o.p; return tp; }
+    TilePlan tile_plan() const { TilePlan tp; tp.ntiles = ntiles; tp.tile_pt = tile_pt.p; tp.tile_o = tile_o.p; tp.tile_r = tile_r.p; return tp; }
     SchurPlan schur_plan() const {
-        SchurPlan sp; sp.G = schur_G; sp.nchunk = schur_nchunk; sp.npairs = npairs; sp.blk_jk = blk_jk.p; sp.blk_pair = blk_pair.p;
+        SchurPlan sp; sp.G = schur_G; sp.nchunk = schur_nchunk; sp.npairs = npairs; sp.nslots = schur_NW * schur_NB; sp.blk_jk = blk_jk.p;
+        sp.blk_pair = blk_pair.p; sp.hit_tab = hit_tab.p; sp.hit_ent = hit_ent.p; sp.hit_ptr = hit_ptr.p;
         return sp;
     }
-    LinTilePlan lin_plan() const { LinTilePlan lp; lp.obs_lpt = obs_lpt.p; lp.corder = corder.p; lp.cstart = cstart.p; return lp; }
+    LinTilePlan lin_plan() const { LinTilePlan lp; lp.obs_lpt = obs_lpt.p; lp.corder = corder.p; lp.cstart = cstart.p; lp.row_obs = row_obs.p; return lp; }
     LinTileOut lin_out() {
-        LinTileOut o; o.Z = Z.p; o.zsign = zsign.p; o.Vinv = Vinv.p; o.V = V.p; o.eb = eb.p; o.vstate = vstate.p; o.Upart = Upart2.p;
+        LinTileOut o; o.Z = Z.p; o.zs = zs.p; o.zsign = zsign.p; o.Vinv = Vinv.p; o.V = V.p; o.eb = eb.p; o.vstate = vstate.p; o.Upart = Upart2.p;
         o.scpart = scpart.p; o.flag = flags.p; return o;
     }
     ParamBufs pbufs() const { ParamBufs b; b.cam[0] = camb[0].p; b.cam[1] = camb[1].p; b.pts[0] = ptsb[0].p; b.pts[1] = ptsb[1].p; return b; }
@@ -310,9 +313,8 @@ int enqueue_attempt_motstr(argus_ba_ctx *c, bool controller, double *dbout)
     {
         ProfScope ps(c, P_SCHUR);
         dim3 grid(c->schur_nchunk, c->schur_G);
-        const size_t sm = (size_t)2 * ((size_t)c->tile_obs * 384 + 384 + (size_t)kTilePts * c->rank_mp) + 384;
-#define SCHUR_LAUNCH(NB_, NW_) k_schur_mma<NB_, NW_, 0><<<grid, (NW_) * 32, sm, s>>>(c->problem(), c->tile_plan(), c->schur_plan(), c->Z.p, \
-                                                                              c->zsign.p, c->pt_rank.p, c->rank_mp, c->Spart.p, done)
+#define SCHUR_LAUNCH(NB_, NW_) k_schur_mma<NB_, NW_><<<grid, (NW_) * 32, 2 * schur_stage_bytes((NB_) * (NW_)), s>>>(c->tile_plan(), c->schur_plan(), c->Z.p, \
+                                                                                                      c->zs.p, c->Spart.p, done)
         switch (c->schur_NB * 100 + c->schur_NW) {
             case 108: SCHUR_LAUNCH(1, 8); break;
             case 308: SCHUR_LAUNCH(3, 8); break;
@@ -485,14 +487,13 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
     {   // opt in to large dynamic shared memory: once per device and process, always to the worst case of each kernel
         std::lock_guard<std::mutex> lk(g_once_mutex);
         if (device < 64 && !(g_attr_done & (1ull << device))) {
-            const int smx = 2 * (256 * 384 + 384 + 32 * 64) + 384;
             const int lin_max = (int)((((size_t)ARGUS_BA_MAX_CAMS * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)256 * (kGa + kBs) * sizeof(double) +
                                       (size_t)kTilePts * kPs * sizeof(double));
             e = cudaFuncSetAttribute(k_chol_solve2, cudaFuncAttributeMaxDynamicSharedMemorySize, 214000);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<1, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<3, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<5, 8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<6, 12, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smx);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)schur_stage_bytes(8));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)schur_stage_bytes(24));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)schur_stage_bytes(40));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<6, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)schur_stage_bytes(72));
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
@@ -516,7 +517,8 @@ void argus_ba_destroy(argus_ba_ctx *c)
                               &c->dbuf, &c->scpart, &c->red12, &c->max2, &c->Spart, &c->S, &c->E, &c->da_free, &c->da_full, &c->part3, &c->att3,
                               &c->cam2, &c->scal, &c->respart, &c->Upart2, &c->cholwork, &c->Z};
     for (auto *b : bufs) b->release();
-    c->obs_lpt.release(); c->corder.release(); c->pt_rank.release(); c->cam_fix.release(); c->cstart.release(); c->vmask_dev.release();
+    c->obs_lpt.release(); c->corder.release(); c->row_obs.release(); c->pt_slot0.release(); c->tile_r.release(); c->zs.release();
+    c->hit_tab.release(); c->hit_ent.release(); c->hit_ptr.release(); c->cam_fix.release(); c->cstart.release(); c->vmask_dev.release();
     c->idx_btot.release(); c->flags.release(); c->tile_pt.release(); c->tile_o.release(); c->blk_jk.release(); c->blk_pair.release();
     c->zsign.release(); c->st.release();
     if (c->lmlog) cudaFree(c->lmlog);
@@ -604,24 +606,34 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     c->npairs = mf * (mf + 1) / 2;
     c->grid_pts128 = (int)std::min<int64_t>((n + 127) / 128, (int64_t)c->sms * 8); if (c->grid_pts128 < 1) c->grid_pts128 = 1;
     c->grid_pts256 = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sms * 8); if (c->grid_pts256 < 1) c->grid_pts256 = 1;
-    // ---- plans: point tiles (<= 32 points, <= tile_obs observations) and the block -> (group, warp, slot) map ----
-    std::vector<int32_t> tiles, tile_o;
-    c->tile_obs = 256;
-    int64_t nobs = 0;
+    // ---- plans: point tiles (<= 32 points; every point gets one of four classes, a class holds <= 64 observations per tile;
+    //      the observation of rank r of a point sits in Z row 4 (first index inside the class + r) + class, see ba_schur_mma.cuh)
+    //      and the block -> (group, warp, slot) map ----
+    std::vector<int32_t> tiles, tile_o, tile_r;
+    std::vector<uint8_t> slot0((size_t)n);
+    int64_t nobs = 0, nrows = 0, hits_bound = 0;
     {
         int64_t i = 0;
         while (i < n) {
-            tiles.push_back((int32_t)i); tile_o.push_back((int32_t)nobs);
-            int64_t e = i; int acc = 0;
-            while (e < n && e - i < kTilePts && acc + cnt[e] <= c->tile_obs) acc += cnt[e++];
-            if (e == i) acc = cnt[e++];
-            i = e; nobs += acc;
-            if (nobs > 0x7fffffffLL) return ARGUS_E_ARG;
+            tiles.push_back((int32_t)i); tile_o.push_back((int32_t)nobs); tile_r.push_back((int32_t)nrows);
+            int fill[4] = {0, 0, 0, 0}, npts = 0, acc = 0;
+            while (i < n && npts < kTilePts) {
+                const int v = cnt[i];
+                int cl = 0;
+                for (int q = 1; q < 4; ++q) if (fill[q] < fill[cl]) cl = q;        // emptiest class, lowest id on ties
+                if (fill[cl] + v > kClassCap) break;
+                slot0[i] = (uint8_t)(4 * fill[cl] + cl);
+                fill[cl] += v; acc += v; ++npts; ++i;
+                hits_bound += (int64_t)v * (v + 1) / 2;
+            }
+            nobs += acc;
+            nrows += 4 * std::max(std::max(fill[0], fill[1]), std::max(fill[2], fill[3]));
+            if (nrows > 0x7fffffffLL) return ARGUS_E_ARG;
         }
-        tiles.push_back((int32_t)n); tile_o.push_back((int32_t)nobs);
+        tiles.push_back((int32_t)n); tile_o.push_back((int32_t)nobs); tile_r.push_back((int32_t)nrows);
         c->ntiles = (int)tiles.size() - 1;
     }
-    c->nobs = nobs;
+    c->nobs = nobs; c->nrows = nrows;
     {
         const int cand[3] = {1, 3, 5};
         int NB = 6, NW = 12;
@@ -632,9 +644,8 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         if (nch > c->ntiles) nch = c->ntiles > 0 ? c->ntiles : 1;
         c->schur_nchunk = nch;
     }
-    c->rank_mp = (m + 15) & ~15;
-    // obs_lpt, corder, cstart and pt_rank are derived on the device from obs_ptr / obs_cam / tile_pt (k_index_*, k_build_tile_index)
-    c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)c->tile_obs * (kGa + kBs) * sizeof(double) +
+    // obs_lpt, corder, cstart, row_obs and the hit lists are derived on the device (k_index_*, k_build_tile_index, k_hits_*)
+    c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)kTileRows * (kGa + kBs) * sizeof(double) +
                   (size_t)kTilePts * kPs * sizeof(double);
     {
         int occ = (int)((220 * 1024) / (c->lin_smem + 1024)); if (occ < 1) occ = 1; if (occ > 2) occ = 2;
@@ -658,11 +669,16 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     auto plan = [&]() -> cudaError_t {
 #define PLAN_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 #define PLAN_ENS(buf, cnt_) PLAN_CHECK((buf).ensure((size_t)(cnt_)))
-        PLAN_ENS(c->tile_pt, tiles.size()); PLAN_ENS(c->tile_o, tiles.size()); PLAN_ENS(c->blk_jk, hjk.size()); PLAN_ENS(c->blk_pair, hpair.size());
-        PLAN_ENS(c->zsign, n); if (c->mode == kModeMotStr) { PLAN_ENS(c->Z, 48 * nobs); }
+        PLAN_ENS(c->tile_pt, tiles.size()); PLAN_ENS(c->tile_o, tiles.size()); PLAN_ENS(c->tile_r, tiles.size()); PLAN_ENS(c->blk_jk, hjk.size());
+        PLAN_ENS(c->blk_pair, hpair.size()); PLAN_ENS(c->pt_slot0, n); PLAN_ENS(c->row_obs, nrows); PLAN_ENS(c->zs, (size_t)c->ntiles * 256);
+        PLAN_ENS(c->zsign, n);
+        if (c->mode == kModeMotStr) {
+            PLAN_ENS(c->Z, 48 * nrows);
+            PLAN_ENS(c->hit_tab, (size_t)c->ntiles * hjk.size()); PLAN_ENS(c->hit_ptr, (size_t)c->ntiles * c->schur_G + 1);
+            PLAN_ENS(c->hit_ent, hits_bound + 8 * (int64_t)c->ntiles * c->schur_G + 8);
+        }
         PLAN_ENS(c->obs_lpt, nobs); PLAN_ENS(c->corder, nobs); PLAN_ENS(c->cstart, (size_t)c->ntiles * (m + 1));
         PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1024 + N + 32);
-        PLAN_ENS(c->pt_rank, c->mode == kModeMotStr ? (size_t)c->ntiles * kTilePts * c->rank_mp : 1);
         PLAN_ENS(c->vmask_dev, n * m); PLAN_ENS(c->idx_btot, (n + kIdxPts - 1) / kIdxPts + 1);
         PLAN_ENS(c->obs_ptr, n + 1); PLAN_ENS(c->obs_cam, nobs); PLAN_ENS(c->obs_uv, nobs); PLAN_ENS(c->pt_mask, n);
         PLAN_ENS(c->rot0, 4 * m); PLAN_ENS(c->camb[0], 16 * m); PLAN_ENS(c->camb[1], 16 * m); PLAN_ENS(c->cam0, 16 * m);
@@ -701,6 +717,8 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaMemsetAsync(c->st.p, 0, sizeof(LmState), s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_pt.p, tiles.data(), tiles.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_o.p, tile_o.data(), tile_o.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_r.p, tile_r.data(), tile_r.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (n > 0) ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pt_slot0.p, slot0.data(), (size_t)n, cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_jk.p, hjk.data(), hjk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_pair.p, hpair.data(), hpair.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->vmask_dev.p, vmask, (size_t)n * m, cudaMemcpyHostToDevice, s));
@@ -717,17 +735,24 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cam0.p, p, 16 * m * sizeof(double), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pts0.p, p + 16 * m, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
     // derived static indices, built on the device
-    if (n > 0) {
-        if (c->mode == kModeMotStr && c->ntiles > 0)
-            ARGUS_CUDA_CHECK(cudaMemsetAsync(c->pt_rank.p, 0xFF, (size_t)c->ntiles * kTilePts * c->rank_mp, s));
-        if (c->ntiles > 0)
-            k_build_tile_index<<<c->ntiles, 256, 0, s>>>(m, c->tile_pt.p, c->tile_o.p, c->obs_ptr.p, c->obs_cam.p, c->obs_lpt.p, c->corder.p,
-                                                         c->cstart.p, ncon, c->rank_mp, c->mode == kModeMotStr ? c->pt_rank.p : nullptr);
+    if (n > 0 && c->ntiles > 0) {
+        ARGUS_CUDA_CHECK(cudaMemsetAsync(c->row_obs.p, 0xFF, (size_t)nrows, s));
+        ARGUS_CUDA_CHECK(cudaMemsetAsync(c->zs.p, 0, (size_t)c->ntiles * 256, s));
+        k_build_tile_index<<<c->ntiles, 256, 0, s>>>(m, c->tile_pt.p, c->tile_o.p, c->tile_r.p, c->obs_ptr.p, c->obs_cam.p, c->pt_slot0.p,
+                                                     c->obs_lpt.p, c->corder.p, c->cstart.p, c->row_obs.p);
+        if (c->mode == kModeMotStr) {
+            const int G = c->schur_G, nslots = c->schur_NW * c->schur_NB, ntg = c->ntiles * G;
+            k_hits_count<<<c->ntiles, 256, (size_t)G * sizeof(int), s>>>(c->ntiles, G, nslots, c->tile_pt.p, ncon, c->pt_mask.p, c->pt_slot0.p,
+                                                                         c->blk_jk.p, c->hit_ptr.p);
+            k_index_scan<<<1, 1024, 0, s>>>(ntg, c->hit_ptr.p);
+            k_hits_fill<<<c->ntiles, 256, (size_t)G * nslots * sizeof(int), s>>>(c->ntiles, G, nslots, c->tile_pt.p, ncon, c->pt_mask.p,
+                                                                               c->pt_slot0.p, c->blk_jk.p, c->hit_ptr.p, c->hit_tab.p, c->hit_ent.p);
+        }
         ARGUS_CUDA_CHECK(cudaGetLastError());
     }
     ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));      // host staging vectors go out of scope
     c->h2d_bytes += (size_t)n * m + nobs * sizeof(double2) + (4 + 16) * m * sizeof(double) + 3 * n * sizeof(double) +
-                    2 * tiles.size() * sizeof(int32_t);
+                    3 * tiles.size() * sizeof(int32_t) + (size_t)n;
     return argus_ba_reset(c);
 }
 

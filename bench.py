@@ -5,12 +5,14 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
     python bench.py --impl reference ...      (the reference's own CPU implementation, oracle/_ref, on a bounded sample)
 
-Workload (BASELINE.json config 4 per GPU, weak scaling): 16 cameras, 2,000,000 points x 10 views = 20,000,000
-observations per rank, all 10 Argus intrinsics + pose free (nccalib = ncdist = 0), cameras shared by all ranks.
+Workload (BASELINE.json config 4): 16 cameras, 2,000,000 points x 10 views = 20,000,000 observations, all 10 Argus
+intrinsics + pose free (nccalib = ncdist = 0).  With N > 1 the points (and all their observations) of THAT scene are sharded
+over the ranks, balanced by observations, cameras replicated - the configuration as BASELINE.json words it ("sharded across
+2/4/8 B200"): strong scaling, the default.  `--scaling weak` gives every rank its own 20 M-observation scene instead.
 A "step" is one pass of the hot path over that batch: ITERS_PER_STEP (10) Levenberg-Marquardt iterations from the same
 perturbed start (stop tests disabled so every step does identical work; asserted).
-metric = observations x LM iterations per second, whole job (all ranks).  The reduced camera system and three
-scalars are all-reduced (NCCL) per iteration when N > 1; points/observations never move.
+metric = observations x LM iterations per second, whole job (all ranks).  Per damping attempt the ranks exchange one
+all-reduce of [U, ea, Schur sums, E] + two maxima and one of four scalars (NCCL, issued by the library itself).
 
 One JSON line on rank 0; see DESIGN.md for the roofline definitions.
 """
@@ -27,8 +29,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FP64_PEAK_TFLOPS = 37.1      # measured on this pool's B200 with tools/microbench/fp64_peak.cu (DMMA.8x8x4, sustained);
-                             # MEASURED_PEAKS.json has no fp64 entry - see profiles/r01_fp64_peak.txt
+FP64_PEAK_FALLBACK = 37.1    # only if the in-run measurement (argus_fp64_peak) fails: profiles/r01_fp64_peak.txt
 ITERS_PER_STEP = 10
 WORKLOADS = {
     # name: (cameras, points per rank, views per point, nccalib, ncdist)
@@ -107,6 +108,17 @@ def make_scene(workload, rank):
     return s, p0, rot0, (m, n, views, nk, nd)
 
 
+def measure_fp64_peak(device_index):
+    """fp64 throughput of this GPU, measured now (MEASURED_PEAKS.json has no fp64 entry): DMMA m8n8k4 and DFMA, TFLOP/s."""
+    import ctypes
+    from argus_gui_b200 import _lib
+    a, b = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    rc = _lib.load().argus_fp64_peak(int(device_index), 0.3, ctypes.byref(a), ctypes.byref(b))
+    if rc != 0 or a.value <= 0:
+        return FP64_PEAK_FALLBACK, FP64_PEAK_FALLBACK, "fallback constant (profiles/r01_fp64_peak.txt)"
+    return a.value, b.value, "measured in this run (argus_fp64_peak: mma.sync m8n8k4 f64 / DFMA loops, 0.3 s each)"
+
+
 def algorithmic_counts(vmask, m):
     """per LM iteration flops = nobs*(1025 + 90 + 1316) + 768 * sum_i v_i (v_i + 1) + Sdim^3/3,
     bytes = 40 nobs + 72 npts + 8 Sdim^2; the Schur kernel alone: 768 * sum_i v_i (v_i + 1) flops."""
@@ -150,7 +162,7 @@ def run_reference_arm(args, rank, world):
     value = nobs * ITERS_PER_STEP * args.steps / dt
     sample = "first %d points (%d observations) of the %s scene, %d cameras, %d LM iterations per step" % (vm.shape[0], nobs, args.workload, m, ITERS_PER_STEP)
     line = {"impl": "reference", "metric": "ba_observations_per_second", "value": value, "unit": "obs*iters/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: BA %d cameras, bounded sample" % (args.workload, m), "sample": sample, "iters_per_step": ITERS_PER_STEP},
             "cpu_baseline": {"value": value, "unit": "obs*iters/s", "cores": 1, "kind": kind, "sample": sample, "host_cores": os.cpu_count()},
@@ -246,7 +258,7 @@ def bench_pair(rank):
     return out
 
 
-def bench_dlt(torch, device, stream, steps, warmup, rank, world, hbm_peak):
+def bench_dlt(torch, device, stream, steps, warmup, rank, world, hbm_peak, dfma_peak):
     """BASELINE config 2 per rank: 1M frames x 4 cameras x 10 tracks; triangulation + reprojection error."""
     import ctypes
     from argus_gui_b200 import scenes, dlt as dlt_host, _lib
@@ -302,13 +314,17 @@ def bench_dlt(torch, device, stream, steps, warmup, rank, world, hbm_peak):
     out = {"workload": "c2: %d frames x %d cameras x %d tracks per rank" % (N, m, k), "points_per_sec": npts / (fused_ms * 1e-3),
            "points_per_sec_two_calls": npts / ((tri_ms + err_ms) * 1e-3),
            "ms_triangulate": tri_ms, "ms_reproj_error": err_ms, "ms_fused_reconstruct": fused_ms,
-           "roofline_fused": {"bound": "hbm", "achieved": fused_bytes / (fused_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                              "frac": fused_bytes / (fused_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                              "note": "fp64-instruction bound (ncu: fp64 pipe 71-77 % of peak, issue slots 63-65 %, DRAM 13-17 %: profiles/r01_final_ncu_full_dlt.txt): 5 undistortion iterations with a correctly rounded division each, no FMA contraction (bit-exact float32 output)"},
-           "roofline_triangulate": {"bound": "hbm", "achieved": tri_bytes / (tri_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                    "frac": tri_bytes / (tri_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
-           "roofline_reproj_error": {"bound": "hbm", "achieved": err_bytes / (err_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                     "frac": err_bytes / (err_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+           # about 900 fp64 operations per (frame, track) with 4 cameras: 4 x 5 undistortion iterations ~ 700, the (n+1)-row least
+           # squares ~ 110, the reprojection ~ 90; ncu: fp64 pipe 71-77 % busy, DRAM 13-17 % (profiles/r01_final_ncu_full_dlt.txt)
+           "roofline_fused": {"bound": "fp64", "achieved": 900.0 * npts / (fused_ms * 1e-3) / 1e12, "peak": dfma_peak, "unit": "TFLOP/s",
+                              "frac": 900.0 * npts / (fused_ms * 1e-3) / 1e12 / dfma_peak, "traffic": None,
+                              "hbm_frac": fused_bytes / (fused_ms * 1e-3) / 1e9 / hbm_peak,
+                              "note": "fp64-instruction bound: the executed instruction stream keeps the fp64 pipe 71-77 % busy (ncu), about 4x the algorithmic count above - "
+                                      "5 undistortion iterations with a correctly rounded division each and no FMA contraction, the price of bit-exact float32 output"},
+           "roofline_triangulate": {"bound": "fp64", "achieved": 810.0 * npts / (tri_ms * 1e-3) / 1e12, "peak": dfma_peak, "unit": "TFLOP/s",
+                                    "frac": 810.0 * npts / (tri_ms * 1e-3) / 1e12 / dfma_peak, "hbm_frac": tri_bytes / (tri_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
+           "roofline_reproj_error": {"bound": "fp64", "achieved": 790.0 * npts / (err_ms * 1e-3) / 1e12, "peak": dfma_peak, "unit": "TFLOP/s",
+                                     "frac": 790.0 * npts / (err_ms * 1e-3) / 1e12 / dfma_peak, "hbm_frac": err_bytes / (err_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None},
            "e2e": {"value": npts / e2e_s, "unit": "points/s", "h2d_bytes_per_step": int(d["pts"].nbytes), "d2h_bytes_per_step": int(xyz.nbytes + err.nbytes)},
            "gpu_launches": 3 * steps}
     # bootstrap confidence intervals (bootstrapXYZs: 250 perturbed re-triangulations per point), host API, 100k frames
@@ -333,6 +349,117 @@ def bench_dlt(torch, device, stream, steps, warmup, rank, world, hbm_peak):
     return out
 
 
+def bench_extras(torch, ba, local, stream, args, dmma_peak):
+    """BASELINE.json's other named configurations and the reference's own known-answer run, N = 1, rank 0 (short runs beside
+    the headline): c1 through the wand driver with the reference's C code timed on the same sba inputs, c3, c5 (device timed,
+    10 LM iterations per step) and sba-1.6p/demo's 54camsvarKD data set (published: 34 iterations, error 0.128779, 55.17 s)."""
+    import contextlib
+    import io
+    import tempfile
+    from argus_gui_b200 import scenes, sbaDriver, sba
+    from oracle import sba_ref
+    out = {}
+    # ---- c1: 3-camera wand calibration through sbaArgusDriver.fix() (what Argus users run) ----
+    w = scenes.make_wand_scene(nframes=2000, nbackground=100, m=3, seed=1)
+    tmp = tempfile.mkdtemp()
+    sink = io.StringIO()
+    runs = []
+    for rep in range(3):
+        with contextlib.redirect_stdout(sink):
+            t0 = time.perf_counter()
+            d = sbaDriver.sbaArgusDriver(w["ppts"].copy(), w["uppts"].copy(), w["cams"].copy(), display=False, scale=0.5, modeString="01",
+                                         name=os.path.join(tmp, "c1"), temp=tmp, report=False)
+            t1 = time.perf_counter()
+            res = d.fix()
+            t2 = time.perf_counter()
+        runs.append((t1 - t0, t2 - t1))
+    points = sba.Points.fromDylan(d.pts); cameras = sba.Cameras.fromDylan(np.hstack((d.cams, d.ext)))
+    a, r0 = cameras.pack()
+    p_sba = np.concatenate([a.ravel(), points.B.ravel()])
+    nobs1 = int(points.vmask.sum())
+    with torch.cuda.stream(stream):
+        B = ba.BundleAdjuster(device=local, stream=stream.cuda_stream)
+        B.upload(points.vmask, p_sba, r0.ravel(), points.X, 5, 4)
+        for _ in range(3):
+            B.reset(); B.solve(itmax=150)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(10):
+            B.reset(); ret1, info1 = B.solve(itmax=150)
+        torch.cuda.synchronize(); res_ms = 1e3 * (time.perf_counter() - t0) / 10
+        B.close()
+    t0 = time.perf_counter(); ba.solve_motstr(points.vmask, p_sba, r0.ravel(), points.X, 5, 4, itmax=150); one_ms = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter(); ba.solve_motstr(points.vmask, p_sba, r0.ravel(), points.X, 5, 4, itmax=150); one_ms = min(one_ms, 1e3 * (time.perf_counter() - t0))
+    c1 = {"workload": "c1: 3 cameras, 2000 wand frames + 100 background points -> %d points, %d observations, mode '01'" % (d.pts.shape[0], nobs1),
+          "driver_ms": {"constructor (parse + CUDA two-view initialisation)": 1e3 * min(r[0] for r in runs), "fix() (BA + DLT fits + files)": 1e3 * min(r[1] for r in runs)},
+          "ba_iterations": int(ret1), "ba_resident_ms": res_ms, "ba_ms_per_iteration": res_ms / max(int(ret1), 1), "ba_one_shot_call_ms": one_ms,
+          "wand_score": float(res.wandscore), "dlt_rmse": [float(v) for v in res.dlterrors]}
+    if sba_ref.available():
+        t0 = time.perf_counter(); pr, ir, rr = sba_ref.ref_motstr(p_sba, points.X, points.vmask, r0.ravel(), 5, 4, itmax=150); dt = time.perf_counter() - t0
+        c1["cpu_baseline"] = {"value": 1e3 * dt, "unit": "ms for the same bundle adjustment (%d iterations)" % rr, "cores": 1, "kind": "reference",
+                              "sample": "the whole problem (sba_motstr_levmar_x + img_projsKDRTS_x/_jac_x on the same arrays)"}
+        c1["final_cost_rel_diff_vs_reference"] = abs(info1[1] - ir[1]) / ir[1]
+    out["c1"] = c1
+
+    # ---- c3 / c5: device-timed, ITERS_PER_STEP iterations per step ----
+    for wl in (["c3"] + ([] if args.no_c5 else ["c5"])):
+        s, p0, rot0, (m, n, views, nk, nd) = make_scene(wl, 0)
+        cnt = algorithmic_counts(s["vmask"], m)
+        with torch.cuda.stream(stream):
+            B = ba.BundleAdjuster(device=local, stream=stream.cuda_stream)
+            B.upload(s["vmask"], p0, rot0, s["x"], nk, nd)
+            if wl == "c5":
+                B.set_camera_fix([5] * 16 + [0] * 16, [5] * 16 + [0] * 16)
+            for _ in range(2):
+                B.reset(); B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+            steps = 3
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            prof = {}
+            e0.record(stream)
+            for _ in range(steps):
+                B.reset(); ret, info = B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK, profile=True)
+                assert ret == ITERS_PER_STEP, (wl, ret, info)
+                for kname, (ms, c_) in B.profile().items():
+                    q = prof.setdefault(kname, [0.0, 0]); q[0] += ms; q[1] += c_
+            e1.record(stream); e1.synchronize()
+            ms_it = e0.elapsed_time(e1) / (steps * ITERS_PER_STEP)
+            B.close()
+        sch = prof["schur"][0] / max(prof["schur"][1], 1)
+        r = {"workload": "%s: %d cameras, %d points x %d views = %d observations%s" % (wl, m, n, views, s["nobs"],
+                         ", cameras 0-15 fixed intrinsics / 16-31 free, 10 %% outlier tracks" if wl == "c5" else ""),
+             "value": s["nobs"] / (ms_it * 1e-3), "unit": "obs*iters/s", "ms_per_iteration": ms_it,
+             "kernels_ms_per_iteration": {k_: v[0] / (steps * ITERS_PER_STEP) for k_, v in sorted(prof.items()) if v[1]},
+             "schur": {"ms_per_launch": sch, "tflops": cnt["schur_flops"] / (sch * 1e-3) / 1e12, "frac_of_fp64_peak": cnt["schur_flops"] / (sch * 1e-3) / 1e12 / dmma_peak},
+             "iteration_fp64_frac": cnt["flops_iter"] / (ms_it * 1e-3) / 1e12 / dmma_peak}
+        if sba_ref.available() and wl == "c3":
+            vm, xs, ps = reference_sample(s, p0, m, 16384)
+            t0 = time.perf_counter(); _, iref, _ = sba_ref.ref_motstr(ps, xs, vm, rot0, nk, nd, itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK); dt = time.perf_counter() - t0
+            r["cpu_baseline"] = {"value": int(vm.sum()) * int(iref[5]) / dt, "unit": "obs*iters/s", "cores": 1, "kind": "reference",
+                                 "sample": "first %d points (%d observations) of the same scene, %d LM iterations, %.1f s" % (vm.shape[0], int(vm.sum()), int(iref[5]), dt)}
+        if wl == "c5":
+            r["cpu_baseline"] = {"value": None, "kind": "reference", "sample": "not runnable: the reference indexes its Jacobian buffer with a 32-bit int (sba_levmar.c:676), "
+                                 "60 M observations overflow it, and it has no per-camera fixed / free masks"}
+        out[wl] = r
+        del s, p0
+
+    # ---- the reference's own largest known-answer run: demo/54camsvarKD.txt + 54pts.txt (README.txt:197-206) ----
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    if helpers.have_demo():
+        cams, pts, vmask, x = helpers.load_demo("54camsvarKD.txt", "54pts.txt")
+        p0, rot0 = scenes.pack_ba_problem(cams, pts)
+        ba.solve_motstr(vmask, p0, rot0, x, 2, 3, itmax=150)
+        t0 = time.perf_counter(); pg, ig, rg = ba.solve_motstr(vmask, p0, rot0, x, 2, 3, itmax=150); dtg = time.perf_counter() - t0
+        k = {"workload": "sba-1.6p/demo 54camsvarKD: 54 cameras, 5207 points, 24609 projections, 16485 variables",
+             "published": {"iterations": 34, "final_error": 0.128779, "elapsed_s": 55.17, "source": "sba-1.6p/demo/README.txt:197-206 (hardware not stated)"},
+             "gpu": {"iterations": int(rg), "stop_reason": int(ig[6]), "final_error": float(ig[1] / x.shape[0]), "one_shot_call_s": dtg}}
+        if sba_ref.available():
+            t0 = time.perf_counter(); pr, ir, rr = sba_ref.ref_motstr(p0, x, vmask, rot0, 2, 3, itmax=150); dtr = time.perf_counter() - t0
+            k["cpu_baseline"] = {"value": dtr, "unit": "s", "cores": 1, "kind": "reference", "iterations": int(rr), "final_error": float(ir[1] / x.shape[0]),
+                                 "sample": "the whole problem, the reference's own compiled code on this host"}
+        out["demo_54camsvarKD"] = k
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -340,11 +467,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = the ONE scene of the workload sharded over the ranks (BASELINE.json config 4 as written); weak = one scene per rank")
     ap.add_argument("--ref-points", type=int, default=4096, help="points in the bounded CPU sample")
     ap.add_argument("--cpu-baseline-points", type=int, default=32768)
     ap.add_argument("--no-dlt", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-blockdiag", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c1 / c3 / c5 / 54camsvarKD section (N = 1)")
+    ap.add_argument("--no-c5", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -364,22 +495,34 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     hbm_peak, hbm_src = measured_peaks()
+    dmma_peak, dfma_peak, fp64_src = measure_fp64_peak(local)
     stream = torch.cuda.Stream(device=device)
 
-    s, p0, rot0, (m, n, views, nk, nd) = make_scene(args.workload, rank)
-    counts = algorithmic_counts(s["vmask"], m)
-    nobs_local = s["nobs"]
+    strong = args.scaling == "strong"
+    s, p0, rot0, (m, n, views, nk, nd) = make_scene(args.workload, 0 if strong else rank)
+    counts = algorithmic_counts(s["vmask"], m)              # of the whole scene (strong) / of this rank's scene (weak)
+    if strong and world > 1:
+        vm_l, p_l, x_l, (lo, hi) = ba.shard_problem(s["vmask"], p0, s["x"], m, world, rank, balance_observations=True)
+        vm_l = np.ascontiguousarray(vm_l); p_l = np.ascontiguousarray(p_l); x_l = np.ascontiguousarray(x_l)
+    else:
+        vm_l, p_l, x_l = s["vmask"], p0, s["x"]
+    n_l = vm_l.shape[0]
+    nobs_local = int(np.count_nonzero(vm_l))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.cuda.stream(stream):
-        B = ba.BundleAdjuster(device=local, stream=stream.cuda_stream)
+    def new_adjuster():
+        B_ = ba.BundleAdjuster(device=local, stream=stream.cuda_stream)
         if world > 1:
-            B.init_nccl(rank, world)
-        B.upload(s["vmask"], p0, rot0, s["x"], nk, nd)
+            B_.init_nccl(rank, world)
+        return B_
+
+    with torch.cuda.stream(stream):
+        B = new_adjuster()
+        B.upload(vm_l, p_l, rot0, x_l, nk, nd)
         if args.workload == "c5":
             B.set_camera_fix([5] * 16 + [0] * 16, [5] * 16 + [0] * 16)
         for _ in range(args.warmup):
@@ -401,17 +544,27 @@ def main():
         clocks = sampler.stop()
         ms_total = e0.elapsed_time(e1)
         c1 = B.counters()
+        # the same steps replayed as CUDA graphs (no per-kernel events): what a resident user gets
+        barrier()
+        g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+        B.reset(); B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+        g0.record(stream)
+        for _ in range(args.steps):
+            B.reset(); ret, info_g = B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+        g1.record(stream)
+        barrier()
+        ms_graph = g0.elapsed_time(g1)
         # time to convergence with the reference's default options, outside the timed region
         B.reset(); torch.cuda.synchronize()
         tc0 = time.perf_counter()
         retc, infoc = B.solve(itmax=150)
         conv = {"iterations": int(infoc[5]), "stop_reason": int(infoc[6]), "ms": 1e3 * (time.perf_counter() - tc0),
                 "initial_cost": float(infoc[0]), "final_cost": float(infoc[1]), "opts": "default (1e-3, 1e-12, 1e-12, 1e-12, 0), itmax 150"}
-    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    t_ms = torch.tensor([ms_total, ms_graph], dtype=torch.float64, device=device)
     tot_obs = torch.tensor([float(nobs_local)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX); dist.all_reduce(tot_obs, op=dist.ReduceOp.SUM)
-    ms_total = float(t_ms.item()); total_obs = float(tot_obs.item())
+    ms_total = float(t_ms[0].item()); ms_graph = float(t_ms[1].item()); total_obs = float(tot_obs.item())
     value = total_obs * ITERS_PER_STEP * args.steps / (ms_total * 1e-3)
     final_cost = float(info[1])
 
@@ -419,9 +572,9 @@ def main():
     e2e = None
     if not args.no_e2e:
         n_e2e = max(1, min(args.steps, 3))
-        hps = [torch.from_numpy(p0.copy()).pin_memory().numpy() for _ in range(n_e2e)]      # p is in/out: one pinned copy per step
-        hx = torch.from_numpy(np.ascontiguousarray(s["x"])).pin_memory().numpy()
-        hv = torch.from_numpy(np.ascontiguousarray(s["vmask"]).view(np.int8)).pin_memory().numpy()
+        hps = [torch.from_numpy(p_l.copy()).pin_memory().numpy() for _ in range(n_e2e)]      # p is in/out: one pinned copy per step
+        hx = torch.from_numpy(np.ascontiguousarray(x_l)).pin_memory().numpy()
+        hv = torch.from_numpy(np.ascontiguousarray(vm_l).view(np.int8)).pin_memory().numpy()
         barrier()
         t0 = time.perf_counter()
         for hp in hps:
@@ -429,47 +582,54 @@ def main():
                 pe, ie, re_ = ba.solve_motstr(hv, hp, rot0, hx, nk, nd, itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK, inplace=True)
             else:
                 with torch.cuda.stream(stream):
-                    Be = ba.BundleAdjuster(device=local, stream=stream.cuda_stream)
-                    Be.init_nccl(rank, world)
+                    Be = new_adjuster()
+                    Be.set_graph(False)
                     Be.upload(hv, hp, rot0, hx, nk, nd)
                     re_, ie = Be.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
-                    pe = Be.download(); Be.close()
+                    Be.download(out=hp); Be.close()
             assert re_ == ITERS_PER_STEP
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        per_step_h2d = int((c1["h2d_bytes"]) / 1)      # bytes of one upload (counted by the library from the arrays it copies)
+        per_step_h2d = int(hv.nbytes + hx.nbytes + 8 * (16 * m + 3 * n_l) + 8 * 4 * m)
         e2e = {"value": total_obs * ITERS_PER_STEP * n_e2e / float(dt.item()), "unit": "obs*iters/s",
-               "h2d_bytes_per_step": per_step_h2d, "d2h_bytes_per_step": int(8 * (16 * m + 3 * n)), "steps": n_e2e,
-               "api": "argus_ba_motstr_kdrts (host pointers: alloc + index build + H2D + %d LM iterations + D2H)" % ITERS_PER_STEP}
+               "h2d_bytes_per_step": per_step_h2d, "d2h_bytes_per_step": int(8 * (16 * m + 3 * n_l)), "steps": n_e2e,
+               "bytes": "per rank", "api": "argus_ba_motstr_kdrts (host pointers: alloc + index build + H2D + %d LM iterations + D2H)" % ITERS_PER_STEP
+               if world == 1 else "argus_ba_create + comm_init_nccl + upload + solve + download + destroy per step, pinned host buffers"}
 
     # ---- roofline of the dominant kernel (CUDA events on the launching stream, inside the timed region) ----
     kern = {k_: v for k_, v in prof.items() if v[1] > 0 and k_ != "allreduce"}
     dom = max(kern, key=lambda k_: kern[k_][0])
     dom_ms = kern[dom][0] / kern[dom][1]
     sum_ms = sum(v[0] for v in kern.values())
+    v_l = vm_l.sum(axis=1).astype(np.float64)
+    schur_flops_local = 768.0 * float((v_l * (v_l + 1.0)).sum())
     if dom == "schur":
-        rl = {"kernel": dom, "bound": "tensor", "achieved": counts["schur_flops"] / (dom_ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS,
-              "unit": "TFLOP/s", "peak_source": "fp64 DMMA/DFMA peak measured with tools/microbench/fp64_peak.cu (profiles/r01_fp64_peak.txt)"}
+        rl = {"kernel": dom, "bound": "tensor", "achieved": schur_flops_local / (dom_ms * 1e-3) / 1e12, "peak": dmma_peak,
+              "unit": "TFLOP/s", "peak_source": "fp64 tensor pipe (DMMA m8n8k4), " + fp64_src}
     else:
-        per = {"linearize": 40.0 * counts["nobs"] + 72.0 * n, "backsub_eval": 40.0 * counts["nobs"] + 72.0 * n}.get(dom, 40.0 * counts["nobs"])
+        per = {"linearize": 40.0 * nobs_local + 72.0 * n_l, "backsub_eval": 40.0 * nobs_local + 72.0 * n_l}.get(dom, 40.0 * nobs_local)
         rl = {"kernel": dom, "bound": "hbm", "achieved": per / (dom_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src}
     rl["frac"] = rl["achieved"] / rl["peak"]
     rl["traffic"] = None
     try:        # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture of the same command
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        if tr.get("workload") == args.workload and dom in tr:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        if tr.get("workload") == args.workload and world == 1 and dom in tr:
             rl["traffic"] = tr[dom]; rl["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
     except Exception:
         pass
     rl["ms_per_launch"] = dom_ms
     rl["share_of_kernel_time"] = kern[dom][0] / sum_ms
     t_iter = ms_total * 1e-3 / (ITERS_PER_STEP * args.steps)
-    rl["iteration"] = {"ms": t_iter * 1e3, "fp64_frac": counts["flops_iter"] / t_iter / 1e12 / FP64_PEAK_TFLOPS,
-                       "hbm_frac": counts["bytes_iter"] / t_iter / 1e9 / hbm_peak,
-                       "algorithmic_gflop": counts["flops_iter"] / 1e9, "algorithmic_gbyte": counts["bytes_iter"] / 1e9}
+    flops_iter_job = counts["flops_iter"] * (1 if strong else world)
+    bytes_iter_job = counts["bytes_iter"] * (1 if strong else world)
+    rl["iteration"] = {"ms": t_iter * 1e3, "fp64_frac": flops_iter_job / t_iter / 1e12 / (dmma_peak * world),
+                       "hbm_frac": bytes_iter_job / t_iter / 1e9 / (hbm_peak * world),
+                       "algorithmic_gflop": flops_iter_job / 1e9, "algorithmic_gbyte": bytes_iter_job / 1e9,
+                       "ms_graph_replay": ms_graph / (ITERS_PER_STEP * args.steps)}
     rl["kernels_ms_per_iteration"] = {k_: v[0] / (ITERS_PER_STEP * args.steps) for k_, v in sorted(prof.items())}
+    rl["fp64_peaks_tflops"] = {"dmma_m8n8k4": dmma_peak, "dfma": dfma_peak, "source": fp64_src}
 
     # ---- CPU baseline: the reference's own C code on the host cores of this box (rank 0, N = 1) ----
     cpu = None
@@ -492,27 +652,38 @@ def main():
         bd_res = bench_blockdiag(torch, ba, stream, local, s, p0, rot0, m, nk, nd, max(2, min(args.steps, 5)),
                                  args.cpu_baseline_points if (rank == 0 and world == 1) else 0)
     pair_res = bench_pair(rank) if (not args.no_blockdiag and world == 1) else None
+    del s
+    extras = None
+    if world == 1 and rank == 0 and not args.no_extras:
+        extras = bench_extras(torch, ba, local, stream, args, dmma_peak)
     dlt_res = None
     if not args.no_dlt:
-        dlt_res = bench_dlt(torch, device, stream, max(3, min(args.steps, 10)), 3, rank, world, hbm_peak)
+        dlt_res = bench_dlt(torch, device, stream, max(3, min(args.steps, 10)), 3, rank, world, hbm_peak, dfma_peak)
         if world > 1:
             v = torch.tensor([dlt_res["points_per_sec"]], dtype=torch.float64, device=device)
             dist.all_reduce(v, op=dist.ReduceOp.SUM)
             dlt_res["points_per_sec"] = float(v.item())
 
     if rank == 0:
+        if strong:
+            wl = "%s: BA %d cameras, %d points x %d views = %d observations%s, 16 free parameters per camera" % (
+                args.workload, m, n, views, int(total_obs), (" sharded over %d GPUs (balanced by observations)" % world) if world > 1 else "")
+        else:
+            wl = "%s: BA %d cameras, %d points x %d views = %d observations per GPU, 16 free parameters per camera" % (args.workload, m, n, views, nobs_local)
         line = {"metric": "ba_observations_per_second", "value": value, "unit": "obs*iters/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "%s: BA %d cameras, %d points x %d views = %d observations per GPU, 16 free parameters per camera"
-                                       % (args.workload, m, n, views, nobs_local),
+                "config": {"workload": wl,
                            "iters_per_step": ITERS_PER_STEP, "parallelism": "points sharded x%d, cameras replicated" % world,
-                           "l2": "inputs larger than L2 (>= %.1f GB of per-observation blocks per pass)" % (nobs_local * 48 * 8 / 1e9),
+                           "l2": "inputs larger than L2 (>= %.1f GB of per-observation blocks per pass and rank)" % (nobs_local * 48 * 8 / 1e9),
                            "final_cost": final_cost},
                 "convergence": conv,
                 "lm_iters_per_sec": ITERS_PER_STEP * args.steps / (ms_total * 1e-3),
+                "graph_replay": {"value": total_obs * ITERS_PER_STEP * args.steps / (ms_graph * 1e-3), "unit": "obs*iters/s",
+                                 "note": "same steps, every damping attempt one CUDA graph launch, no per-kernel events"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(c1["launches"] - c0["launches"]),
-                "allreduces": int(c1["allreduces"] - c0["allreduces"]), "roofline": rl, "cpu_baseline": cpu, "blockdiag": bd_res, "pair_init": pair_res, "dlt": dlt_res}
+                "allreduces": int(c1["allreduces"] - c0["allreduces"]), "roofline": rl, "cpu_baseline": cpu, "blockdiag": bd_res, "pair_init": pair_res,
+                "configs": extras, "dlt": dlt_res}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -183,6 +183,10 @@ int  argus_dlt_reproj_error_dev(const double *d_xyz, const double *d_pts, int64_
 
 const char *argus_b200_version(void);
 
+/* Measured fp64 throughput of `device` in TFLOP/s (2 flop per FMA): mma.sync m8n8k4 f64 (the tensor-pipe form the Schur
+ * kernel uses) and plain DFMA, each run back to back for about `seconds`.  bench.py's roofline denominators. */
+int argus_fp64_peak(int device, double seconds, double *dmma_tflops, double *dfma_tflops);
+
 /* ---- two-view initialisation (what feeds the bundle adjustment) ----
  * One camera paired with the reference camera: Triangulator(p1, p2, f1, f2, c1, c2, dist1, dist2).triangulate() of
  * argus_gui/triangulate.py:27-212 as one call.  p1 / p2: N x 2 pixel coordinates in camera k / in the reference camera (N >= 8,

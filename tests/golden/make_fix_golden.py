@@ -48,6 +48,15 @@ CASES = [("noref", None, "Axis points", "01"), ("axis1", "axis1", "Axis points",
          ("plane", "plane", "Plane", "10")]
 out = {"cases": np.array([c[0] for c in CASES])}
 tmp = tempfile.mkdtemp()
+# remember the info vector of the bundle adjustment the reference driver runs (it is a local of fix())
+from argus_gui_b200 import sba as _sba
+_last = {}
+_orig_sba = _sba.SparseBundleAdjust
+def _capture(cameras, points, options):
+    r = _orig_sba(cameras, points, options)
+    _last["info"] = np.array(r[2].info)
+    return r
+_sba.SparseBundleAdjust = _capture
 for name, kind, rtype, mode in CASES:
     rng = np.random.default_rng(100 + len(name))
     w = scenes.make_wand_scene(nframes=260, nbackground=40, m=3 if name != "plane" else 4, seed=11 + len(name))
@@ -61,7 +70,7 @@ for name, kind, rtype, mode in CASES:
     d.fix()
     g = d.grapher
     o = {"ppts": w["ppts"], "uppts": w["uppts"], "cams": w["cams"], "mode": np.array(mode), "rtype": np.array(rtype), "order": np.asarray(d.order),
-         "pts": d.pts, "ext": d.ext, "newcams": np.loadtxt(os.path.join(tmp, g.key + "_cn.txt")), "newpts": np.loadtxt(os.path.join(tmp, g.key + "_np.txt")),
+         "pts": d.pts, "ext": d.ext, "info": _last["info"], "newcams": np.loadtxt(os.path.join(tmp, g.key + "_cn.txt")), "newpts": np.loadtxt(os.path.join(tmp, g.key + "_np.txt")),
          "xyzs": g.xyzs, "dlts": np.asarray(g.dlts)[:, :, 0], "dlterrors": g.dlterrors, "wandscore": np.array(float(g.wandscore)),
          "outlier_index": np.array(sorted(set(g.index))), "outlier_frames": np.array([q["frame"] for q in g.outliers]),
          "outlier_cams": np.array([q["camera"] for q in g.outliers]), "outlier_err": np.array([q["error"] for q in g.outliers]),
