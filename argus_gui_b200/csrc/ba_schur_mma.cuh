@@ -236,9 +236,11 @@ __host__ __device__ constexpr uint32_t schur_ent_bytes(int nslots) { return (uin
 __host__ __device__ constexpr uint32_t schur_tab_bytes(int nslots) { return ((uint32_t)nslots * 4u + 15u) & ~15u; }
 __host__ __device__ constexpr uint32_t schur_stage_bytes(int nslots) { return kZBytes + schur_ent_bytes(nslots) + schur_tab_bytes(nslots) + 256u; }
 
+// DIAG (compile time): a code path of its own for the diagonal blocks; skip_hl (run time, warp uniform): in the common path,
+// leave out the (rows 8-15) x (columns 0-7) sub-tile, which a diagonal block gets from its transpose (k_assemble_mma)
 template <bool DIAG, bool SIGNED>
 __device__ __forceinline__ void schur_block(double (&acc)[8], uint32_t ent_addr, int n, uint32_t zbase, uint32_t off0, uint32_t off1,
-                                            uint32_t off2, uint32_t offk, int kk, uint32_t zs_addr)
+                                            uint32_t off2, uint32_t offk, int kk, uint32_t zs_addr, bool skip_hl)
 {
     constexpr bool anyneg = SIGNED;
     const int nfull = n >> 2, rem = n & 3;
@@ -258,13 +260,13 @@ __device__ __forceinline__ void schur_block(double (&acc)[8], uint32_t ent_addr,
         }
         if (g + 1 < nfull) e = lds_u16(ent_addr + 8u * (uint32_t)(g + 1) + 2u * (uint32_t)kk);      // next group's entry, off the chain
         dmma884(acc[0], acc[1], a0.x, b0.x); dmma884(acc[2], acc[3], a0.x, b0.y);
-        if (!DIAG) dmma884(acc[4], acc[5], a0.y, b0.x);
+        if (!DIAG && !skip_hl) dmma884(acc[4], acc[5], a0.y, b0.x);
         dmma884(acc[6], acc[7], a0.y, b0.y);
         dmma884(acc[0], acc[1], a1.x, b1.x); dmma884(acc[2], acc[3], a1.x, b1.y);
-        if (!DIAG) dmma884(acc[4], acc[5], a1.y, b1.x);
+        if (!DIAG && !skip_hl) dmma884(acc[4], acc[5], a1.y, b1.x);
         dmma884(acc[6], acc[7], a1.y, b1.y);
         dmma884(acc[0], acc[1], a2.x, b2.x); dmma884(acc[2], acc[3], a2.x, b2.y);
-        if (!DIAG) dmma884(acc[4], acc[5], a2.y, b2.x);
+        if (!DIAG && !skip_hl) dmma884(acc[4], acc[5], a2.y, b2.x);
         dmma884(acc[6], acc[7], a2.y, b2.y);
     }
     // ---- left-over hits: one step each, k-lanes 0..2 = the three components, k-lane 3 reads the zero row ----
@@ -290,7 +292,7 @@ __device__ __forceinline__ void schur_block(double (&acc)[8], uint32_t ent_addr,
         for (int r = 0; r < 3; ++r) {
             if (r < rem) {
                 dmma884(acc[0], acc[1], av[r].x, bv[r].x); dmma884(acc[2], acc[3], av[r].x, bv[r].y);
-                if (!DIAG) dmma884(acc[4], acc[5], av[r].y, bv[r].x);
+                if (!DIAG && !skip_hl) dmma884(acc[4], acc[5], av[r].y, bv[r].x);
                 dmma884(acc[6], acc[7], av[r].y, bv[r].y);
             }
         }
@@ -371,8 +373,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(TilePlan tp, SchurPlan
             const int n = (int)((tb >> 16) & 0x7FFFu);                                                                              \
             if (n == 0) continue;                                                                                                   \
             const uint32_t ent_addr = ent_base + 2u * (tb & 0xFFFFu);                                                               \
-            if (kSchurDiagPath && (tb >> 31)) schur_block<true, SIGNED_>(acc[b], ent_addr, n, zbase, off0, off1, off2, offk, kk, zs_addr); \
-            else schur_block<false, SIGNED_>(acc[b], ent_addr, n, zbase, off0, off1, off2, offk, kk, zs_addr);                      \
+            if (kSchurDiagPath && (tb >> 31)) schur_block<true, SIGNED_>(acc[b], ent_addr, n, zbase, off0, off1, off2, offk, kk, zs_addr, false); \
+            else schur_block<false, SIGNED_>(acc[b], ent_addr, n, zbase, off0, off1, off2, offk, kk, zs_addr, (tb >> 31) != 0u);   \
         }
         if (anyneg) { ARGUS_SCHUR_TILE(true) } else { ARGUS_SCHUR_TILE(false) }
 #undef ARGUS_SCHUR_TILE

@@ -55,7 +55,7 @@ def test_converged_parameters_within_1e6_of_the_reference(shape):
     (pr, ir, rr), (pg, ig, rg) = _both(s, nk, nd, itmax=150, mcon=1, ncon=1)
     print("reference", list(ir[5:]), ir[1], "gpu", list(ig[5:]), ig[1])
     assert rr > 0 and rg > 0 and int(ir[6]) in (2, 4) and int(ig[6]) in (2, 4)          # both converged (small step / stagnation)
-    assert abs(ir[1] - ig[1]) <= 1e-9 * ir[1]                                            # final cost
+    assert abs(ir[1] - ig[1]) <= 1e-8 * ir[1]                                            # final cost, each solver at its own stop (the reference against itself with another BLAS thread count: 1.8e-9)
     if rr != rg:
         # stop reason 4 cannot be switched off and, with eps4 = 0, fires on rounding noise once the cost stagnates
         # (sba_levmar.c:1312; the reference does not even reproduce its own iteration count across BLAS thread counts,
@@ -63,6 +63,7 @@ def test_converged_parameters_within_1e6_of_the_reference(shape):
         k = min(rr, rg)
         (pr, ir, rr), (pg, ig, rg) = _both(s, nk, nd, itmax=k, mcon=1, ncon=1)
         assert rr == rg == k
+    assert abs(ir[1] - ig[1]) <= 1e-9 * ir[1]                                            # cost at the same iteration
     assert list(ir[7:]) == list(ig[7:])                                                  # evaluations and linear systems
     assert rel_blocks(pg, pr, m) < 1e-6                                                  # cameras (by block) and points
     assert np.array_equal(pg[:16], pr[:16]) and np.array_equal(pg[16 * m:16 * m + 3], pr[16 * m:16 * m + 3])
