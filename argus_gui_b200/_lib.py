@@ -52,6 +52,7 @@ SIGNATURES = {
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
     "argus_ba_set_mode": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "argus_ba_set_camera_fix": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "argus_ba_set_wand": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double]),
     "argus_ba_reset": (ctypes.c_int, [ctypes.c_void_p]),
     "argus_ba_solve": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "argus_ba_download": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

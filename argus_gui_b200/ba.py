@@ -125,6 +125,18 @@ class BundleAdjuster:
             rc = self.lib.argus_ba_set_camera_fix(self.h, _ptr(a), _ptr(b))
         _lib.check(rc, "argus_ba_set_camera_fix")
 
+    def set_wand(self, ia, ib, length, weight):
+        """In-solver wand-length constraint (extension, parity unpinned - the reference only rescales after the adjustment,
+        argus_gui/sbaDriver.py:703-713): residual ``weight * (length - ||X_ia - X_ib||)`` per pair; ``length`` a scalar or one
+        value per pair.  ``weight=0`` or no pairs switches it off.  After ``upload``."""
+        ia = np.ascontiguousarray(ia, dtype=np.int64).ravel(); ib = np.ascontiguousarray(ib, dtype=np.int64).ravel()
+        if ia.size != ib.size:
+            raise ValueError("ia and ib must have the same length")
+        ln = np.ascontiguousarray(np.broadcast_to(np.asarray(length, dtype=np.float64), ia.shape))
+        rc = self.lib.argus_ba_set_wand(self.h, ia.size, _ptr(ia), _ptr(ib), _ptr(ln), float(weight))
+        _lib.check(rc, "argus_ba_set_wand")
+        return self
+
     def reset(self):
         _lib.check(self.lib.argus_ba_reset(self.h), "argus_ba_reset")
 

@@ -23,6 +23,7 @@ struct BaProblem {
     const double2  *obs_uv;   // nobs: measured pixel
     const uint64_t *pt_mask;  // n: bit j set <=> point seen by camera j
     const double   *rot0;     // 4m
+    const int32_t  *wand_of;  // optional (extension, ba_wand.cuh): n entries, index of the wand pair a point belongs to or -1; nullptr = no pairs
 };
 
 // ---- Levenberg-Marquardt state, resident on the device ------------------------------------------------

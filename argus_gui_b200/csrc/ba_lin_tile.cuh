@@ -319,8 +319,10 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
 #pragma unroll
                 for (int t = 0; t < 10; ++t) P[t] = 0.0;
                 if (pfree) {
-                    ebmax = fmax(ebmax, fmax(fabs(b0), fmax(fabs(b1), fabs(b2))));
-                    vdmax = fmax(vdmax, fmax(v00, fmax(v11, v22)));
+                    if (!(pb.wand_of && pb.wand_of[i] >= 0)) {       // points of a wand pair: k_wand_prepare adds the pair's share first
+                        ebmax = fmax(ebmax, fmax(fabs(b0), fmax(fabs(b1), fabs(b2))));
+                        vdmax = fmax(vdmax, fmax(v00, fmax(v11, v22)));
+                    }
                     if (mode != 0) {
                         double vv[6] = {v00, v01, v02, v11, v12, v22};
                         if (use_state) { vv[0] = out.vstate[3 * i]; vv[3] = out.vstate[3 * i + 1]; vv[5] = out.vstate[3 * i + 2]; }
@@ -450,8 +452,8 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
 
 // Fixed-order reduction of the per-CTA Gram fragments into the packed per-camera layout the rest of the solver uses:
 //   Ured[j][0..135] upper triangle of U_j, [136..151] ea_j;  Eout[j][0..15] = E_j (= sum A^T e').
-// Also reduces the scalar partials: sum2 = {cost, sum pts^2}, max2 = {max|eb|, max diag V}.  grid = m blocks of 192.
-__global__ void __launch_bounds__(192) k_lin_tile_reduce(int m, int nparts, const double *__restrict__ Upart, const double *__restrict__ scpart,
+// Also reduces the nparts_sc scalar partials: sum2 = {cost, sum pts^2}, max2 = {max|eb|, max diag V}.  grid = m blocks of 192.
+__global__ void __launch_bounds__(192) k_lin_tile_reduce(int m, int nparts, int nparts_sc, const double *__restrict__ Upart, const double *__restrict__ scpart,
                                                          double *__restrict__ Ured, double *__restrict__ Eout, double *__restrict__ sum2,
                                                          double *__restrict__ max2, const int *__restrict__ done)
 {
@@ -477,7 +479,7 @@ __global__ void __launch_bounds__(192) k_lin_tile_reduce(int m, int nparts, cons
     if (j == 0 && t >= 168 && t < 172) {
         const int w = t - 168;
         double s = (w == 1) ? 0.0 : ((w == 2) ? -1.79769313486231570e308 : 0.0);
-        for (int q = 0; q < nparts; ++q) {
+        for (int q = 0; q < nparts_sc; ++q) {              // nparts_sc >= nparts: the wand kernel's partials follow the tile kernel's
             const double v = scpart[4 * q + w];
             if (w == 1 || w == 2) s = fmax(s, v); else s += v;
         }
@@ -513,6 +515,7 @@ __global__ void __launch_bounds__(128) k_backsub_recompute(BaProblem pb, ParamBu
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < pb.n; base += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = base + threadIdx.x;
         if (i >= pb.n) continue;
+        if (pb.wand_of && pb.wand_of[i] >= 0) continue;             // the two points of a wand pair are coupled: k_wand_backsub
         const double M0 = pts[3 * i], M1 = pts[3 * i + 1], M2 = pts[3 * i + 2];
         const int k0 = pb.obs_ptr[i], k1 = pb.obs_ptr[i + 1];
         double d0 = 0.0, d1 = 0.0, d2 = 0.0;

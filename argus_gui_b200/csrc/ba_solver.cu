@@ -26,6 +26,7 @@
 #include "ba_blockdiag.cuh"
 #include "ba_chol_coop.cuh"
 #include "ba_lm_controller.cuh"
+#include "ba_wand.cuh"
 #include "nccl_dyn.h"
 
 using namespace argus;
@@ -140,6 +141,9 @@ struct argus_ba_ctx {
     DevBuf<uint8_t> obs_lpt, corder, row_obs, pt_slot0, vmask_dev; DevBuf<int32_t> idx_btot;
     DevBuf<uint32_t> hit_tab; DevBuf<uint16_t> hit_ent; DevBuf<int32_t> hit_ptr;     // static hit lists of the Schur kernel
     DevBuf<uint8_t> cam_fix; bool cam_fix_on = false; DevBuf<uint16_t> cstart;
+    // wand pairs (extension, ba_wand.cuh); their buffers live outside the arena: argus_ba_set_wand comes after the upload
+    int64_t wand_n = 0; double wand_w = 0.0; int wand_grid = 0, wand_chunks = 0;
+    DevBuf<int32_t> wand_ia, wand_ib, wand_of; DevBuf<double> wand_len, wand_rec, wand_Q, wand_part;
     int grid_lin = 1; size_t lin_smem = 0;
     int64_t nrows = 0;                 // Z rows (>= nobs: a tile has 4 * max class fill rows)
     int ntiles = 0, schur_G = 1, schur_NB = 1, schur_NW = 8, schur_nchunk = 1;
@@ -174,7 +178,12 @@ struct argus_ba_ctx {
         BaProblem pb;
         pb.n = n; pb.ncon = (mode == kModeMot) ? n : ncon; pb.m = m; pb.mcon = (mode == kModeStr) ? m : mcon; pb.nobs = nobs; pb.nfix_k = nfix_k; pb.nfix_d = nfix_d; pb.cam_fix = cam_fix_on ? cam_fix.p : nullptr;
         pb.obs_ptr = obs_ptr.p; pb.obs_cam = obs_cam.p; pb.obs_uv = obs_uv.p; pb.pt_mask = pt_mask.p; pb.rot0 = rot0.p;
+        pb.wand_of = wand_n > 0 ? wand_of.p : nullptr;
         return pb;
+    }
+    WandPlan wand_plan() const {
+        WandPlan wp; wp.npairs = wand_n; wp.ia = wand_ia.p; wp.ib = wand_ib.p; wp.len = wand_len.p; wp.w = wand_w; wp.rec = wand_rec.p; wp.Q = wand_Q.p;
+        return wp;
     }
 };
 
@@ -241,7 +250,11 @@ int enqueue_cost(argus_ba_ctx *c, int trial_cam, double *hx)
     {
         ProfScope ps(c, P_RESIDUAL);
         k_residual<<<c->grid_pts256, 256, cam_smem(c->m), c->stream>>>(c->problem(), c->pbufs(), c->st.p, trial_cam, hx, c->respart.p);
-        k_reduce_cost<<<1, 32, 0, c->stream>>>(c->respart.p, c->grid_pts256, c->att3.p, c->done_ptr());
+        if (c->wand_n > 0) {
+            k_wand_cost<<<c->wand_grid, kWandThreads, 0, c->stream>>>(c->wand_plan(), c->pbufs(), c->st.p, c->respart.p + c->grid_pts256);
+            c->launches += 1;
+        }
+        k_reduce_cost<<<1, 32, 0, c->stream>>>(c->respart.p, c->grid_pts256 + c->wand_grid, c->att3.p, c->done_ptr());
         c->launches += 2;
     }
     ARGUS_CUDA_CHECK(cudaGetLastError());
@@ -259,10 +272,15 @@ int enqueue_lin(argus_ba_ctx *c, int mode)
         const int mc = (m - c->mcon + 7) / 8;
         if (mc <= 2) LIN_LAUNCH(2); else if (mc <= 4) LIN_LAUNCH(4); else LIN_LAUNCH(8);
 #undef LIN_LAUNCH
+        if (c->wand_n > 0) {
+            k_wand_prepare<<<c->wand_grid, kWandThreads, cam_smem(m), c->stream>>>(c->problem(), c->wand_plan(), c->pbufs(), c->st.p, mode, c->V.p, c->eb.p,
+                                                                                   c->Vinv.p, c->scpart.p + 4 * (size_t)c->grid_lin);
+            c->launches += 1;
+        }
     }
     {
         ProfScope ps(c, P_LIN_REDUCE);
-        k_lin_tile_reduce<<<m, 192, 0, c->stream>>>(m, c->grid_lin, c->Upart2.p, c->scpart.p, c->red1, c->red2 + (int64_t)c->npairs * 256,
+        k_lin_tile_reduce<<<m, 192, 0, c->stream>>>(m, c->grid_lin, c->grid_lin + c->wand_grid, c->Upart2.p, c->scpart.p, c->red1, c->red2 + (int64_t)c->npairs * 256,
                                                    c->red1 + (int64_t)m * kU, c->max2.p, c->done_ptr());
     }
     c->launches += 2;
@@ -327,6 +345,12 @@ int enqueue_attempt_motstr(argus_ba_ctx *c, bool controller, double *dbout)
     {
         ProfScope ps(c, P_SCHUR_REDUCE);
         k_reduce_sum<<<(unsigned)((slen + 127) / 128), 128, 0, s>>>(c->Spart.p, c->schur_nchunk, slen, slen, c->red2, done);
+        if (c->wand_n > 0) {     // rank-one corrections of the wand pairs: Schur sums -= sigma q q^T, E -= beta q
+            const int64_t wlen = slen + 16 * m;
+            k_wand_schur<<<dim3(c->npairs + 1, c->wand_chunks), 256, 0, s>>>(c->problem(), c->wand_plan(), mf, c->st.p, c->wand_part.p);
+            k_wand_apply<<<(unsigned)((wlen + 255) / 256), 256, 0, s>>>(c->npairs, m, c->wand_chunks, c->wand_part.p, c->red2, done);
+            c->launches += 2;
+        }
     }
     c->launches += 2;
     ARGUS_CUDA_CHECK(cudaGetLastError());
@@ -362,7 +386,12 @@ int enqueue_attempt_motstr(argus_ba_ctx *c, bool controller, double *dbout)
         k_cam_update<<<1, 256, 0, s>>>(m, mcon, c->pbufs(), c->st.p, c->da_free.p, c->red1, c->da_full.p, c->cam2.p);
         const size_t sm = 2 * cam_smem(m) + (size_t)m * 17 * sizeof(double);
         k_backsub_recompute<<<c->grid_pts128, 128, sm, s>>>(c->problem(), c->pbufs(), c->st.p, 1, c->da_full.p, c->Vinv.p, c->eb.p, dbout, c->part3.p);
-        k_reduce_attempt<<<1, 32, 0, s>>>(c->part3.p, c->grid_pts128, c->flags.p, c->att3.p, done);
+        if (c->wand_n > 0) {
+            k_wand_backsub<<<c->wand_grid, kWandThreads, sm, s>>>(c->problem(), c->wand_plan(), c->pbufs(), c->st.p, c->da_full.p, c->Vinv.p, c->eb.p,
+                                                                   dbout, c->part3.p + 3 * (size_t)c->grid_pts128);
+            c->launches += 1;
+        }
+        k_reduce_attempt<<<1, 32, 0, s>>>(c->part3.p, c->grid_pts128 + c->wand_grid, c->flags.p, c->att3.p, done);
     }
     c->launches += 5;
     ARGUS_CUDA_CHECK(cudaGetLastError());
@@ -521,6 +550,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
     c->hit_tab.release(); c->hit_ent.release(); c->hit_ptr.release(); c->cam_fix.release(); c->cstart.release(); c->vmask_dev.release();
     c->idx_btot.release(); c->flags.release(); c->tile_pt.release(); c->tile_o.release(); c->blk_jk.release(); c->blk_pair.release();
     c->zsign.release(); c->st.release();
+    c->wand_ia.release(); c->wand_ib.release(); c->wand_of.release(); c->wand_len.release(); c->wand_rec.release(); c->wand_Q.release(); c->wand_part.release();
     if (c->lmlog) cudaFree(c->lmlog);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto &e : c->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -602,6 +632,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         }
     });
     c->n = n; c->ncon = ncon; c->m = m; c->mcon = mcon; c->nfix_k = nccalib; c->nfix_d = ncdist; c->cam_fix_on = false;
+    c->wand_n = 0; c->wand_grid = 0; c->wand_chunks = 0;       // pairs refer to the points of one upload
     const int mf = m - mcon, N = 16 * mf;
     c->npairs = mf * (mf + 1) / 2;
     c->grid_pts128 = (int)std::min<int64_t>((n + 127) / 128, (int64_t)c->sms * 8); if (c->grid_pts128 < 1) c->grid_pts128 = 1;
@@ -684,10 +715,10 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         PLAN_ENS(c->rot0, 4 * m); PLAN_ENS(c->camb[0], 16 * m); PLAN_ENS(c->camb[1], 16 * m); PLAN_ENS(c->cam0, 16 * m);
         PLAN_ENS(c->ptsb[0], 3 * n); PLAN_ENS(c->ptsb[1], 3 * n); PLAN_ENS(c->pts0, 3 * n);
         PLAN_ENS(c->V, 6 * n); PLAN_ENS(c->eb, 3 * n); PLAN_ENS(c->vstate, 3 * n); PLAN_ENS(c->Vinv, 6 * n); PLAN_ENS(c->dbuf, 3 * n);
-        PLAN_ENS(c->scpart, 4 * c->grid_lin); PLAN_ENS(c->red12, c->r1len + slen + 16 * m); PLAN_ENS(c->max2, 2);
+        PLAN_ENS(c->scpart, 4 * (c->grid_lin + kWandGridMax)); PLAN_ENS(c->red12, c->r1len + slen + 16 * m); PLAN_ENS(c->max2, 2);
         PLAN_ENS(c->Spart, (int64_t)c->schur_nchunk * slen);
         PLAN_ENS(c->S, (int64_t)N * N); PLAN_ENS(c->E, N); PLAN_ENS(c->da_free, N); PLAN_ENS(c->da_full, 16 * m);
-        PLAN_ENS(c->part3, 3 * c->grid_pts128); PLAN_ENS(c->att3, 4); PLAN_ENS(c->cam2, 2); PLAN_ENS(c->scal, 8); PLAN_ENS(c->respart, c->grid_pts256);
+        PLAN_ENS(c->part3, 3 * (c->grid_pts128 + kWandGridMax)); PLAN_ENS(c->att3, 4); PLAN_ENS(c->cam2, 2); PLAN_ENS(c->scal, 8); PLAN_ENS(c->respart, c->grid_pts256 + kWandGridMax);
         PLAN_ENS(c->flags, 4); PLAN_ENS(c->st, 1);
 #undef PLAN_ENS
 #undef PLAN_CHECK
@@ -779,6 +810,35 @@ int argus_ba_set_camera_fix(argus_ba_ctx *c, const int *nccalib, const int *ncdi
     ARGUS_CUDA_CHECK(c->cam_fix.ensure(h.size()));
     ARGUS_CUDA_CHECK(cudaMemcpy(c->cam_fix.p, h.data(), h.size(), cudaMemcpyHostToDevice));
     c->cam_fix_on = true;
+    return ARGUS_OK;
+}
+
+int argus_ba_set_wand(argus_ba_ctx *c, int64_t npairs, const int64_t *ia, const int64_t *ib, const double *length, double weight)
+{
+    if (!c || c->m == 0 || npairs < 0 || (npairs > 0 && (!ia || !ib || !length)) || !(weight >= 0.0)) return ARGUS_E_ARG;
+    ARGUS_CUDA_CHECK(cudaSetDevice(c->device));
+    drop_graph(c);
+    c->wand_n = 0; c->wand_grid = 0; c->wand_chunks = 0; c->wand_w = weight;
+    if (npairs == 0 || weight == 0.0) return ARGUS_OK;          // off: the solver is the unconstrained one, bit for bit
+    if (c->mode != kModeMotStr || npairs > 0x7fffffffLL) return ARGUS_E_ARG;
+    std::vector<int32_t> of((size_t)c->n, -1), ha((size_t)npairs), hb((size_t)npairs);
+    for (int64_t p = 0; p < npairs; ++p) {
+        const int64_t a = ia[p], b = ib[p];
+        if (a < 0 || b < 0 || a >= c->n || b >= c->n || a == b || of[a] >= 0 || of[b] >= 0 || !(length[p] > 0.0)) return ARGUS_E_ARG;
+        of[a] = (int32_t)p; of[b] = (int32_t)p; ha[p] = (int32_t)a; hb[p] = (int32_t)b;
+    }
+    const int grid = (int)std::min<int64_t>(kWandGridMax, (npairs + kWandThreads - 1) / kWandThreads);
+    const int chunks = (int)std::min<int64_t>(128, (npairs + 255) / 256);
+    ARGUS_CUDA_CHECK(c->wand_ia.ensure(npairs)); ARGUS_CUDA_CHECK(c->wand_ib.ensure(npairs)); ARGUS_CUDA_CHECK(c->wand_of.ensure(c->n));
+    ARGUS_CUDA_CHECK(c->wand_len.ensure(npairs)); ARGUS_CUDA_CHECK(c->wand_rec.ensure((size_t)npairs * kWandRec));
+    ARGUS_CUDA_CHECK(c->wand_Q.ensure((size_t)npairs * c->m * 16));
+    ARGUS_CUDA_CHECK(c->wand_part.ensure((size_t)chunks * ((size_t)c->npairs * 256 + 16 * (size_t)c->m)));
+    ARGUS_CUDA_CHECK(cudaMemcpy(c->wand_ia.p, ha.data(), ha.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ARGUS_CUDA_CHECK(cudaMemcpy(c->wand_ib.p, hb.data(), hb.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ARGUS_CUDA_CHECK(cudaMemcpy(c->wand_of.p, of.data(), of.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    ARGUS_CUDA_CHECK(cudaMemcpy(c->wand_len.p, length, (size_t)npairs * sizeof(double), cudaMemcpyHostToDevice));
+    c->h2d_bytes += (size_t)npairs * (2 * sizeof(int32_t) + sizeof(double)) + (size_t)c->n * sizeof(int32_t);
+    c->wand_n = npairs; c->wand_grid = grid; c->wand_chunks = chunks;
     return ARGUS_OK;
 }
 
@@ -902,6 +962,7 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
     const int m = c->m, mode = c->mode;
     cudaStream_t s = c->stream;
     int rc;
+    if (c->wand_n > 0 && mode != kModeMotStr) return ARGUS_E_ARG;      // the wand term couples points: motion + structure driver only
     // the reference refuses problems with fewer measurements than unknowns (sba_levmar.c:632-637); counts are global over the ranks
     double gc[3];
     if ((rc = global_counts(c, gc))) return rc;

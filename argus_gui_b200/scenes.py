@@ -7,7 +7,7 @@ camera row = [f, cx, cy, AR, s, r2, r4, t1, t2, r6, qw, qx, qy, qz, tx, ty, tz].
 """
 import numpy as np
 
-__all__ = ["quat_to_rot", "rot_to_quat", "project_points", "make_ring_cameras", "make_ba_scene",
+__all__ = ["quat_to_rot", "rot_to_quat", "project_points", "make_ring_cameras", "make_ba_scene", "make_ba_wand_scene",
            "make_dlt_scene", "cameras_to_dlt", "pack_ba_problem", "dense_to_sparse"]
 
 
@@ -88,7 +88,7 @@ def make_ring_cameras(m, radius=8.0, height_amp=1.0, dist=(-0.05, 0.01, 0.001, -
 
 
 def make_ba_scene(m, n, views, seed, noise=0.5, radius=8.0, perturb=True, outlier_frac=0.0,
-                  dist=(-0.05, 0.01, 0.001, -0.001, 0.0), point_sigma=1.0, pert_scale=1.0, cam_seed=None):
+                  dist=(-0.05, 0.01, 0.001, -0.001, 0.0), point_sigma=1.0, pert_scale=1.0, cam_seed=None, pts=None):
     """Synthetic BA problem (SURVEY.md 8d, configs C3/C4/C5 by argument).
 
     Returns a dict with the truth, the perturbed start, and the *sparse* problem in the layout the
@@ -97,7 +97,7 @@ def make_ba_scene(m, n, views, seed, noise=0.5, radius=8.0, perturb=True, outlie
     """
     rng = np.random.default_rng(seed)
     cams = make_ring_cameras(m, radius=radius, dist=dist)
-    pts = rng.normal(0.0, point_sigma, size=(n, 3))
+    pts = rng.normal(0.0, point_sigma, size=(n, 3)) if pts is None else np.array(pts, dtype=np.float64).reshape(n, 3)
     views = min(views, m)
     if views == m:
         vmask = np.ones((n, m), dtype=np.uint8)
@@ -140,6 +140,19 @@ def make_ba_scene(m, n, views, seed, noise=0.5, radius=8.0, perturb=True, outlie
         pts0 += rng.uniform(-0.02 * s, 0.02 * s, size=(n, 3))
     return {"m": m, "n": n, "cams_true": cams, "pts_true": pts, "cams0": cams0, "pts0": pts0,
             "vmask": vmask, "x": x, "nobs": int(x.shape[0])}
+
+
+def make_ba_wand_scene(m, npairs, nextra, views, seed, wand=0.5, point_sigma=1.0, **kw):
+    """A BA scene whose first 2 * npairs points are the two ends of ``npairs`` wand positions (ends 1 first, then ends 2 - the
+    order in which Argus' driver stacks its paired points, argus_gui/sbaDriver.py:183-197), followed by ``nextra`` free
+    points.  Adds ``ia``, ``ib`` (the point indices of every pair) and ``wand`` to the dict of ``make_ba_scene``."""
+    rng = np.random.default_rng(seed + 7919)
+    centre = rng.normal(0.0, point_sigma, size=(npairs, 3))
+    d = rng.normal(size=(npairs, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pts = np.vstack([centre - 0.5 * wand * d, centre + 0.5 * wand * d, rng.normal(0.0, point_sigma, size=(nextra, 3))])
+    s = make_ba_scene(m, 2 * npairs + nextra, views, seed, point_sigma=point_sigma, pts=pts, **kw)
+    s["ia"] = np.arange(npairs, dtype=np.int64); s["ib"] = np.arange(npairs, 2 * npairs, dtype=np.int64); s["wand"] = wand
+    return s
 
 
 def pack_ba_problem(cams17, pts):

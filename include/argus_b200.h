@@ -127,6 +127,13 @@ int  argus_ba_set_mode(argus_ba_ctx *ctx, int mode);
  * of fixed trailing intrinsics / distortion coefficients, m entries each, after argus_ba_upload; NULL, NULL restores the global
  * values.  BASELINE config 5 ("mixed fixed/free intrinsics") needs it. */
 int  argus_ba_set_camera_fix(argus_ba_ctx *ctx, const int *nccalib, const int *ncdist);
+/* EXTENSION, parity unpinned (the reference has no counterpart: it applies the wand length after the adjustment, as one global
+ * scale, argus_gui/sbaDriver.py:703-713, and reports the spread as the wand score, :779-781): wand-length constraint inside
+ * the solver.  Every pair (ia[p], ib[p]) of points of the uploaded problem (indices local to this rank, a point in at most one
+ * pair) adds the residual  weight * (length[p] - ||X_ia - X_ib||)  to the cost (weight: pixels per length unit).  Call
+ * after argus_ba_upload, motion + structure mode only; npairs = 0 or weight = 0 switches it off, and the solver is then bit
+ * for bit the unconstrained one.  info[0], info[1] then include the wand residuals. */
+int  argus_ba_set_wand(argus_ba_ctx *ctx, int64_t npairs, const int64_t *ia, const int64_t *ib, const double *length, double weight);
 /* restore the parameter vector uploaded last (device-side copy), e.g. between timed repetitions */
 int  argus_ba_reset(argus_ba_ctx *ctx);
 int  argus_ba_solve(argus_ba_ctx *ctx, int itmax, int verbose, const double opts[5], double info[10], int flags);
