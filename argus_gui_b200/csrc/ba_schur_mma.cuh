@@ -139,6 +139,27 @@ __device__ __forceinline__ HitCtx hit_ctx(int lane, int p0, int npts, int64_t nc
     return h;
 }
 
+// hits per camera pair over all free points (j <= k, out[j * m + k]): the weights of the block -> warp assignment.  Integer
+// atomics only (order independent).
+__global__ void __launch_bounds__(256) k_pair_hist(int64_t n, int64_t ncon, int m, const uint64_t *__restrict__ pt_mask,
+                                                   unsigned long long *__restrict__ out)
+{
+    extern __shared__ unsigned int s_h[];      // m * m
+    for (int t = threadIdx.x; t < m * m; t += blockDim.x) s_h[t] = 0u;
+    __syncthreads();
+    for (int64_t i = ncon + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t a = pt_mask[i];
+        while (a) {
+            const int j = __ffsll((long long)a) - 1;
+            uint64_t b = a;
+            while (b) { const int k = __ffsll((long long)b) - 1; b &= b - 1; atomicAdd(&s_h[j * m + k], 1u); }
+            a &= a - 1;
+        }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < m * m; t += blockDim.x) if (s_h[t]) atomicAdd(&out[t], (unsigned long long)s_h[t]);
+}
+
 __global__ void __launch_bounds__(256) k_hits_count(int ntiles, int G, int nslots, const int32_t *__restrict__ tile_pt, int64_t ncon,
                                                     const uint64_t *__restrict__ pt_mask, const uint8_t *__restrict__ pt_slot0,
                                                     const uint16_t *__restrict__ blk_jk, int32_t *__restrict__ tg_count)

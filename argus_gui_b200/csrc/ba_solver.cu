@@ -682,18 +682,9 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         int occ = (int)((220 * 1024) / (c->lin_smem + 1024)); if (occ < 1) occ = 1; if (occ > 2) occ = 2;
         c->grid_lin = std::min(c->ntiles > 0 ? c->ntiles : 1, c->sms * occ);
     }
+    // block -> (group, warp, slot): filled further down, once the device has counted the hits of every camera pair
     std::vector<uint16_t> hjk((size_t)c->schur_G * c->schur_NW * c->schur_NB, 0xFFFF);
     std::vector<int32_t> hpair((size_t)c->schur_G * c->schur_NW * c->schur_NB, -1);
-    {
-        int pidx = 0;
-        for (int a = 0; a < mf; ++a)
-            for (int b = a; b < mf; ++b, ++pidx) {
-                const int grp = pidx % c->schur_G, q = pidx / c->schur_G, w = q % c->schur_NW, slot = q / c->schur_NW;
-                const size_t at = ((size_t)grp * c->schur_NW + w) * c->schur_NB + slot;
-                hjk[at] = (uint16_t)((mcon + a) | ((mcon + b) << 8));
-                hpair[at] = pidx;
-            }
-    }
     const int64_t slen = (int64_t)c->npairs * 256;
     c->r1len = ((int64_t)m * kU + 2 + 1) & ~(int64_t)1;
     // every device buffer of the problem comes out of ONE allocation: measure, allocate, assign
@@ -750,8 +741,6 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_o.p, tile_o.data(), tile_o.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->tile_r.p, tile_r.data(), tile_r.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     if (n > 0) ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pt_slot0.p, slot0.data(), (size_t)n, cudaMemcpyHostToDevice, s));
-    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_jk.p, hjk.data(), hjk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
-    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_pair.p, hpair.data(), hpair.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->vmask_dev.p, vmask, (size_t)n * m, cudaMemcpyHostToDevice, s));
     if (n > 0) {
         const int nb = (int)((n + kIdxPts - 1) / kIdxPts);
@@ -765,6 +754,81 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->rot0.p, rot0, 4 * m * sizeof(double), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cam0.p, p, 16 * m * sizeof(double), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pts0.p, p + 16 * m, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    {
+        // Every warp of the Schur kernel keeps its blocks for the whole launch and the warps of a CTA advance tile by tile
+        // together (two shared-memory stages), so the slowest warp sets the pace: deal the blocks by weight.  Weight = hits of
+        // the camera pair over all points (counted on the device) - a diagonal block needs 3 of the 4 sub-tiles - plus a fixed
+        // cost per tile; longest-processing-time-first into the G x NW warps, each with NB slots.
+        std::vector<unsigned long long> hist((size_t)m * m, 0ull);
+        if (n > ncon && c->mode == kModeMotStr) {
+            unsigned long long *dh = reinterpret_cast<unsigned long long *>(c->S.p);      // scratch: S (N x N doubles >= m x m) is not in use yet
+            if ((size_t)N * N >= (size_t)m * m) {
+                ARGUS_CUDA_CHECK(cudaMemsetAsync(dh, 0, (size_t)m * m * sizeof(unsigned long long), s));
+                const int gh = (int)std::min<int64_t>((n - ncon + 255) / 256, (int64_t)c->sms * 4);
+                k_pair_hist<<<gh, 256, (size_t)m * m * sizeof(unsigned int), s>>>(n, ncon, m, c->pt_mask.p, dh);
+                ARGUS_CUDA_CHECK(cudaMemcpyAsync(hist.data(), dh, hist.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+                ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));
+            }
+        }
+        struct Blk { int a, b, pidx; double w; };
+        std::vector<Blk> blks;
+        int pidx = 0;
+        for (int a = 0; a < mf; ++a)
+            for (int b = a; b < mf; ++b, ++pidx) {
+                const double h = (double)hist[(size_t)(mcon + a) * m + (mcon + b)];
+                blks.push_back({a, b, pidx, h * (a == b ? 0.75 : 1.0) + 1.5 * (double)c->ntiles});
+            }
+        std::stable_sort(blks.begin(), blks.end(), [](const Blk &x, const Blk &y) { return x.w > y.w; });
+        const int nbins = c->schur_G * c->schur_NW, NBs = c->schur_NB;
+        std::vector<double> load((size_t)nbins, 0.0);
+        std::vector<std::vector<int>> bins((size_t)nbins);
+        for (int i = 0; i < (int)blks.size(); ++i) {
+            int best = -1;
+            for (int q = 0; q < nbins; ++q)
+                if ((int)bins[q].size() < NBs && (best < 0 || load[q] < load[best])) best = q;
+            bins[best].push_back(i); load[best] += blks[i].w;
+        }
+        // local search on the heaviest warp: the slot limit makes plain LPT leave it up to 10 % above what a move or a swap reaches
+        for (int iter = 0; iter < 4096; ++iter) {
+            int bm = 0;
+            for (int q = 1; q < nbins; ++q) if (load[q] > load[bm]) bm = q;
+            double bestv = load[bm]; int bi = -1, bc = -1, bj = -1;
+            for (int ii = 0; ii < (int)bins[bm].size(); ++ii) {
+                const double wi = blks[bins[bm][ii]].w;
+                for (int q = 0; q < nbins; ++q) {
+                    if (q == bm) continue;
+                    if ((int)bins[q].size() < NBs) {
+                        const double v = std::max(load[bm] - wi, load[q] + wi);
+                        if (v < bestv * (1.0 - 1e-12)) { bestv = v; bi = ii; bc = q; bj = -1; }
+                    }
+                    for (int jj = 0; jj < (int)bins[q].size(); ++jj) {
+                        const double wj = blks[bins[q][jj]].w;
+                        const double v = std::max(load[bm] - wi + wj, load[q] + wi - wj);
+                        if (v < bestv * (1.0 - 1e-12)) { bestv = v; bi = ii; bc = q; bj = jj; }
+                    }
+                }
+            }
+            if (bi < 0) break;
+            const int i = bins[bm][bi];
+            if (bj < 0) {
+                bins[bm].erase(bins[bm].begin() + bi); bins[bc].push_back(i);
+                load[bm] -= blks[i].w; load[bc] += blks[i].w;
+            } else {
+                const int j = bins[bc][bj];
+                bins[bm][bi] = j; bins[bc][bj] = i;
+                load[bm] += blks[j].w - blks[i].w; load[bc] += blks[i].w - blks[j].w;
+            }
+        }
+        for (int q = 0; q < nbins; ++q)
+            for (int t = 0; t < (int)bins[q].size(); ++t) {
+                const Blk &bk = blks[bins[q][t]];
+                const size_t at = (size_t)q * NBs + t;
+                hjk[at] = (uint16_t)((mcon + bk.a) | ((mcon + bk.b) << 8));
+                hpair[at] = bk.pidx;
+            }
+        ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_jk.p, hjk.data(), hjk.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, s));
+        ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->blk_pair.p, hpair.data(), hpair.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    }
     // derived static indices, built on the device
     if (n > 0 && c->ntiles > 0) {
         ARGUS_CUDA_CHECK(cudaMemsetAsync(c->row_obs.p, 0xFF, (size_t)nrows, s));

@@ -197,6 +197,11 @@ class Options(object):
         self.expert = True
         self.analyticjac = True
         self.compat_sba16 = True      # reproduce sba 1.6's damping behaviour after a rejected step
+        # EXTENSION, parity unpinned (python-sba / sba 1.6 have no such option): wand-length constraint inside the solver,
+        # residual wand_weight * (wand_length - ||X_a - X_b||) per pair; wand_pairs = (ia, ib) point indices, off by default
+        self.wand_pairs = None
+        self.wand_length = None
+        self.wand_weight = 0.0
 
     @classmethod
     def fromInput(cls, cameras, points):
@@ -249,6 +254,17 @@ def SparseBundleAdjust(cameras, points, options):
         pts, info, ret = _ba.solve_str(points.vmask, points.B.ravel(), a.ravel(), rot0.ravel(), points.X, ncon=options.ncon, **common)
         pn = np.concatenate([a.ravel(), pts])
         nvars = 3 * n
+    elif options.wand_pairs is not None and options.wand_weight > 0 and len(options.wand_pairs[0]) > 0:
+        # constrained problem: the resident-data calls (the one-shot call is the reference's signature and has no pair list)
+        p = np.concatenate([a.ravel(), points.B.ravel()])
+        B = _ba.BundleAdjuster().upload(points.vmask, p, rot0.ravel(), points.X, options.nccalib, options.ncdist, ncon=options.ncon, mcon=options.mcon)
+        try:
+            B.set_wand(options.wand_pairs[0], options.wand_pairs[1], options.wand_length, options.wand_weight)
+            ret, info = B.solve(itmax=options.maxIter, opts=options.opts, verbose=options.verbose, compat=options.compat_sba16)
+            pn = B.download()
+        finally:
+            B.close()
+        nvars = 16 * m + 3 * n
     else:
         p = np.concatenate([a.ravel(), points.B.ravel()])
         pn, info, ret = _ba.solve_motstr(points.vmask, p, rot0.ravel(), points.X, options.nccalib, options.ncdist, ncon=options.ncon,

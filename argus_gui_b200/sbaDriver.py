@@ -125,7 +125,10 @@ def align_to_reference(xyzs, nref, reference_type='Axis points', recording_frequ
 
 class sbaArgusDriver(object):
     def __init__(self, ppts, uppts, cams, display=True, scale=None, modeString=None, ref=None, name=None, temp="",
-                 report=True, outputCPs=True, reorder=True, reference_type='Axis points', recording_frequency=100):
+                 report=True, outputCPs=True, reorder=True, reference_type='Axis points', recording_frequency=100, wand_weight=0.0):
+        """The reference's constructor (sbaDriver.py:50-77) plus ONE optional extension at the end: ``wand_weight`` > 0 puts
+        the wand length into the bundle adjustment itself (parity unpinned; residual = wand_weight pixels per unit RELATIVE
+        length error of every paired frame); 0 is the reference's behaviour, where the wand only sets the scale afterwards."""
         self.ppts = ppts
         self.uppts = uppts
         self.cams = cams
@@ -143,6 +146,7 @@ class sbaArgusDriver(object):
         self.reorder = reorder
         self.reference_type = reference_type
         self.recording_frequency = recording_frequency
+        self.wand_weight = float(wand_weight)
         self.sba_options = {}           # extra solver options (maxIter, opts, mcon, ...) applied in fix()
         self.info = None
         self.grapher = None
@@ -252,6 +256,18 @@ class sbaArgusDriver(object):
         options.nccalib = {'0': sba.OPTS_FIX5_INTR, '1': sba.OPTS_FIX4_INTR, '2': sba.OPTS_FIX2_INTR}.get(self.modeString[0], options.nccalib)
         options.ncdist = {'0': sba.OPTS_FIX5_DIST, '1': sba.OPTS_FIX4_DIST, '2': sba.OPTS_FIX3_DIST,
                           '3': sba.OPTS_FIX0_DIST}.get(self.modeString[1], options.ncdist)
+        if self.wand_weight > 0 and self.indices.get('paired') is not None:
+            # the frames seen in both tracks are the wand pairs (pairedIsomorphism); the solver's length unit is the initial
+            # triangulation's, so the known length is expressed as the current mean and the true scale is applied afterwards as ever
+            i0, i1 = self.indices['paired']
+            pos0 = {f: k for k, f in enumerate(i0)}; pos1 = {f: k for k, f in enumerate(i1)}
+            common = sorted(set(i0) & set(i1))
+            nref = self.ref.shape[0] if self.ref is not None else 0
+            ia = np.array([nref + pos0[f] for f in common], dtype=np.int64)
+            ib = np.array([nref + len(i0) + pos1[f] for f in common], dtype=np.int64)
+            if ia.size:
+                L0 = float(np.linalg.norm(points.B[ia] - points.B[ib], axis=1).mean())
+                options.wand_pairs, options.wand_length, options.wand_weight = (ia, ib), L0, self.wand_weight / L0
         for k, v in self.sba_options.items():
             setattr(options, k, v)
         newcameras, newpoints, info = sba.SparseBundleAdjust(cameras, points, options)

@@ -63,3 +63,21 @@ def test_c1_wand_calibration_end_to_end(tmp_path):
     assert prof.shape == (3, 17)
     dl = np.loadtxt(str(tmp_path / "c1-dlt-coefficients.csv"), delimiter=",")
     assert dl.shape == (11, 3) and res.dlterrors.max() < 2.0
+
+
+@pytest.mark.gpu
+def test_c1_with_the_wand_length_inside_the_solver(tmp_path):
+    """Extension (parity unpinned): wand_weight > 0 constrains the wand length during the adjustment; the wand score (spread of
+    the reconstructed lengths, sbaDriver.py:779-781) drops, the files keep their formats and the scale is still the wand's."""
+    scores = {}
+    for ww in (0.0, 3000.0):
+        w = scenes.make_wand_scene(nframes=600, nbackground=60, m=3, seed=4, noise=1.0)
+        d = sbaDriver.sbaArgusDriver(w["ppts"].copy(), w["uppts"].copy(), w["cams"].copy(), display=False, scale=0.5, modeString="01",
+                                     name=str(tmp_path / ("w%d" % int(ww))), temp=str(tmp_path), report=False, wand_weight=ww)
+        res = d.fix()
+        scores[ww] = res.wandscore
+        paired = np.loadtxt(str(tmp_path / ("w%d-paired-points-xyz.csv" % int(ww))), delimiter=",", skiprows=1)
+        ok = ~np.isnan(paired).any(axis=1)
+        assert abs(np.linalg.norm(paired[ok, :3] - paired[ok, 3:], axis=1).mean() - 0.5) < 1e-9
+        assert res.dlterrors.max() < 4.0
+    assert scores[3000.0] < 0.5 * scores[0.0]
