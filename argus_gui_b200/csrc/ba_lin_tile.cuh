@@ -369,7 +369,8 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             g[33] = t3.x - (B0 * c0 + B1 * c1 + B2 * c2);
             g[35] = t3.y - (B3 * c0 + B4 * c1 + B5 * c2);
             const double l0 = P[0], l1 = P[1], l2 = P[2], s0 = P[3], s1 = P[4], s2 = P[5];
-            double *Zt = out.Z + 48 * (int64_t)r0 + 4 * (int64_t)tid;     // chunk-major tile block (z_index): chunk c of this row at Zt + c * nrows_t * 4
+            const size_t zpl = (size_t)(nrows_t + 1) * 4;                // doubles per chunk plane (one padding chunk, z_index)
+            double *Zt = out.Z + 48 * ((int64_t)r0 + tile) + 4 * (int64_t)tid;     // chunk-major tile block: chunk c of this row at Zt + c * zpl
             // two rows (r, r+1) x three components x (lo, hi) = 12 doubles = three 32-byte stores (full sectors)
 #pragma unroll
             for (int r = 0; r < 8; r += 2) {
@@ -385,10 +386,10 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                     zz[rr * 6 + 2] = (l0 * wl0 + wl1) * s1; zz[rr * 6 + 3] = (l0 * wh0 + wh1) * s1;
                     zz[rr * 6 + 4] = (l1 * wl0 + l2 * wl1 + wl2) * s2; zz[rr * 6 + 5] = (l1 * wh0 + l2 * wh1 + wh2) * s2;
                 }
-                double *zp = Zt + (size_t)((r >> 1) * 3) * (size_t)nrows_t * 4;       // chunks 3 r/2 .. 3 r/2 + 2: consecutive lanes write consecutive chunks
+                double *zp = Zt + (size_t)((r >> 1) * 3) * zpl;       // chunks 3 r/2 .. 3 r/2 + 2: consecutive lanes write consecutive chunks
                 st_global_v4(zp, zz[0], zz[1], zz[2], zz[3]);
-                st_global_v4(zp + (size_t)nrows_t * 4, zz[4], zz[5], zz[6], zz[7]);
-                st_global_v4(zp + (size_t)nrows_t * 8, zz[8], zz[9], zz[10], zz[11]);
+                st_global_v4(zp + zpl, zz[4], zz[5], zz[6], zz[7]);
+                st_global_v4(zp + 2 * zpl, zz[8], zz[9], zz[10], zz[11]);
             }
         }
         __syncthreads();

@@ -53,9 +53,11 @@ struct SchurPlan {
     int nslots;                     // NW * NB block slots per group
     const uint16_t *blk_jk;         // [G][NW][NB]: j | k << 8 (absolute camera ids), 0xFFFF = empty slot
     const int32_t *blk_pair;        // [G][NW][NB]: pair index (row-major upper triangle over free cameras) or -1
-    const uint32_t *hit_tab;        // [ntiles][G][nslots]: offset of the block's list inside the (tile, group) entry block | hits << 16 | diagonal block << 31
-    const uint16_t *hit_ent;        // entries: row of Z_ij | row of Z_ik << 8
-    const int32_t *hit_ptr;         // [ntiles * G + 1]: first entry of every (tile, group) block (multiples of 8 entries)
+    const uint16_t *hit_blob;       // per (tile, group) ONE contiguous record, copied into shared memory by one bulk copy:
+                                    //   table, nslots + 4 words: [b] = offset of block b's list (in entries) | hits << 16 | diagonal block << 31,
+                                    //                            [nslots] = Z rows of the tile;
+                                    //   then the entries: row of Z_ij | row of Z_ik << 8
+    const int32_t *hit_ptr;         // [ntiles * G + 1]: start of every record in hit_blob, in 16-bit units (multiples of 8)
 };
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) ----
@@ -108,20 +110,22 @@ __device__ __forceinline__ double flip_sign(double v, uint32_t bit)      // bit 
 }
 __device__ __forceinline__ double2 flip_sign2(double2 v, uint32_t bit) { v.x = flip_sign(v.x, bit); v.y = flip_sign(v.y, bit); return v; }
 
-// Z in HBM: per tile one block of 48 * nrows doubles, chunk-major inside the block: the 12 four-double chunks of a row
-// (chunk = zperm / 4) live in 12 planes of nrows chunks each, so that the one-thread-per-row producer writes consecutive
-// 32-byte chunks (coalesced) and the Schur kernel copies a tile plane by plane.
-//   element e (= zperm(r, c)) of row `row` of a tile whose first row is r0:
-__host__ __device__ __forceinline__ int64_t z_index(int64_t r0, int nrows, int row, int e)
+// Z in HBM: per tile one block of 48 * (nrows + 1) doubles, chunk-major inside the block: the 12 four-double chunks of a row
+// (chunk = zperm / 4) live in 12 planes of nrows + 1 chunks each (the last one is padding: with nrows a multiple of 4,
+// consecutive planes start 32 bytes = 8 banks apart in shared memory), so that the one-thread-per-row producer writes
+// consecutive 32-byte chunks (coalesced) and the Schur kernel brings the WHOLE tile into shared memory with one bulk copy.
+//   element e (= zperm(r, c)) of row `row` of tile `tile`, whose first row is r0 (the padding adds one row per earlier tile):
+__host__ __device__ __forceinline__ int64_t z_index(int64_t r0, int64_t tile, int nrows, int row, int e)
 {
-    return 48 * r0 + ((int64_t)(e >> 2) * nrows + row) * 4 + (e & 3);
+    return 48 * (r0 + tile) + ((int64_t)(e >> 2) * (nrows + 1) + row) * 4 + (e & 3);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // Static hit lists.  One CTA per tile; a warp takes block slots round robin, lane = point of the tile.
-//   pass 0 (k_hits_count): per (tile, group) the number of entries, rounded up to 8 (16-byte granularity of the bulk copies)
+//   pass 0 (k_hits_count): per (tile, group) the size of the record (table + entries, in 16-bit units, rounded up to 8: the
+//                          16-byte granularity of the bulk copies)
 //   scan (k_index_scan of ba_lin_tile.cuh) -> hit_ptr
-//   pass 1 (k_hits_fill): entries in processing order + the (offset, count) table
+//   pass 1 (k_hits_fill): the table and the entries in processing order
 // Order of a list of n hits: sorted by class, the classes by ascending population, then dealt round robin to the n / 4 full
 // groups (hit at sorted position q < 4 (n / 4) -> group q mod (n / 4), k-lane q div (n / 4)): a group receives two hits of one
 // class only when that class holds more than n / 4 of the hits; the n mod 4 hits left over come from the most populous class.
@@ -179,13 +183,13 @@ __global__ void __launch_bounds__(256) k_hits_count(int ntiles, int G, int nslot
         if (lane == 0 && n) atomicAdd(&s_tot[q / nslots], n);          // integer: order independent
     }
     __syncthreads();
-    for (int g = threadIdx.x; g < G; g += blockDim.x) tg_count[(size_t)tile * G + g] = (s_tot[g] + 7) & ~7;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) tg_count[(size_t)tile * G + g] = (2 * (nslots + 4) + s_tot[g] + 7) & ~7;
 }
 
 __global__ void __launch_bounds__(256) k_hits_fill(int ntiles, int G, int nslots, const int32_t *__restrict__ tile_pt, int64_t ncon,
                                                    const uint64_t *__restrict__ pt_mask, const uint8_t *__restrict__ pt_slot0,
-                                                   const uint16_t *__restrict__ blk_jk, const int32_t *__restrict__ hit_ptr,
-                                                   uint32_t *__restrict__ hit_tab, uint16_t *__restrict__ hit_ent)
+                                                   const uint16_t *__restrict__ blk_jk, const int32_t *__restrict__ tile_r,
+                                                   const int32_t *__restrict__ hit_ptr, uint16_t *__restrict__ hit_blob)
 {
     extern __shared__ int s_n[];         // G * nslots: hits per slot, then offsets
     const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -214,7 +218,9 @@ __global__ void __launch_bounds__(256) k_hits_fill(int ntiles, int G, int nslots
     __syncthreads();
     for (int q = warp; q < nq; q += 8) {
         const uint32_t tb = (uint32_t)s_n[q];
-        if (lane == 0) hit_tab[(size_t)tile * nq + q] = tb;
+        uint16_t *rec = hit_blob + (size_t)hit_ptr[(size_t)tile * G + q / nslots];
+        if (lane == 0) reinterpret_cast<uint32_t *>(rec)[q % nslots] = tb;
+        if (lane == 1 && q % nslots == 0) reinterpret_cast<uint32_t *>(rec)[nslots] = (uint32_t)(tile_r[tile + 1] - tile_r[tile]);
         const int n = (int)((tb >> 16) & 0x7FFFu);
         if (!n) continue;
         const uint32_t jk = blk_jk[q];
@@ -237,25 +243,34 @@ __global__ void __launch_bounds__(256) k_hits_fill(int ntiles, int G, int nslots
             const int idx = (pos < 4 * F) ? 4 * (pos % F) + pos / F : pos;
             const uint32_t ra = h.slot0 + 4u * (uint32_t)__popcll(h.mask & ((1ull << j) - 1ull));
             const uint32_t rb = h.slot0 + 4u * (uint32_t)__popcll(h.mask & ((1ull << k) - 1ull));
-            hit_ent[(size_t)hit_ptr[(size_t)tile * G + q / nslots] + (tb & 0xFFFFu) + idx] = (uint16_t)(ra | (rb << 8));
+            rec[2 * (nslots + 4) + (tb & 0xFFFFu) + idx] = (uint16_t)(ra | (rb << 8));
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // The Schur kernel.  grid = (nchunk, G); NW consumer warps, each owning NB blocks; the copy producer is lane 0 of warp 0.
-// Dynamic shared memory: 2 stages of [Z tile: 12 chunk planes of (256 + 1) x 32 bytes | hit entries | hit table | sign bytes].
-// Row 256 of every plane is never written by the copies: it is the all-zero row the fourth k-lane of a left-over step reads.
+// Dynamic shared memory: 2 stages of [Z tile: 12 chunk planes of (nrows + 1) x 32 bytes | the (tile, group) record: table, entries |
+// sign bytes], filled by THREE bulk copies per tile (the copies are issued by one lane of a warp that also computes: with one
+// copy per plane that warp fell a whole tile behind the others, which then waited for it at every tile).  The metadata of the
+// next tile (first row, record bounds) reaches shared memory through cp.async, off that warp's critical path as well.
 // Spart[chunk][pair][256]: per-chunk partial sums in fragment order (lane * 8 + q), q = (ri*2 + ci)*2 + e for the
 // 8x8 sub-tile (ri, ci) of the block: element (row = ri*8 + lane>>2, col = ci*8 + 2*(lane&3) + e).
 // ---------------------------------------------------------------------------------------------------------------------------
+#ifdef ARGUS_SCHUR_TRACE
+// debug builds only (tools/schur_trace.py): per (CTA < 4, tile < 256, warp) clock64 stamps {wait begin, wait end, tile done, loads issued}
+__device__ long long *g_schur_trace = nullptr;
+#define ARGUS_TRACE(slot_) do { if (g_schur_trace && blockIdx.x < 2 && it < 256) \
+    g_schur_trace[((((size_t)(blockIdx.y * 2 + blockIdx.x) * 256 + it) * NW + warp) * 4) + (slot_)] = clock64(); } while (0)
+#else
+#define ARGUS_TRACE(slot_) do { } while (0)
+#endif
 constexpr int kSchurUnroll = 1;      // groups of four hits per trip of the inner loop
 constexpr bool kSchurDiagPath = false;   // a separate 9-DMMA code path for the diagonal blocks (j == k): fewer DMMAs for 16 of 136 blocks, twice the code
-constexpr uint32_t kPlaneBytes = (kTileRows + 1) * 32u;              // 8224: consecutive planes start 8 banks apart
-constexpr uint32_t kZBytes = 12u * kPlaneBytes;
+constexpr uint32_t kZBytes = 12u * (kTileRows + 1) * 32u;            // largest tile: 12 planes of 257 chunks
 __host__ __device__ constexpr uint32_t schur_ent_bytes(int nslots) { return (uint32_t)nslots * kTilePts * 2u; }
-__host__ __device__ constexpr uint32_t schur_tab_bytes(int nslots) { return ((uint32_t)nslots * 4u + 15u) & ~15u; }
-__host__ __device__ constexpr uint32_t schur_stage_bytes(int nslots) { return kZBytes + schur_ent_bytes(nslots) + schur_tab_bytes(nslots) + 256u; }
+__host__ __device__ constexpr uint32_t schur_tab_bytes(int nslots) { return ((uint32_t)nslots + 4u) * 4u; }        // table + the tile's row count, 16-byte multiple
+__host__ __device__ constexpr uint32_t schur_stage_bytes(int nslots) { return kZBytes + schur_tab_bytes(nslots) + schur_ent_bytes(nslots) + 16u + 256u; }
 
 // DIAG (compile time): a code path of its own for the diagonal blocks; skip_hl (run time, warp uniform): in the common path,
 // leave out the (rows 8-15) x (columns 0-7) sub-tile, which a diagonal block gets from its transpose (k_assemble_mma)
@@ -335,35 +350,47 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(TilePlan tp, SchurPlan
     const int g8 = lane >> 2, kk = lane & 3;
     const int chunk = blockIdx.x, grp = blockIdx.y;
     const int ntl = (tp.ntiles > chunk) ? (tp.ntiles - chunk + sp.nchunk - 1) / sp.nchunk : 0;   // tiles of this chunk
+    __shared__ __align__(16) int32_t s_meta[2][4];      // per tile: first Z row, first Z row of the next tile, record begin, record end
 
-    // the zero row (index 256) of every chunk plane of both stages
-    for (int t = threadIdx.x; t < 2 * 12 * 8; t += blockDim.x)
-        reinterpret_cast<uint32_t *>(smem_raw + (size_t)(t / 96) * kStage + (size_t)((t % 96) / 8) * kPlaneBytes + (size_t)kTileRows * 32u)[t % 8] = 0u;
     if (threadIdx.x == 0) { mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1); mbar_init(&mempty[0], NW); mbar_init(&mempty[1], NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
-    // producer duty (warp 0, lane 0): bulk-async copies of the tile's Z planes, hit entries, hit table and sign bytes into
-    // stage it & 1, after every warp has released that stage (mempty)
+    // producer duty (warp 0, lane 0): the tile's Z block, its (tile, group) record and its sign bytes into stage it & 1, after every
+    // warp has released that stage (mempty)
+    auto fetch_meta = [&](int it) {                      // asynchronous 4-byte copies: nothing to wait for now
+        const int t = chunk + it * sp.nchunk;
+        const uint32_t d = smem_u32(&s_meta[it & 1][0]);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(tp.tile_r + t) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u), "l"(tp.tile_r + t + 1) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 8u), "l"(sp.hit_ptr + (size_t)t * sp.G + grp) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 12u), "l"(sp.hit_ptr + (size_t)t * sp.G + grp + 1) : "memory");
+    };
     auto produce = [&](int it) {
         if (warp == 0 && lane == 0) {
             const int b = it & 1;
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            int4 mt;
+            asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(mt.x), "=r"(mt.y), "=r"(mt.z), "=r"(mt.w) : "r"(smem_u32(&s_meta[b][0])) : "memory");
+            if (it + 1 < ntl) fetch_meta(it + 1);
             if (it >= 2) mbar_wait(&mempty[b], (uint32_t)(((it >> 1) - 1) & 1));
             const int t = chunk + it * sp.nchunk;
-            const int r0 = tp.tile_r[t], nrows = tp.tile_r[t + 1] - r0;
-            const int32_t e0 = sp.hit_ptr[(size_t)t * sp.G + grp], e1 = sp.hit_ptr[(size_t)t * sp.G + grp + 1];
-            const uint32_t pl = (uint32_t)nrows * 32u, eb = (uint32_t)(e1 - e0) * 2u;
+            const uint32_t zb = (uint32_t)(mt.y - mt.x + 1) * 384u, rb = (uint32_t)(mt.w - mt.z) * 2u;
             unsigned char *dst = smem_raw + (size_t)b * kStage;
-            mbar_expect_tx(&mfull[b], 12u * pl + eb + kTab + 256u);
-            const char *src = reinterpret_cast<const char *>(Z + 48 * (int64_t)r0);
-            if (pl) for (uint32_t q = 0; q < 12u; ++q) bulk_g2s(dst + q * kPlaneBytes, src + (size_t)q * pl, pl, &mfull[b]);
-            if (eb) bulk_g2s(dst + kZBytes, sp.hit_ent + e0, eb, &mfull[b]);
-            bulk_g2s(dst + kZBytes + kEnt, sp.hit_tab + ((size_t)t * sp.G + grp) * kSlots, kTab, &mfull[b]);
-            bulk_g2s(dst + kZBytes + kEnt + kTab, zs + (size_t)t * 256, 256u, &mfull[b]);
+            mbar_expect_tx(&mfull[b], zb + rb + 256u);
+            bulk_g2s(dst, Z + 48 * ((int64_t)mt.x + t), zb, &mfull[b]);
+            bulk_g2s(dst + kZBytes, sp.hit_blob + mt.z, rb, &mfull[b]);
+            bulk_g2s(dst + kZBytes + kTab + kEnt + 16u, zs + (size_t)t * 256, 256u, &mfull[b]);
+#ifdef ARGUS_SCHUR_TRACE
+            if (g_schur_trace && blockIdx.x < 2 && it < 256) g_schur_trace[((((size_t)(blockIdx.y * 2 + blockIdx.x) * 256 + it) * NW + 0) * 4) + 3] = clock64();
+#endif
         }
         __syncwarp();
     };
-    if (ntl > 0) produce(0);
+    if (ntl > 0) {
+        if (warp == 0 && lane == 0) fetch_meta(0);
+        produce(0);
+    }
 
     double acc[NB][8];
 #pragma unroll
@@ -372,17 +399,23 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(TilePlan tp, SchurPlan
         for (int q = 0; q < 8; ++q) acc[b][q] = 0.0;
 
     const uint32_t smem_base = smem_u32(smem_raw);
-    // byte offset of the 16-byte element x = g8 * 3 + component of a row, relative to the row's slot in plane 0
-    auto elem_off = [&](int x) { return (uint32_t)(x >> 1) * kPlaneBytes + (uint32_t)(x & 1) * 16u; };
-    const uint32_t off0 = elem_off(g8 * 3), off1 = elem_off(g8 * 3 + 1), off2 = elem_off(g8 * 3 + 2);
-    const uint32_t offk = (kk == 1) ? off1 : (kk == 2) ? off2 : off0;
 
     for (int it = 0; it < ntl; ++it) {
         if (it + 1 < ntl) produce(it + 1);
         const int sb = it & 1;
+        if (lane == 0) ARGUS_TRACE(0);
         mbar_wait(&mfull[sb], (uint32_t)((it >> 1) & 1));
+        if (lane == 0) ARGUS_TRACE(1);
         const uint32_t zbase = smem_base + (uint32_t)sb * kStage;
-        const uint32_t ent_base = zbase + kZBytes, tab_base = ent_base + kEnt + (uint32_t)(warp * NB) * 4u, zs_addr = ent_base + kEnt + kTab;
+        const uint32_t tab_base = zbase + kZBytes, ent_base = tab_base + kTab, zs_addr = ent_base + kEnt + 16u;
+        // byte offset of the 16-byte element x = g8 * 3 + component of a row, relative to the row's slot in plane 0; a plane
+        // has one chunk per row of THIS tile plus one of padding
+        uint32_t pstride;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pstride) : "r"(tab_base + 4u * (uint32_t)kSlots));
+        pstride = (pstride + 1u) * 32u;
+        auto elem_off = [&](int x) { return (uint32_t)(x >> 1) * pstride + (uint32_t)(x & 1) * 16u; };
+        const uint32_t off0 = elem_off(g8 * 3), off1 = elem_off(g8 * 3 + 1), off2 = elem_off(g8 * 3 + 2);
+        const uint32_t offk = (kk == 1) ? off1 : (kk == 2) ? off2 : off0;
         uint32_t s0, s1;
         asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(s0), "=r"(s1) : "r"(zs_addr + 8u * (uint32_t)lane));
         const bool anyneg = __any_sync(0xffffffffu, (s0 | s1) != 0u);
@@ -390,7 +423,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(TilePlan tp, SchurPlan
 #define ARGUS_SCHUR_TILE(SIGNED_)                                                                                                   \
         _Pragma("unroll") for (int b = 0; b < NB; ++b) {                                                                            \
             uint32_t tb;                                                                                                            \
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tb) : "r"(tab_base + 4u * (uint32_t)b));                                  \
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tb) : "r"(tab_base + 4u * (uint32_t)(warp * NB + b)));                    \
             const int n = (int)((tb >> 16) & 0x7FFFu);                                                                              \
             if (n == 0) continue;                                                                                                   \
             const uint32_t ent_addr = ent_base + 2u * (tb & 0xFFFFu);                                                               \
@@ -400,6 +433,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(TilePlan tp, SchurPlan
         if (anyneg) { ARGUS_SCHUR_TILE(true) } else { ARGUS_SCHUR_TILE(false) }
 #undef ARGUS_SCHUR_TILE
         __syncwarp();
+        if (lane == 0) ARGUS_TRACE(2);
         if (lane == 0) mbar_arrive(&mempty[sb]);       // this warp is done with the stage
     }
 

@@ -139,7 +139,7 @@ struct argus_ba_ctx {
     // tile / MMA plan
     DevBuf<int32_t> tile_pt, tile_o, tile_r; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign, zs; DevBuf<double> Z;
     DevBuf<uint8_t> obs_lpt, corder, row_obs, pt_slot0, vmask_dev; DevBuf<int32_t> idx_btot;
-    DevBuf<uint32_t> hit_tab; DevBuf<uint16_t> hit_ent; DevBuf<int32_t> hit_ptr;     // static hit lists of the Schur kernel
+    DevBuf<uint16_t> hit_blob; DevBuf<int32_t> hit_ptr;     // static hit lists of the Schur kernel: one record per (tile, group)
     DevBuf<uint8_t> cam_fix; bool cam_fix_on = false; DevBuf<uint16_t> cstart;
     // wand pairs (extension, ba_wand.cuh); their buffers live outside the arena: argus_ba_set_wand comes after the upload
     int64_t wand_n = 0; double wand_w = 0.0; int wand_grid = 0, wand_chunks = 0;
@@ -164,7 +164,7 @@ struct argus_ba_ctx {
     TilePlan tile_plan() const { TilePlan tp; tp.ntiles = ntiles; tp.tile_pt = tile_pt.p; tp.tile_o = tile_o.p; tp.tile_r = tile_r.p; return tp; }
     SchurPlan schur_plan() const {
         SchurPlan sp; sp.G = schur_G; sp.nchunk = schur_nchunk; sp.npairs = npairs; sp.nslots = schur_NW * schur_NB; sp.blk_jk = blk_jk.p;
-        sp.blk_pair = blk_pair.p; sp.hit_tab = hit_tab.p; sp.hit_ent = hit_ent.p; sp.hit_ptr = hit_ptr.p;
+        sp.blk_pair = blk_pair.p; sp.hit_blob = hit_blob.p; sp.hit_ptr = hit_ptr.p;
         return sp;
     }
     LinTilePlan lin_plan() const { LinTilePlan lp; lp.obs_lpt = obs_lpt.p; lp.corder = corder.p; lp.cstart = cstart.p; lp.row_obs = row_obs.p; return lp; }
@@ -474,6 +474,10 @@ int global_counts(argus_ba_ctx *c, double out[3])
 
 extern "C" {
 
+#ifdef ARGUS_SCHUR_TRACE
+int argus_debug_set_schur_trace(long long *dev_ptr) { return cudaMemcpyToSymbol(g_schur_trace, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? 0 : -1; }
+#endif
+
 const char *argus_b200_version(void) { return "argus_b200 0.2 (sm_100a, fp64)"; }
 
 int argus_set_default_device(int device)
@@ -547,7 +551,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
                               &c->cam2, &c->scal, &c->respart, &c->Upart2, &c->cholwork, &c->Z};
     for (auto *b : bufs) b->release();
     c->obs_lpt.release(); c->corder.release(); c->row_obs.release(); c->pt_slot0.release(); c->tile_r.release(); c->zs.release();
-    c->hit_tab.release(); c->hit_ent.release(); c->hit_ptr.release(); c->cam_fix.release(); c->cstart.release(); c->vmask_dev.release();
+    c->hit_blob.release(); c->hit_ptr.release(); c->cam_fix.release(); c->cstart.release(); c->vmask_dev.release();
     c->idx_btot.release(); c->flags.release(); c->tile_pt.release(); c->tile_o.release(); c->blk_jk.release(); c->blk_pair.release();
     c->zsign.release(); c->st.release();
     c->wand_ia.release(); c->wand_ib.release(); c->wand_of.release(); c->wand_len.release(); c->wand_rec.release(); c->wand_Q.release(); c->wand_part.release();
@@ -695,9 +699,9 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         PLAN_ENS(c->blk_pair, hpair.size()); PLAN_ENS(c->pt_slot0, n); PLAN_ENS(c->row_obs, nrows); PLAN_ENS(c->zs, (size_t)c->ntiles * 256);
         PLAN_ENS(c->zsign, n);
         if (c->mode == kModeMotStr) {
-            PLAN_ENS(c->Z, 48 * nrows);
-            PLAN_ENS(c->hit_tab, (size_t)c->ntiles * hjk.size()); PLAN_ENS(c->hit_ptr, (size_t)c->ntiles * c->schur_G + 1);
-            PLAN_ENS(c->hit_ent, hits_bound + 8 * (int64_t)c->ntiles * c->schur_G + 8);
+            PLAN_ENS(c->Z, 48 * (nrows + c->ntiles));          // one padding chunk per plane and tile (z_index)
+            PLAN_ENS(c->hit_ptr, (size_t)c->ntiles * c->schur_G + 1);
+            PLAN_ENS(c->hit_blob, hits_bound + (2 * (int64_t)(c->schur_NW * c->schur_NB + 4) + 8) * c->ntiles * c->schur_G + 8);
         }
         PLAN_ENS(c->obs_lpt, nobs); PLAN_ENS(c->corder, nobs); PLAN_ENS(c->cstart, (size_t)c->ntiles * (m + 1));
         PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1024 + N + 32);
@@ -782,6 +786,9 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         const int nbins = c->schur_G * c->schur_NW, NBs = c->schur_NB;
         std::vector<double> load((size_t)nbins, 0.0);
         std::vector<std::vector<int>> bins((size_t)nbins);
+        // warp 0 of every CTA also issues the tile copies (about 1200 clocks per tile, measured with tools/schur_trace.py: the
+        // time of ~6 hits); without this head start the other warps wait for it at every tile
+        for (int q = 0; q < nbins; q += c->schur_NW) load[q] = 6.0 * (double)c->ntiles;
         for (int i = 0; i < (int)blks.size(); ++i) {
             int best = -1;
             for (int q = 0; q < nbins; ++q)
@@ -841,7 +848,9 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
                                                                          c->blk_jk.p, c->hit_ptr.p);
             k_index_scan<<<1, 1024, 0, s>>>(ntg, c->hit_ptr.p);
             k_hits_fill<<<c->ntiles, 256, (size_t)G * nslots * sizeof(int), s>>>(c->ntiles, G, nslots, c->tile_pt.p, ncon, c->pt_mask.p,
-                                                                               c->pt_slot0.p, c->blk_jk.p, c->hit_ptr.p, c->hit_tab.p, c->hit_ent.p);
+                                                                               c->pt_slot0.p, c->blk_jk.p, c->tile_r.p, c->hit_ptr.p, c->hit_blob.p);
+            // the padding chunks of Z travel to shared memory with every tile: keep them defined
+            ARGUS_CUDA_CHECK(cudaMemsetAsync(c->Z.p, 0, (size_t)48 * (nrows + c->ntiles) * sizeof(double), s));
         }
         ARGUS_CUDA_CHECK(cudaGetLastError());
     }
