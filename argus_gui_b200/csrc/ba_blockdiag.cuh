@@ -17,7 +17,7 @@ __global__ void k_bd_finalize(int mode, const double *__restrict__ Ured, ParamBu
                               const double *__restrict__ sum2, const double *__restrict__ max2, double *__restrict__ scal)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0 || st->done) return;
-    const double *cam = pbuf.cam[st->cur_cam];
+    const double *cam = pb_cam(pbuf, st->cur_cam);
     double inf = 0.0, dmax = 2.2250738585072014e-308 /* DBL_MIN */, psq = 0.0;
     if (mode == kModeMot) {
         for (int j = mcon; j < m; ++j) {
@@ -40,8 +40,8 @@ __global__ void __launch_bounds__(64) k_mot_solve(int m, int mcon, const double 
 {
     if (st->done) return;
     const double mu_diag = st->mu_u, mu = st->mu;
-    const double *cam = pbuf.cam[st->cur_cam];
-    double *cam_new = pbuf.cam[st->cur_cam ^ 1];
+    const double *cam = pb_cam(pbuf, st->cur_cam);
+    double *cam_new = pb_cam(pbuf, st->cur_cam ^ 1);
     __shared__ double s_d2[ARGUS_BA_MAX_CAMS], s_dl[ARGUS_BA_MAX_CAMS];
     __shared__ int s_ok[ARGUS_BA_MAX_CAMS];
     const int j = threadIdx.x;

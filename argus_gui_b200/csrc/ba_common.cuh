@@ -55,6 +55,9 @@ struct ParamBufs {
     double *cam[2];
     double *pts[2];
 };
+// selection by a run-time index through a conditional: indexing the kernel parameter itself would copy the table to local memory
+__device__ __forceinline__ double *pb_cam(const ParamBufs &b, int which) { return which ? b.cam[1] : b.cam[0]; }
+__device__ __forceinline__ double *pb_pts(const ParamBufs &b, int which) { return which ? b.pts[1] : b.pts[0]; }
 
 constexpr int kU = 152;       // per camera: 136 upper-triangle entries of U_j + 16 of ea_j
 

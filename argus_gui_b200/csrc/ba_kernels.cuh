@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(256) k_residual(BaProblem pb, ParamBufs pbuf, 
     CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);
     __shared__ double red[32];
     if (st->done) return;
-    const double *cam = pbuf.cam[st->cur_cam ^ trial_cam], *pts = pbuf.pts[st->cur_pts];
+    const double *cam = pb_cam(pbuf, st->cur_cam ^ trial_cam), *pts = pb_pts(pbuf, st->cur_pts);
     load_cameras(sc, cam, pb.rot0, pb.m);
     double acc = 0.0;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < pb.n; base += (int64_t)gridDim.x * blockDim.x) {
@@ -66,7 +66,7 @@ __global__ void k_lin_finalize(const double *__restrict__ Ured, ParamBufs pbuf, 
                                const double *__restrict__ sum2, const double *__restrict__ max2, double *__restrict__ scal)
 {
     if (blockIdx.x != 0 || threadIdx.x >= 32 || st->done) return;
-    const double *cam = pbuf.cam[st->cur_cam];
+    const double *cam = pb_cam(pbuf, st->cur_cam);
     const int lane = threadIdx.x;
     double inf = 0.0, dmax = 2.2250738585072014e-308 /* DBL_MIN, sba_levmar.c:982 */, psq = 0.0;
     for (int t = mcon * 16 + lane; t < m * 16; t += 32) {           // one (camera, parameter) per lane and pass
@@ -277,8 +277,8 @@ __global__ void k_cam_update(int m, int mcon, ParamBufs pbuf, const LmState *__r
 {
     __shared__ double red[32];
     if (st->done) return;
-    const double *cam = pbuf.cam[st->cur_cam];
-    double *cam_new = pbuf.cam[st->cur_cam ^ 1];
+    const double *cam = pb_cam(pbuf, st->cur_cam);
+    double *cam_new = pb_cam(pbuf, st->cur_cam ^ 1);
     const double mu = st->mu;
     double s0 = 0.0, s1 = 0.0;
     for (int t = threadIdx.x; t < 16 * m; t += blockDim.x) {

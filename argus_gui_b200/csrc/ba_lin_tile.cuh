@@ -23,10 +23,12 @@ constexpr int kUfrag = 320;      // per camera: 5 DMMA tiles x 64 fragment eleme
 constexpr int kPs = 16;          // per point scratch: li[3], sq[3], c[3], sign, free
 
 struct LinTilePlan {
-    const uint8_t *obs_lpt;      // nobs: local point index of each observation inside its tile
     const uint8_t *corder;       // nobs: per tile, local observation indices sorted by camera
     const uint16_t *cstart;      // ntiles x (m+1): start of each camera's run in corder (local)
-    const uint8_t *row_obs;      // Z rows: local observation index held by each row of a tile's Z block, 0xFF = unused row
+    const uint32_t *row_info;    // Z rows: what the row of a tile's Z block holds - local observation index | camera << 8 | local point << 16,
+                                 // 0xFFFFFFFF = unused row
+    const double2 *row_uv;       // Z rows: the measured pixel of that observation (a row-ordered copy of obs_uv: the tile kernel's
+                                 // per-row inputs are then two independent, coalesced loads)
 };
 
 struct LinTileOut {
@@ -126,14 +128,14 @@ __global__ void __launch_bounds__(256) k_index_fill(int64_t n, const uint64_t *_
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 255) obs_ptr[n] = k;     // last thread of the last block ends at the grand total
 }
 
-// per tile: local point index of every observation, camera-sorted (stable) observation order, the camera run starts, and which
-// observation every row of the tile's Z block holds: the observation of rank r of a point sits in row pt_slot0[point] + 4 r
-// (ba_schur_mma.cuh: four classes of points, rows 4 i + class); row_obs is pre-filled with 0xFF (unused row)
+// per tile: camera-sorted (stable) observation order, the camera run starts, and what every row of the tile's Z block holds: the
+// observation of rank r of a point sits in row pt_slot0[point] + 4 r (ba_schur_mma.cuh: four classes of points, rows 4 i + class);
+// row_info is pre-filled with 0xFF bytes (unused row)
 __global__ void __launch_bounds__(256) k_build_tile_index(int m, const int32_t *__restrict__ tile_pt, const int32_t *__restrict__ tile_o,
                                                           const int32_t *__restrict__ tile_r, const int32_t *__restrict__ obs_ptr,
-                                                          const uint8_t *__restrict__ obs_cam, const uint8_t *__restrict__ pt_slot0,
-                                                          uint8_t *__restrict__ obs_lpt, uint8_t *__restrict__ corder,
-                                                          uint16_t *__restrict__ cstart, uint8_t *__restrict__ row_obs)
+                                                          const uint8_t *__restrict__ obs_cam, const double2 *__restrict__ obs_uv,
+                                                          const uint8_t *__restrict__ pt_slot0, uint8_t *__restrict__ corder,
+                                                          uint16_t *__restrict__ cstart, uint32_t *__restrict__ row_info, double2 *__restrict__ row_uv)
 {
     __shared__ int s_pofs[kTilePts + 1];
     __shared__ uint8_t s_cam[256];
@@ -148,8 +150,9 @@ __global__ void __launch_bounds__(256) k_build_tile_index(int m, const int32_t *
     if (tid < nobs_t) {
         int lp = 0;
         while (lp + 1 < npts && tid >= s_pofs[lp + 1]) ++lp;
-        obs_lpt[o0 + tid] = (uint8_t)lp;
-        row_obs[(size_t)tile_r[tile] + pt_slot0[p0 + lp] + 4 * (tid - s_pofs[lp])] = (uint8_t)tid;
+        const size_t row = (size_t)tile_r[tile] + pt_slot0[p0 + lp] + 4 * (tid - s_pofs[lp]);
+        row_info[row] = (uint32_t)tid | ((uint32_t)s_cam[tid] << 8) | ((uint32_t)lp << 16);
+        row_uv[row] = obs_uv[o0 + tid];
         atomicAdd(&s_cnt[s_cam[tid] + 1], 1);               // integer histogram: order-independent
     }
     __syncthreads();
@@ -177,8 +180,8 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                                                   const LmState *__restrict__ st, int mode, LinTileOut out)
 {
     if (st->done) return;
-    const double *__restrict__ cam = pbuf.cam[st->cur_cam];
-    const double *__restrict__ pts = pbuf.pts[st->cur_pts];
+    const double *__restrict__ cam = st->cur_cam ? pbuf.cam[1] : pbuf.cam[0];      // (a run-time index would put the pointer table in local memory)
+    const double *__restrict__ pts = st->cur_pts ? pbuf.pts[1] : pbuf.pts[0];
     const double mu = st->mu;
     const int use_state = st->use_state, write_state = st->write_state;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -223,13 +226,10 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
         // the tile's index data and points -> shared memory (the previous tile ended with a barrier).  In the per-observation
         // phases P1 and P3 a thread is a ROW of the tile's Z block (so that the Z stores of a warp are consecutive 32-byte
         // chunks); li is the observation that row holds - the index everything in shared memory is keyed by
-        double2 z = make_double2(0.0, 0.0); int my_cam = 0, my_lp = 0, li = 0xFF;
-        if (tid < nrows_t) li = lp.row_obs[(size_t)r0 + tid];
-        const bool act = li != 0xFF;
-        if (act) {
-            const int k = o0 + li;
-            z = pb.obs_uv[k]; my_cam = pb.obs_cam[k]; my_lp = lp.obs_lpt[k];
-        }
+        double2 z = make_double2(0.0, 0.0); uint32_t info = 0xFFFFFFFFu;
+        if (tid < nrows_t) { info = lp.row_info[(size_t)r0 + tid]; z = lp.row_uv[(size_t)r0 + tid]; }
+        const bool act = info != 0xFFFFFFFFu;
+        const int li = (int)(info & 0xFFu), my_cam = (int)((info >> 8) & 0xFFu), my_lp = (int)((info >> 16) & 0xFFu);
         if (tid < nobs_t) s_cord[tid] = lp.corder[o0 + tid];
         if (tid <= npts) s_pofs[tid] = pb.obs_ptr[p0 + tid] - o0;
         if (tid < npts) { const int64_t i = p0 + tid; s_M[3 * tid] = pts[3 * i]; s_M[3 * tid + 1] = pts[3 * i + 1]; s_M[3 * tid + 2] = pts[3 * i + 2]; }
@@ -271,12 +271,10 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             *reinterpret_cast<double2 *>(b + 6) = make_double2(e0, e1);
         }
         if (ntile < tp.ntiles) {      // L2 prefetch of the next tile's inputs (one request per 128-byte line)
-            const int no = nx_o1 - nx_o0, np = nx_p1 - nx_p0;
-            if ((tid & 7) == 0 && tid < no) prefetch_l2(pb.obs_uv + nx_o0 + tid);
-            if (tid < 3 && tid * 128 < no + 127) {
-                prefetch_l2(pb.obs_cam + nx_o0 + tid * 128); prefetch_l2(lp.obs_lpt + nx_o0 + tid * 128); prefetch_l2(lp.corder + nx_o0 + tid * 128);
-                prefetch_l2(lp.row_obs + nx_r0 + tid * 128);
-            }
+            const int no = nx_o1 - nx_o0, np = nx_p1 - nx_p0, nr = nx_r1 - nx_r0;
+            if ((tid & 7) == 0 && tid < nr) prefetch_l2(lp.row_uv + nx_r0 + tid);
+            if ((tid & 31) == 0 && tid < nr) prefetch_l2(lp.row_info + nx_r0 + tid);
+            if (tid < 3 && tid * 128 < no + 127) prefetch_l2(lp.corder + nx_o0 + tid * 128);
             if (tid >= 32 && tid < 40 && (tid - 32) * 16 < 3 * np + 15) prefetch_l2(pts + 3 * (int64_t)nx_p0 + (tid - 32) * 16);
             if (tid == 64) { prefetch_l2(pb.obs_ptr + nx_p0); prefetch_l2(pb.obs_ptr + nx_p0 + 31); prefetch_l2(lp.cstart + (size_t)ntile * (pb.m + 1)); }
         }
@@ -500,10 +498,11 @@ __global__ void __launch_bounds__(128) k_backsub_recompute(BaProblem pb, ParamBu
 {
     if (st->done) return;
     const double mu = st->mu;
-    const double *__restrict__ cam = pbuf.cam[st->cur_cam];
-    const double *__restrict__ cam_new = pbuf.cam[st->cur_cam ^ (cam_moves ? 1 : 0)];
-    const double *__restrict__ pts = pbuf.pts[st->cur_pts];
-    double *__restrict__ pts_new = pbuf.pts[st->cur_pts ^ 1];
+    const int ccur = st->cur_cam, pcur = st->cur_pts;
+    const double *__restrict__ cam = ccur ? pbuf.cam[1] : pbuf.cam[0];
+    const double *__restrict__ cam_new = (ccur ^ (cam_moves ? 1 : 0)) ? pbuf.cam[1] : pbuf.cam[0];
+    const double *__restrict__ pts = pcur ? pbuf.pts[1] : pbuf.pts[0];
+    double *__restrict__ pts_new = pcur ? pbuf.pts[0] : pbuf.pts[1];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);          // old cameras
     CamConst *sn = sc + pb.m;                                        // trial cameras

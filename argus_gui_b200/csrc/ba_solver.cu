@@ -138,7 +138,7 @@ struct argus_ba_ctx {
     double *lmlog = nullptr;          // device, verbose > 1 only
     // tile / MMA plan
     DevBuf<int32_t> tile_pt, tile_o, tile_r; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign, zs; DevBuf<double> Z;
-    DevBuf<uint8_t> obs_lpt, corder, row_obs, pt_slot0, vmask_dev; DevBuf<int32_t> idx_btot;
+    DevBuf<uint8_t> corder, pt_slot0, vmask_dev; DevBuf<int32_t> idx_btot; DevBuf<uint32_t> row_info; DevBuf<double2> row_uv;
     DevBuf<uint16_t> hit_blob; DevBuf<int32_t> hit_ptr;     // static hit lists of the Schur kernel: one record per (tile, group)
     DevBuf<uint8_t> cam_fix; bool cam_fix_on = false; DevBuf<uint16_t> cstart;
     // wand pairs (extension, ba_wand.cuh); their buffers live outside the arena: argus_ba_set_wand comes after the upload
@@ -167,7 +167,7 @@ struct argus_ba_ctx {
         sp.blk_pair = blk_pair.p; sp.hit_blob = hit_blob.p; sp.hit_ptr = hit_ptr.p;
         return sp;
     }
-    LinTilePlan lin_plan() const { LinTilePlan lp; lp.obs_lpt = obs_lpt.p; lp.corder = corder.p; lp.cstart = cstart.p; lp.row_obs = row_obs.p; return lp; }
+    LinTilePlan lin_plan() const { LinTilePlan lp; lp.corder = corder.p; lp.cstart = cstart.p; lp.row_info = row_info.p; lp.row_uv = row_uv.p; return lp; }
     LinTileOut lin_out() {
         LinTileOut o; o.Z = Z.p; o.zs = zs.p; o.zsign = zsign.p; o.Vinv = Vinv.p; o.V = V.p; o.eb = eb.p; o.vstate = vstate.p; o.Upart = Upart2.p;
         o.scpart = scpart.p; o.flag = flags.p; return o;
@@ -550,7 +550,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
                               &c->dbuf, &c->scpart, &c->red12, &c->max2, &c->Spart, &c->S, &c->E, &c->da_free, &c->da_full, &c->part3, &c->att3,
                               &c->cam2, &c->scal, &c->respart, &c->Upart2, &c->cholwork, &c->Z};
     for (auto *b : bufs) b->release();
-    c->obs_lpt.release(); c->corder.release(); c->row_obs.release(); c->pt_slot0.release(); c->tile_r.release(); c->zs.release();
+    c->corder.release(); c->row_info.release(); c->row_uv.release(); c->pt_slot0.release(); c->tile_r.release(); c->zs.release();
     c->hit_blob.release(); c->hit_ptr.release(); c->cam_fix.release(); c->cstart.release(); c->vmask_dev.release();
     c->idx_btot.release(); c->flags.release(); c->tile_pt.release(); c->tile_o.release(); c->blk_jk.release(); c->blk_pair.release();
     c->zsign.release(); c->st.release();
@@ -679,7 +679,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         if (nch > c->ntiles) nch = c->ntiles > 0 ? c->ntiles : 1;
         c->schur_nchunk = nch;
     }
-    // obs_lpt, corder, cstart, row_obs and the hit lists are derived on the device (k_index_*, k_build_tile_index, k_hits_*)
+    // corder, cstart, row_info / row_uv and the hit lists are derived on the device (k_index_*, k_build_tile_index, k_hits_*)
     c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)kTileRows * (kGa + kBs) * sizeof(double) +
                   (size_t)kTilePts * kPs * sizeof(double);
     {
@@ -696,14 +696,14 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
 #define PLAN_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return e_; } while (0)
 #define PLAN_ENS(buf, cnt_) PLAN_CHECK((buf).ensure((size_t)(cnt_)))
         PLAN_ENS(c->tile_pt, tiles.size()); PLAN_ENS(c->tile_o, tiles.size()); PLAN_ENS(c->tile_r, tiles.size()); PLAN_ENS(c->blk_jk, hjk.size());
-        PLAN_ENS(c->blk_pair, hpair.size()); PLAN_ENS(c->pt_slot0, n); PLAN_ENS(c->row_obs, nrows); PLAN_ENS(c->zs, (size_t)c->ntiles * 256);
+        PLAN_ENS(c->blk_pair, hpair.size()); PLAN_ENS(c->pt_slot0, n); PLAN_ENS(c->row_info, nrows); PLAN_ENS(c->row_uv, nrows); PLAN_ENS(c->zs, (size_t)c->ntiles * 256);
         PLAN_ENS(c->zsign, n);
         if (c->mode == kModeMotStr) {
             PLAN_ENS(c->Z, 48 * (nrows + c->ntiles));          // one padding chunk per plane and tile (z_index)
             PLAN_ENS(c->hit_ptr, (size_t)c->ntiles * c->schur_G + 1);
             PLAN_ENS(c->hit_blob, hits_bound + (2 * (int64_t)(c->schur_NW * c->schur_NB + 4) + 8) * c->ntiles * c->schur_G + 8);
         }
-        PLAN_ENS(c->obs_lpt, nobs); PLAN_ENS(c->corder, nobs); PLAN_ENS(c->cstart, (size_t)c->ntiles * (m + 1));
+        PLAN_ENS(c->corder, nobs); PLAN_ENS(c->cstart, (size_t)c->ntiles * (m + 1));
         PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1024 + N + 32);
         PLAN_ENS(c->vmask_dev, n * m); PLAN_ENS(c->idx_btot, (n + kIdxPts - 1) / kIdxPts + 1);
         PLAN_ENS(c->obs_ptr, n + 1); PLAN_ENS(c->obs_cam, nobs); PLAN_ENS(c->obs_uv, nobs); PLAN_ENS(c->pt_mask, n);
@@ -838,10 +838,11 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     }
     // derived static indices, built on the device
     if (n > 0 && c->ntiles > 0) {
-        ARGUS_CUDA_CHECK(cudaMemsetAsync(c->row_obs.p, 0xFF, (size_t)nrows, s));
+        ARGUS_CUDA_CHECK(cudaMemsetAsync(c->row_info.p, 0xFF, (size_t)nrows * sizeof(uint32_t), s));
+        ARGUS_CUDA_CHECK(cudaMemsetAsync(c->row_uv.p, 0, (size_t)nrows * sizeof(double2), s));
         ARGUS_CUDA_CHECK(cudaMemsetAsync(c->zs.p, 0, (size_t)c->ntiles * 256, s));
-        k_build_tile_index<<<c->ntiles, 256, 0, s>>>(m, c->tile_pt.p, c->tile_o.p, c->tile_r.p, c->obs_ptr.p, c->obs_cam.p, c->pt_slot0.p,
-                                                     c->obs_lpt.p, c->corder.p, c->cstart.p, c->row_obs.p);
+        k_build_tile_index<<<c->ntiles, 256, 0, s>>>(m, c->tile_pt.p, c->tile_o.p, c->tile_r.p, c->obs_ptr.p, c->obs_cam.p, c->obs_uv.p, c->pt_slot0.p,
+                                                     c->corder.p, c->cstart.p, c->row_info.p, c->row_uv.p);
         if (c->mode == kModeMotStr) {
             const int G = c->schur_G, nslots = c->schur_NW * c->schur_NB, ntg = c->ntiles * G;
             k_hits_count<<<c->ntiles, 256, (size_t)G * sizeof(int), s>>>(c->ntiles, G, nslots, c->tile_pt.p, ncon, c->pt_mask.p, c->pt_slot0.p,

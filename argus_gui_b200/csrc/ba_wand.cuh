@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kWandThreads) k_wand_cost(WandPlan wp, ParamBu
 {
     __shared__ double red[32];
     if (st->done) return;
-    const double *pts = pbuf.pts[st->cur_pts];
+    const double *pts = pb_pts(pbuf, st->cur_pts);
     double acc = 0.0;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < wp.npairs; p += (int64_t)gridDim.x * blockDim.x) {
         const WandGeom g = wand_geom(pts, wp.ia[p], wp.ib[p], wp.len[p], wp.w);
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(kWandThreads) k_wand_prepare(BaProblem pb, Wan
     CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);
     __shared__ double red[32];
     if (st->done) return;
-    const double *cam = pbuf.cam[st->cur_cam], *pts = pbuf.pts[st->cur_pts];
+    const double *cam = pb_cam(pbuf, st->cur_cam), *pts = pb_pts(pbuf, st->cur_pts);
     load_cameras(sc, cam, pb.rot0, pb.m);
     double cost = 0.0, ebmax = 0.0, vdmax = -1.79769313486231570e308;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < wp.npairs; p += (int64_t)gridDim.x * blockDim.x) {
@@ -270,10 +270,10 @@ __global__ void __launch_bounds__(kWandThreads) k_wand_backsub(BaProblem pb, Wan
 {
     if (st->done) return;
     const double mu = st->mu;
-    const double *__restrict__ cam = pbuf.cam[st->cur_cam];
-    const double *__restrict__ cam_new = pbuf.cam[st->cur_cam ^ 1];
-    const double *__restrict__ pts = pbuf.pts[st->cur_pts];
-    double *__restrict__ pts_new = pbuf.pts[st->cur_pts ^ 1];
+    const double *__restrict__ cam = pb_cam(pbuf, st->cur_cam);
+    const double *__restrict__ cam_new = pb_cam(pbuf, st->cur_cam ^ 1);
+    const double *__restrict__ pts = pb_pts(pbuf, st->cur_pts);
+    double *__restrict__ pts_new = pb_pts(pbuf, st->cur_pts ^ 1);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);
     CamConst *sn = sc + pb.m;
