@@ -47,6 +47,7 @@ SIGNATURES = {
     "argus_nccl_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
     "argus_ba_comm_init_nccl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "argus_ba_set_comm_nccl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "argus_ba_get_comm_nccl": (ctypes.c_void_p, [ctypes.c_void_p]),
     "argus_ba_set_graph": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "argus_ba_upload": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),

@@ -97,6 +97,19 @@ class BundleAdjuster:
         _lib.check(self.lib.argus_ba_comm_init_nccl(self.h, int(rank), int(world), _ptr(uid)), "argus_ba_comm_init_nccl")
         return self
 
+    def nccl_comm(self):
+        """The NCCL communicator of this context (an opaque handle) or None."""
+        return self.lib.argus_ba_get_comm_nccl(self.h)
+
+    def share_nccl(self, other, rank, world):
+        """Use the communicator of another BundleAdjuster of this process (which must outlive this one): no second
+        ncclCommInitRank."""
+        comm = other.nccl_comm()
+        if not comm:
+            raise RuntimeError("the other context has no NCCL communicator")
+        _lib.check(self.lib.argus_ba_set_comm_nccl(self.h, int(rank), int(world), ctypes.c_void_p(comm)), "argus_ba_set_comm_nccl")
+        return self
+
     def set_graph(self, on):
         _lib.check(self.lib.argus_ba_set_graph(self.h, 1 if on else 0), "argus_ba_set_graph")
 

@@ -451,14 +451,16 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
 
 // Fixed-order reduction of the per-CTA Gram fragments into the packed per-camera layout the rest of the solver uses:
 //   Ured[j][0..135] upper triangle of U_j, [136..151] ea_j;  Eout[j][0..15] = E_j (= sum A^T e').
-// Also reduces the nparts_sc scalar partials: sum2 = {cost, sum pts^2}, max2 = {max|eb|, max diag V}.  grid = m blocks of 192.
-__global__ void __launch_bounds__(192) k_lin_tile_reduce(int m, int nparts, int nparts_sc, const double *__restrict__ Upart, const double *__restrict__ scpart,
-                                                         double *__restrict__ Ured, double *__restrict__ Eout, double *__restrict__ sum2,
-                                                         double *__restrict__ max2, const int *__restrict__ done)
+// Also reduces the nparts_sc scalar partials: sum2 = {cost, sum pts^2}, max2 = {max|eb|, max diag V}.  grid = m blocks of 1024.
+constexpr int kLinRedSlices = 6;      // 6 x 168 = 1008 threads: every output element is summed by 6 threads over interleaved partials
+__global__ void __launch_bounds__(1024) k_lin_tile_reduce(int m, int nparts, int nparts_sc, const double *__restrict__ Upart, const double *__restrict__ scpart,
+                                                          double *__restrict__ Ured, double *__restrict__ Eout, double *__restrict__ sum2,
+                                                          double *__restrict__ max2, const int *__restrict__ done)
 {
-    const int j = blockIdx.x, t = threadIdx.x;
+    __shared__ double s_part[kLinRedSlices][168];
+    const int j = blockIdx.x, t = threadIdx.x % 168, slice = threadIdx.x / 168;
     if (*done) return;
-    if (t < 168) {
+    if (slice < kLinRedSlices) {
         // element -> (tile, row, col) of the 24-column Gram matrix
         int r, c;
         if (t < 136) { r = 0; int q = t; while (q >= 16 - r) { q -= 16 - r; ++r; } c = r + q; }
@@ -472,11 +474,18 @@ __global__ void __launch_bounds__(192) k_lin_tile_reduce(int m, int nparts, int 
         const int idx = ln * 10 + tl * 2 + (cc & 1);
         double s = 0.0;
         const double *p = Upart + (size_t)j * kUfrag + idx;
-        for (int q = 0; q < nparts; ++q) s += p[(size_t)q * m * kUfrag];
+        for (int q = slice; q < nparts; q += kLinRedSlices) s += p[(size_t)q * m * kUfrag];       // fixed order inside a slice
+        s_part[slice][t] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < 168) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < kLinRedSlices; ++q) s += s_part[q][t];                                // and over the slices
         if (t < 152) Ured[j * kU + t] = s; else Eout[j * 16 + (t - 152)] = s;
     }
-    if (j == 0 && t >= 168 && t < 172) {
-        const int w = t - 168;
+    if (j == 0 && threadIdx.x >= 1008 && threadIdx.x < 1012) {
+        const int w = threadIdx.x - 1008;
         double s = (w == 1) ? 0.0 : ((w == 2) ? -1.79769313486231570e308 : 0.0);
         for (int q = 0; q < nparts_sc; ++q) {              // nparts_sc >= nparts: the wand kernel's partials follow the tile kernel's
             const double v = scpart[4 * q + w];

@@ -280,7 +280,7 @@ int enqueue_lin(argus_ba_ctx *c, int mode)
     }
     {
         ProfScope ps(c, P_LIN_REDUCE);
-        k_lin_tile_reduce<<<m, 192, 0, c->stream>>>(m, c->grid_lin, c->grid_lin + c->wand_grid, c->Upart2.p, c->scpart.p, c->red1, c->red2 + (int64_t)c->npairs * 256,
+        k_lin_tile_reduce<<<m, 1024, 0, c->stream>>>(m, c->grid_lin, c->grid_lin + c->wand_grid, c->Upart2.p, c->scpart.p, c->red1, c->red2 + (int64_t)c->npairs * 256,
                                                    c->red1 + (int64_t)m * kU, c->max2.p, c->done_ptr());
     }
     c->launches += 2;
@@ -583,6 +583,8 @@ int argus_nccl_unique_id(void *out128)
     memcpy(out128, &id, sizeof(id));
     return ARGUS_OK;
 }
+
+void *argus_ba_get_comm_nccl(const argus_ba_ctx *c) { return c ? (void *)c->nccl : nullptr; }
 
 int argus_ba_set_comm_nccl(argus_ba_ctx *c, int rank, int world, void *nccl_comm)
 {

@@ -582,7 +582,8 @@ def main():
                 pe, ie, re_ = ba.solve_motstr(hv, hp, rot0, hx, nk, nd, itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK, inplace=True)
             else:
                 with torch.cuda.stream(stream):
-                    Be = new_adjuster()
+                    Be = ba.BundleAdjuster(device=local, stream=stream.cuda_stream)
+                    Be.share_nccl(B, rank, world)          # the process keeps ONE communicator; creating one is not part of a solve
                     Be.set_graph(False)
                     Be.upload(hv, hp, rot0, hx, nk, nd)
                     re_, ie = Be.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
@@ -596,7 +597,7 @@ def main():
         e2e = {"value": total_obs * ITERS_PER_STEP * n_e2e / float(dt.item()), "unit": "obs*iters/s",
                "h2d_bytes_per_step": per_step_h2d, "d2h_bytes_per_step": int(8 * (16 * m + 3 * n_l)), "steps": n_e2e,
                "bytes": "per rank", "api": "argus_ba_motstr_kdrts (host pointers: alloc + index build + H2D + %d LM iterations + D2H)" % ITERS_PER_STEP
-               if world == 1 else "argus_ba_create + comm_init_nccl + upload + solve + download + destroy per step, pinned host buffers"}
+               if world == 1 else "argus_ba_create + set_comm_nccl (the process's communicator) + upload + solve + download + destroy per step, pinned host buffers"}
 
     # ---- roofline of the dominant kernel (CUDA events on the launching stream, inside the timed region) ----
     kern = {k_: v for k_, v in prof.items() if v[1] > 0 and k_ != "allreduce"}

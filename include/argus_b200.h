@@ -111,6 +111,9 @@ void argus_ba_destroy(argus_ba_ctx *ctx);
 int  argus_nccl_unique_id(void *out128);
 int  argus_ba_comm_init_nccl(argus_ba_ctx *ctx, int rank, int world, const void *unique_id128);
 int  argus_ba_set_comm_nccl(argus_ba_ctx *ctx, int rank, int world, void *nccl_comm);
+/* the context's communicator (created by argus_ba_comm_init_nccl or adopted), so that further contexts of the same process
+ * can share it through argus_ba_set_comm_nccl instead of paying ncclCommInitRank again; NULL if none */
+void *argus_ba_get_comm_nccl(const argus_ba_ctx *ctx);
 int  argus_ba_set_comm(argus_ba_ctx *ctx, int rank, int world, argus_allreduce_fn fn, void *user);
 /* a damping attempt is replayed as a CUDA graph from the first solve after an upload (default on); 0 launches kernel by kernel */
 int  argus_ba_set_graph(argus_ba_ctx *ctx, int on);
