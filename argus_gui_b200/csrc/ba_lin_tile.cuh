@@ -484,14 +484,17 @@ __global__ void __launch_bounds__(1024) k_lin_tile_reduce(int m, int nparts, int
         for (int q = 0; q < kLinRedSlices; ++q) s += s_part[q][t];                                // and over the slices
         if (t < 152) Ured[j * kU + t] = s; else Eout[j * 16 + (t - 152)] = s;
     }
-    if (j == 0 && threadIdx.x >= 1008 && threadIdx.x < 1012) {
-        const int w = threadIdx.x - 1008;
-        double s = (w == 1) ? 0.0 : ((w == 2) ? -1.79769313486231570e308 : 0.0);
-        for (int q = 0; q < nparts_sc; ++q) {              // nparts_sc >= nparts: the wand kernel's partials follow the tile kernel's
-            const double v = scpart[4 * q + w];
-            if (w == 1 || w == 2) s = fmax(s, v); else s += v;
+    if (j == 0 && threadIdx.x >= 992) {                  // the last warp: scalar partials, lanes interleaved over the parts, fixed-order tree
+        const int lane = threadIdx.x - 992;
+        double c0 = 0.0, c3 = 0.0, m1 = 0.0, m2 = -1.79769313486231570e308;
+        for (int q = lane; q < nparts_sc; q += 32) {        // nparts_sc >= nparts: the wand kernel's partials follow the tile kernel's
+            c0 += scpart[4 * q]; m1 = fmax(m1, scpart[4 * q + 1]); m2 = fmax(m2, scpart[4 * q + 2]); c3 += scpart[4 * q + 3];
         }
-        if (w == 0) sum2[0] = s; else if (w == 3) sum2[1] = s; else if (w == 1) max2[0] = s; else max2[1] = s;
+        for (int o = 16; o > 0; o >>= 1) {
+            c0 += __shfl_xor_sync(0xffffffffu, c0, o); c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+            m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o)); m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        }
+        if (lane == 0) { sum2[0] = c0; sum2[1] = c3; max2[0] = m1; max2[1] = m2; }
     }
 }
 

@@ -273,9 +273,15 @@ int enqueue_lin(argus_ba_ctx *c, int mode)
         if (mc <= 2) LIN_LAUNCH(2); else if (mc <= 4) LIN_LAUNCH(4); else LIN_LAUNCH(8);
 #undef LIN_LAUNCH
         if (c->wand_n > 0) {
-            k_wand_prepare<<<c->wand_grid, kWandThreads, cam_smem(m), c->stream>>>(c->problem(), c->wand_plan(), c->pbufs(), c->st.p, mode, c->V.p, c->eb.p,
-                                                                                   c->Vinv.p, c->scpart.p + 4 * (size_t)c->grid_lin);
+            k_wand_prepare<<<c->wand_grid, kWandThreads, 0, c->stream>>>(c->problem(), c->wand_plan(), c->pbufs(), c->st.p, mode, c->V.p, c->eb.p,
+                                                                         c->Vinv.p, c->scpart.p + 4 * (size_t)c->grid_lin);
             c->launches += 1;
+            if (mode != 0) {
+                const int64_t work = c->wand_n * (m - c->mcon);
+                const int gq = (int)std::min<int64_t>((work + 127) / 128, (int64_t)c->sms * 16);
+                k_wand_q<<<gq, 128, cam_smem(m), c->stream>>>(c->problem(), c->wand_plan(), c->pbufs(), c->st.p);
+                c->launches += 1;
+            }
         }
     }
     {
@@ -347,7 +353,8 @@ int enqueue_attempt_motstr(argus_ba_ctx *c, bool controller, double *dbout)
         k_reduce_sum<<<(unsigned)((slen + 127) / 128), 128, 0, s>>>(c->Spart.p, c->schur_nchunk, slen, slen, c->red2, done);
         if (c->wand_n > 0) {     // rank-one corrections of the wand pairs: Schur sums -= sigma q q^T, E -= beta q
             const int64_t wlen = slen + 16 * m;
-            k_wand_schur<<<dim3(c->npairs + 1, c->wand_chunks), 256, 0, s>>>(c->problem(), c->wand_plan(), mf, c->st.p, c->wand_part.p);
+            k_wand_schur<<<dim3((c->npairs + kWandBlocks - 1) / kWandBlocks, c->wand_chunks), 256, wand_schur_smem(m), s>>>(c->problem(), c->wand_plan(), mf,
+                                                                                                                          c->st.p, c->wand_part.p);
             k_wand_apply<<<(unsigned)((wlen + 255) / 256), 256, 0, s>>>(c->npairs, m, c->wand_chunks, c->wand_part.p, c->red2, done);
             c->launches += 2;
         }
@@ -527,6 +534,7 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)schur_stage_bytes(24));
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)schur_stage_bytes(40));
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<6, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)schur_stage_bytes(72));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wand_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wand_schur_smem(64));
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
@@ -904,7 +912,8 @@ int argus_ba_set_wand(argus_ba_ctx *c, int64_t npairs, const int64_t *ia, const 
         of[a] = (int32_t)p; of[b] = (int32_t)p; ha[p] = (int32_t)a; hb[p] = (int32_t)b;
     }
     const int grid = (int)std::min<int64_t>(kWandGridMax, (npairs + kWandThreads - 1) / kWandThreads);
-    const int chunks = (int)std::min<int64_t>(128, (npairs + 255) / 256);
+    const int nsub = (c->npairs + kWandBlocks - 1) / kWandBlocks;
+    const int chunks = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(1, 3 * c->sms / nsub) /* one wave at 3 CTAs per SM */, (npairs + 4 * wand_batch(c->m) - 1) / (4 * wand_batch(c->m))));
     ARGUS_CUDA_CHECK(c->wand_ia.ensure(npairs)); ARGUS_CUDA_CHECK(c->wand_ib.ensure(npairs)); ARGUS_CUDA_CHECK(c->wand_of.ensure(c->n));
     ARGUS_CUDA_CHECK(c->wand_len.ensure(npairs)); ARGUS_CUDA_CHECK(c->wand_rec.ensure((size_t)npairs * kWandRec));
     ARGUS_CUDA_CHECK(c->wand_Q.ensure((size_t)npairs * c->m * 16));

@@ -23,7 +23,7 @@
 
 namespace argus {
 
-constexpr int kWandGridMax = 64;     // blocks of the per-pair kernels (their partial sums are appended to the per-point kernels')
+constexpr int kWandGridMax = 1024;    // blocks of the per-pair kernels (their partial sums are appended to the per-point kernels')
 constexpr int kWandThreads = 128;
 constexpr int kWandRec = 16;         // doubles per pair: h_a[3], h_b[3], sigma, beta, r, g_a[3], g_b[3], free
 
@@ -78,41 +78,58 @@ __device__ __forceinline__ void sym3_mul(const double *N, const double *v, doubl
     o[2] = N[2] * v[0] + N[4] * v[1] + N[5] * v[2];
 }
 
-// q_pj (+)= W_ij h_i over the observations of point i, W_ij = A_ij^T B_ij re-evaluated; `seen`: cameras already written
-__device__ __forceinline__ void wand_accumulate_q(const BaProblem &pb, const CamConst *sc, const double *__restrict__ pts, int i, const double *h,
-                                                  double *__restrict__ Qp, uint64_t seen)
+// q_pj = sum_{i in {a,b} free, seen by j} A_ij^T (B_ij h_i): one thread per (pair, free camera), Jacobians re-evaluated
+// (every pair costs up to 2 m of them: spread over pairs x cameras they run in parallel)
+__global__ void __launch_bounds__(128) k_wand_q(BaProblem pb, WandPlan wp, ParamBufs pbuf, const LmState *__restrict__ st)
 {
-    const double M0 = pts[3 * (int64_t)i], M1 = pts[3 * (int64_t)i + 1], M2 = pts[3 * (int64_t)i + 2];
-    const int k1 = pb.obs_ptr[i + 1];
-    for (int k = pb.obs_ptr[i]; k < k1; ++k) {
-        const int j = pb.obs_cam[k];
-        double *q = Qp + 16 * j;
-        if (j < pb.mcon) continue;                        // fixed camera: no block in the reduced system
-        double u, v, A[32], B[6];
-        const int nfk = pb.cam_fix ? pb.cam_fix[2 * j] : pb.nfix_k, nfd = pb.cam_fix ? pb.cam_fix[2 * j + 1] : pb.nfix_d;
-        cam_project_jac(sc[j], M0, M1, M2, nfk, nfd, u, v, A, B);
-        const double y0 = B[0] * h[0] + B[1] * h[1] + B[2] * h[2], y1 = B[3] * h[0] + B[4] * h[1] + B[5] * h[2];
-        const bool add = (seen >> j) & 1ull;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);
+    if (st->done) return;
+    const double *cam = pb_cam(pbuf, st->cur_cam), *pts = pb_pts(pbuf, st->cur_pts);
+    load_cameras(sc, cam, pb.rot0, pb.m);
+    const int mf = pb.m - pb.mcon;
+    const int64_t total = wp.npairs * mf;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = t / mf;
+        const int j = pb.mcon + (int)(t % mf);
+        const int idx[2] = {wp.ia[p], wp.ib[p]};
+        const double *rc = wp.rec + (size_t)p * kWandRec;
+        double q[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const double t = A[r] * y0 + A[16 + r] * y1;
-            q[r] = add ? q[r] + t : t;
+        for (int r = 0; r < 16; ++r) q[r] = 0.0;
+        bool any = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int i = idx[s];
+            const uint64_t mk = pb.pt_mask[i];
+            if (i < pb.ncon || !((mk >> j) & 1ull)) continue;
+            any = true;
+            const double M0 = pts[3 * (int64_t)i], M1 = pts[3 * (int64_t)i + 1], M2 = pts[3 * (int64_t)i + 2];
+            double u, v, A[32], B[6];
+            const int nfk = pb.cam_fix ? pb.cam_fix[2 * j] : pb.nfix_k, nfd = pb.cam_fix ? pb.cam_fix[2 * j + 1] : pb.nfix_d;
+            cam_project_jac(sc[j], M0, M1, M2, nfk, nfd, u, v, A, B);
+            const double h0 = rc[3 * s], h1 = rc[3 * s + 1], h2 = rc[3 * s + 2];
+            const double y0 = B[0] * h0 + B[1] * h1 + B[2] * h2, y1 = B[3] * h0 + B[4] * h1 + B[5] * h2;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) q[r] += A[r] * y0 + A[16 + r] * y1;
+        }
+        if (any) {
+            double *Qp = wp.Q + ((size_t)p * pb.m + j) * 16;
+#pragma unroll
+            for (int r = 0; r < 16; r += 2) *reinterpret_cast<double2 *>(Qp + r) = make_double2(q[r], q[r + 1]);
         }
     }
 }
 
 // after the tile lineariser (which leaves V, eb and, mode 1, V*^-1 of every point): statistics of the pairs
-// -> scpart[4 b + {0,1,2}] = {sum r^2, max |eb'|, max diag(V + g g^T)}, and (mode 1) the pair records and q vectors
+// -> scpart[4 b + {0,1,2}] = {sum r^2, max |eb'|, max diag(V + g g^T)}, and (mode 1) the pair records (k_wand_q follows)
 __global__ void __launch_bounds__(kWandThreads) k_wand_prepare(BaProblem pb, WandPlan wp, ParamBufs pbuf, const LmState *__restrict__ st, int mode,
                                                                const double *__restrict__ V, const double *__restrict__ eb,
                                                                const double *__restrict__ Vinv, double *__restrict__ scpart)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    CamConst *sc = reinterpret_cast<CamConst *>(smem_raw);
     __shared__ double red[32];
     if (st->done) return;
-    const double *cam = pb_cam(pbuf, st->cur_cam), *pts = pb_pts(pbuf, st->cur_pts);
-    load_cameras(sc, cam, pb.rot0, pb.m);
+    const double *pts = pb_pts(pbuf, st->cur_pts);
     double cost = 0.0, ebmax = 0.0, vdmax = -1.79769313486231570e308;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < wp.npairs; p += (int64_t)gridDim.x * blockDim.x) {
         const int a = wp.ia[p], b = wp.ib[p];
@@ -143,75 +160,98 @@ __global__ void __launch_bounds__(kWandThreads) k_wand_prepare(BaProblem pb, Wan
         rc[0] = ha[0]; rc[1] = ha[1]; rc[2] = ha[2]; rc[3] = hb[0]; rc[4] = hb[1]; rc[5] = hb[2];
         rc[6] = sigma; rc[7] = beta; rc[8] = g.r;
         rc[9] = ga[0]; rc[10] = ga[1]; rc[11] = ga[2]; rc[12] = gb[0]; rc[13] = gb[1]; rc[14] = gb[2];
-        double *Qp = wp.Q + (size_t)p * pb.m * 16;
-        if (fa) wand_accumulate_q(pb, sc, pts, a, ha, Qp, 0ull);
-        if (fb) wand_accumulate_q(pb, sc, pts, b, hb, Qp, fa ? pb.pt_mask[a] : 0ull);
     }
     const double s0 = block_sum(cost, red), s1 = block_max(ebmax, red), s2 = block_max(vdmax, red);
     if (threadIdx.x == 0) { scpart[4 * blockIdx.x] = s0; scpart[4 * blockIdx.x + 1] = s1; scpart[4 * blockIdx.x + 2] = s2; scpart[4 * blockIdx.x + 3] = 0.0; }
 }
 
-// rank-one corrections of the reduced system, per chunk of pairs: grid = (npairs_cam + 1, nchunk), 256 threads.
-//   blockIdx.x < npairs_cam: block (j, k), thread (r, c):  part = sum_p sigma_p q_pj[r] q_pk[c]
-//   blockIdx.x == npairs_cam: thread (j, r) over all cameras:  part = sum_p beta_p q_pj[r]
-// part[chunk][npairs_cam * 256 + 16 m]
-constexpr int kWandBatch = 32;
+// rank-one corrections of the reduced system.  grid = (nsub, nchunk), 256 threads.  A CTA takes a chunk of pairs and a subset of
+// kWandBlocks (16) camera-pair blocks: per batch of pairs the q vectors of ALL cameras (zeros where a camera sees neither point)
+// are staged in shared memory, plain and scaled by sigma; thread (block of the subset, 4 x 4 micro-tile) accumulates its tile of
+// sum_p sigma_p q_pj q_pk^T  in 16 registers (4 vector loads per 16 FMAs; few registers: several CTAs per SM hide the latencies);
+// subset 0 also forms  sum_p beta_p q_pj  for E.   part[chunk][npairs_cam * 256 + 16 m]
+constexpr int kWandBlocks = 16;
+__host__ __device__ __forceinline__ int wand_batch(int m) { return m <= 8 ? 32 : m <= 16 ? 16 : m <= 32 ? 8 : 4; }
+__host__ __device__ __forceinline__ size_t wand_schur_smem(int m) { return (size_t)wand_batch(m) * m * 16 * 2 * sizeof(double) + 2 * kWandBlocks * sizeof(int); }
 __global__ void __launch_bounds__(256) k_wand_schur(BaProblem pb, WandPlan wp, int mf, const LmState *__restrict__ st, double *__restrict__ part)
 {
-    __shared__ double sj[kWandBatch][16], sk[kWandBatch][16], ss[kWandBatch];
-    __shared__ uint64_t smk[kWandBatch];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     if (st->done) return;
-    const int npc = mf * (mf + 1) / 2, tid = threadIdx.x;
+    const int m = pb.m, W = 16 * m, nb = wand_batch(m), tid = threadIdx.x;
+    double *sQ = reinterpret_cast<double *>(smem_raw);            // [nb][16 m]
+    double *sS = sQ + (size_t)nb * W;                              // the same scaled by sigma
+    int *sj = reinterpret_cast<int *>(sS + (size_t)nb * W), *sk = sj + kWandBlocks;
+    __shared__ double s_sig[32], s_beta[32];
+    __shared__ unsigned long long s_mask[32];
+    const int npc = mf * (mf + 1) / 2, sub = blockIdx.x;
+    const int b0 = sub * kWandBlocks, nblk = min(kWandBlocks, npc - b0);
+    if (tid < nblk) {
+        int a = 0, rem = b0 + tid;
+        while (rem >= mf - a) { rem -= mf - a; ++a; }
+        sj[tid] = (pb.mcon + a) * 16; sk[tid] = (pb.mcon + a + rem) * 16;
+    }
     const int64_t per = (wp.npairs + gridDim.y - 1) / gridDim.y;
     const int64_t p0 = per * blockIdx.y, p1 = (p0 + per < wp.npairs) ? p0 + per : wp.npairs;
-    double *out = part + (size_t)blockIdx.y * ((size_t)npc * 256 + 16 * (size_t)pb.m);
-    if ((int)blockIdx.x < npc) {
-        int a = 0, rem = blockIdx.x;
-        while (rem >= mf - a) { rem -= mf - a; ++a; }
-        const int j = pb.mcon + a, k = pb.mcon + a + rem;
-        const int r = tid >> 4, c = tid & 15;
-        double acc = 0.0;
-        for (int64_t pb0 = p0; pb0 < p1; pb0 += kWandBatch) {
-            // 256 threads = 32 pairs x 8 lanes: each lane brings two entries of q_pj and two of q_pk
-            const int pp = tid >> 3, l = tid & 7;
-            const int64_t p = pb0 + pp;
-            double2 vj = make_double2(0.0, 0.0), vk = vj; double sg = 0.0;
-            if (p < p1) {
-                const uint64_t mk = wand_cams(pb, wp, p);
-                if (((mk >> j) & 1ull) && ((mk >> k) & 1ull)) {
-                    const double *Qp = wp.Q + (size_t)p * pb.m * 16;
-                    vj = *reinterpret_cast<const double2 *>(Qp + 16 * j + 2 * l);
-                    vk = *reinterpret_cast<const double2 *>(Qp + 16 * k + 2 * l);
-                    sg = wp.rec[(size_t)p * kWandRec + 6];
-                }
-            }
-            sj[pp][2 * l] = vj.x * sg; sj[pp][2 * l + 1] = vj.y * sg; sk[pp][2 * l] = vk.x; sk[pp][2 * l + 1] = vk.y;
-            __syncthreads();
+    const int slot = tid >> 4, tr = ((tid & 15) >> 2) * 4, tc = (tid & 3) * 4;
+    double acc[1][16], ae[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-            for (int q = 0; q < kWandBatch; ++q) acc += sj[q][r] * sk[q][c];
-            __syncthreads();
+    for (int q = 0; q < 16; ++q) acc[0][q] = 0.0;
+    for (int64_t pb0 = p0; pb0 < p1; pb0 += nb) {
+        __syncthreads();
+        if (tid < nb) {
+            const bool in = pb0 + tid < p1;
+            s_sig[tid] = in ? wp.rec[(size_t)(pb0 + tid) * kWandRec + 6] : 0.0;
+            s_beta[tid] = in ? wp.rec[(size_t)(pb0 + tid) * kWandRec + 7] : 0.0;
+            s_mask[tid] = in ? wand_cams(pb, wp, pb0 + tid) : 0ull;
         }
-        out[(size_t)blockIdx.x * 256 + tid] = acc;
-    } else {
-        for (int t0 = 0; t0 < 16 * pb.m; t0 += 256) {
-            const int t = t0 + tid, j = t >> 4;
-            double acc = 0.0;
-            for (int64_t pb0 = p0; pb0 < p1; pb0 += kWandBatch) {
-                if (tid < kWandBatch) {
-                    const bool in = pb0 + tid < p1;
-                    ss[tid] = in ? wp.rec[(size_t)(pb0 + tid) * kWandRec + 7] : 0.0;
-                    smk[tid] = in ? wand_cams(pb, wp, pb0 + tid) : 0ull;
+        __syncthreads();
+        for (int t = tid; t < nb * W / 2; t += 256) {              // double2 per thread and pass
+            const int pp = (2 * t) / W, e = (2 * t) % W, j = e >> 4;
+            double2 v = make_double2(0.0, 0.0);
+            if (j >= pb.mcon && ((s_mask[pp] >> j) & 1ull)) v = *reinterpret_cast<const double2 *>(wp.Q + (size_t)(pb0 + pp) * W + e);
+            *reinterpret_cast<double2 *>(sQ + (size_t)pp * W + e) = v;
+            const double sg = s_sig[pp];
+            *reinterpret_cast<double2 *>(sS + (size_t)pp * W + e) = make_double2(v.x * sg, v.y * sg);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int bb = 0; bb < 1; ++bb) {
+            const int b = slot + 16 * bb;
+            if (b < nblk) {
+                const double *qa = sS + sj[b] + tr, *qb = sQ + sk[b] + tc;
+                for (int pp = 0; pp < nb; ++pp) {
+                    const double2 a0 = *reinterpret_cast<const double2 *>(qa + (size_t)pp * W), a1 = *reinterpret_cast<const double2 *>(qa + (size_t)pp * W + 2);
+                    const double2 c0 = *reinterpret_cast<const double2 *>(qb + (size_t)pp * W), c1 = *reinterpret_cast<const double2 *>(qb + (size_t)pp * W + 2);
+                    const double av[4] = {a0.x, a0.y, a1.x, a1.y}, cv[4] = {c0.x, c0.y, c1.x, c1.y};
+#pragma unroll
+                    for (int x = 0; x < 4; ++x)
+#pragma unroll
+                        for (int y = 0; y < 4; ++y) acc[bb][4 * x + y] += av[x] * cv[y];
                 }
-                __syncthreads();
-                if (j < pb.m && j >= pb.mcon) {
-#pragma unroll 4
-                    for (int q = 0; q < kWandBatch; ++q)
-                        if ((smk[q] >> j) & 1ull) acc += ss[q] * wp.Q[(size_t)(pb0 + q) * pb.m * 16 + t];
-                }
-                __syncthreads();
             }
-            if (j < pb.m) out[(size_t)npc * 256 + t] = acc;
         }
+        if (sub == 0) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int e = g * 256 + tid;
+                if (e < W) { double s = ae[g]; for (int pp = 0; pp < nb; ++pp) s += s_beta[pp] * sQ[(size_t)pp * W + e]; ae[g] = s; }
+            }
+        }
+    }
+    double *out = part + (size_t)blockIdx.y * ((size_t)npc * 256 + 16 * (size_t)m);
+#pragma unroll
+    for (int bb = 0; bb < 1; ++bb) {
+        const int b = slot + 16 * bb;
+        if (b < nblk) {
+#pragma unroll
+            for (int x = 0; x < 4; ++x)
+#pragma unroll
+                for (int y = 0; y < 4; ++y) out[(size_t)(b0 + b) * 256 + (tr + x) * 16 + tc + y] = acc[bb][4 * x + y];
+        }
+    }
+    if (sub == 0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) { const int e = g * 256 + tid; if (e < W) out[(size_t)npc * 256 + e] = ae[g]; }
     }
 }
 

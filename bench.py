@@ -441,6 +441,39 @@ def bench_extras(torch, ba, local, stream, args, dmma_peak):
         out[wl] = r
         del s, p0
 
+    # ---- c3 as BASELINE.json words it: "... + wand-length constraint" - the constraint INSIDE the solver (extension, parity
+    #      unpinned: the reference only rescales afterwards).  Same shape: 8 cameras, 100 000 wand positions = 200 000 points ----
+    m, n, views, nk, nd = WORKLOADS["c3"]
+    sw = scenes.make_ba_wand_scene(m, n // 2, 0, views, seed=4, cam_seed=4)
+    p0, rot0 = scenes.pack_ba_problem(sw["cams0"], sw["pts0"])
+    with torch.cuda.stream(stream):
+        B = ba.BundleAdjuster(device=local, stream=stream.cuda_stream)
+        B.upload(sw["vmask"], p0, rot0, sw["x"], nk, nd)
+        res_w = {}
+        for label, weight in (("off", 0.0), ("on", 1000.0)):
+            B.set_wand(sw["ia"], sw["ib"], sw["wand"], weight)
+            for _ in range(2):
+                B.reset(); B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(3):
+                B.reset(); ret, info = B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+                assert ret == ITERS_PER_STEP, (label, ret, info)
+            e1.record(stream); e1.synchronize()
+            ms_it = e0.elapsed_time(e1) / (3 * ITERS_PER_STEP)
+            B.reset(); retc, infoc = B.solve(itmax=150)
+            pts = B.download()[16 * m:].reshape(-1, 3)
+            d = np.linalg.norm(pts[sw["ia"]] - pts[sw["ib"]], axis=1)
+            res_w[label] = {"ms_per_iteration": ms_it, "obs_iters_per_sec": sw["nobs"] / (ms_it * 1e-3), "iterations_to_convergence": int(retc),
+                            "stop_reason": int(infoc[6]), "final_cost": float(infoc[1]),
+                            "wand_score_percent": float(100.0 * d.std() / d.mean()), "mean_wand_length": float(d.mean())}
+        B.close()
+    out["c3_wand"] = {"workload": "c3 with the wand-length constraint in the solver: %d cameras, %d wand positions = %d points x %d views = %d observations, "
+                                  "weight 1000 px per length unit, true length %.2f" % (m, n // 2, n, views, sw["nobs"], sw["wand"]),
+                      "parity": "unpinned (extension: the reference applies the wand length after the adjustment, sbaDriver.py:703-713)",
+                      "constraint_off": res_w["off"], "constraint_on": res_w["on"]}
+    del sw, p0
+
     # ---- the reference's own largest known-answer run: demo/54camsvarKD.txt + 54pts.txt (README.txt:197-206) ----
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers

@@ -83,10 +83,19 @@ def _check_outputs(case, d, res, g, tmp_path, tol, aligned):
     if aligned:
         # reference points pin the frame: coordinates, DLT coefficients and the written files are comparable as they are
         scale = np.abs(g("xyzs")).max()
-        assert np.abs(res.xyzs - g("xyzs")).max() <= tol * scale
-        assert rel(res.dlts[:, :, 0], g("dlts")) <= 20 * tol
-        assert rel(np.loadtxt(pre + "-dlt-coefficients.csv", delimiter=","), g("dlt_csv")) <= 20 * tol
-        assert np.nanmax(np.abs(pc - g("paired_csv"))) <= tol * scale and np.nanmax(np.abs(uc - g("unpaired_csv"))) <= tol * scale
+        sgn = np.ones(3)
+        if case == "plane":
+            # the horizontal-plane alignment takes its two in-plane axes from numpy's SVD of the reference points
+            # (sbaDriver.py:940-975) and never fixes their signs (its `det == -1` test compares floats exactly): a 1e-12 change of
+            # the input can flip x or y.  +z is decided by the side the data lies on and must agree.
+            sgn = np.sign((res.xyzs * g("xyzs")).sum(axis=0))
+            assert sgn[2] == 1.0
+        lsgn = np.array([sgn[0], sgn[1], sgn[2], 1.0, sgn[0], sgn[1], sgn[2], 1.0, sgn[0], sgn[1], sgn[2]])     # L1..L11 multiply x, y, z, 1
+        assert np.abs(res.xyzs * sgn - g("xyzs")).max() <= tol * scale
+        assert rel(res.dlts[:, :, 0] * lsgn, g("dlts")) <= 20 * tol
+        assert rel(np.loadtxt(pre + "-dlt-coefficients.csv", delimiter=",") * lsgn[:, None], g("dlt_csv")) <= 20 * tol
+        assert np.nanmax(np.abs(pc * np.tile(sgn, pc.shape[1] // 3) - g("paired_csv"))) <= tol * scale
+        assert np.nanmax(np.abs(uc * np.tile(sgn, uc.shape[1] // 3) - g("unpaired_csv"))) <= tol * scale
 
 
 @pytest.mark.parametrize("case", CASES)
