@@ -36,6 +36,7 @@ WORKLOADS = {
     "c4": (16, 2_000_000, 10, 0, 0),
     "c3": (8, 200_000, 6, 0, 0),
     "small": (8, 20_000, 6, 0, 0),
+    "c4r8": (16, 250_000, 10, 0, 0),       # what one rank of an 8-GPU strong-scaling run of c4 holds (fixed per-iteration costs)
     # config 5: 32 cameras, 5M points x 12 views, 10 % outlier tracks, cameras 0-15 fixed intrinsics / 16-31 free (extension)
     "c5": (32, 5_000_000, 12, 0, 0),
 }
@@ -425,7 +426,7 @@ def bench_extras(torch, ba, local, stream, args, dmma_peak):
             B.close()
         sch = prof["schur"][0] / max(prof["schur"][1], 1)
         r = {"workload": "%s: %d cameras, %d points x %d views = %d observations%s" % (wl, m, n, views, s["nobs"],
-                         ", cameras 0-15 fixed intrinsics / 16-31 free, 10 %% outlier tracks" if wl == "c5" else ""),
+                         ", cameras 0-15 fixed intrinsics / 16-31 free, 10 % outlier tracks" if wl == "c5" else ""),
              "value": s["nobs"] / (ms_it * 1e-3), "unit": "obs*iters/s", "ms_per_iteration": ms_it,
              "kernels_ms_per_iteration": {k_: v[0] / (steps * ITERS_PER_STEP) for k_, v in sorted(prof.items()) if v[1]},
              "schur": {"ms_per_launch": sch, "tflops": cnt["schur_flops"] / (sch * 1e-3) / 1e12, "frac_of_fp64_peak": cnt["schur_flops"] / (sch * 1e-3) / 1e12 / dmma_peak},

@@ -55,13 +55,19 @@ def test_converged_parameters_within_1e6_of_the_reference(shape):
     (pr, ir, rr), (pg, ig, rg) = _both(s, nk, nd, itmax=150, mcon=1, ncon=1)
     print("reference", list(ir[5:]), ir[1], "gpu", list(ig[5:]), ig[1])
     assert rr > 0 and rg > 0 and int(ir[6]) in (2, 4) and int(ig[6]) in (2, 4)          # both converged (small step / stagnation)
-    assert abs(ir[1] - ig[1]) <= 1e-8 * ir[1]                                            # final cost, each solver at its own stop (the reference against itself with another BLAS thread count: 1.8e-9)
-    if rr != rg:
-        # stop reason 4 cannot be switched off and, with eps4 = 0, fires on rounding noise once the cost stagnates
-        # (sba_levmar.c:1312; the reference does not even reproduce its own iteration count across BLAS thread counts,
-        # SURVEY.md 6.2): compare at the common iteration count, "the same LM iteration count where the trajectory agrees"
-        k = min(rr, rg)
+    # each solver at its OWN stop: the final cost (the reference against itself with another BLAS thread count: 1.8e-9,
+    # BASELINE.md section 2)
+    assert abs(ir[1] - ig[1]) <= 1e-8 * ir[1]
+    if rr != rg or list(ir[6:]) != list(ig[6:]):
+        # stop reason 4 cannot be switched off and, with eps4 = 0, fires on rounding noise once the cost stagnates, and the same
+        # noise decides whether the last tiny steps are accepted (sba_levmar.c:1312; the reference does not reproduce its own
+        # iteration count across BLAS thread counts).  A stop-4 exit is not a stationary point to 1e-6 in the
+        # weakly determined parameters (one more iteration moves the fifth distortion coefficient by 1e-4 at a cost change of
+        # 1e-9), so the parameters are compared at "the same LM iteration count where the trajectory agrees": the last
+        # iteration before the earlier of the two stops
+        k = min(rr, rg) - 1
         (pr, ir, rr), (pg, ig, rg) = _both(s, nk, nd, itmax=k, mcon=1, ncon=1)
+        print("at", k, "reference", list(ir[5:]), ir[1], "gpu", list(ig[5:]), ig[1])
         assert rr == rg == k
     assert abs(ir[1] - ig[1]) <= 1e-9 * ir[1]                                            # cost at the same iteration
     assert list(ir[7:]) == list(ig[7:])                                                  # evaluations and linear systems
