@@ -25,6 +25,7 @@
 #include "ba_lin_tile.cuh"
 #include "ba_blockdiag.cuh"
 #include "ba_chol_coop.cuh"
+#include "ba_chol_cluster.cuh"
 #include "ba_lm_controller.cuh"
 #include "ba_wand.cuh"
 #include "nccl_dyn.h"
@@ -372,7 +373,10 @@ int enqueue_attempt_motstr(argus_ba_ctx *c, bool controller, double *dbout)
     }
     {
         ProfScope ps(c, P_CHOL);
-        if (c->coop_ok && N >= 192) {
+        if (N <= kClMaxN) {
+            // one thread-block cluster, hardware cluster barriers, the right-hand side carried through the factorisation
+            k_chol_cluster<<<kClCtas, kClThreads, chol_cluster_smem(), s>>>(c->S.p, c->E.p, c->da_free.p, N, c->cholwork.p, c->flags.p + 1, c->flags.p + 2, done);
+        } else if (c->coop_ok && N >= 192) {
             // multi-SM factorisation (cooperative grid): a single CTA is latency bound from about 200 unknowns
             double *Sp = c->S.p, *xp = c->da_free.p, *wp = c->cholwork.p; const double *Ep = c->E.p; int Nn = N;
             int *stt = c->flags.p + 1, *fl = c->flags.p + 2;
@@ -535,6 +539,7 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<5, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)schur_stage_bytes(40));
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_schur_mma<6, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (int)schur_stage_bytes(72));
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wand_schur, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wand_schur_smem(64));
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chol_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_cluster_smem());
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin_tile<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(k_lin_tile<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, lin_max);
@@ -714,7 +719,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
             PLAN_ENS(c->hit_blob, hits_bound + (2 * (int64_t)(c->schur_NW * c->schur_NB + 4) + 8) * c->ntiles * c->schur_G + 8);
         }
         PLAN_ENS(c->corder, nobs); PLAN_ENS(c->cstart, (size_t)c->ntiles * (m + 1));
-        PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1024 + N + 32);
+        PLAN_ENS(c->Upart2, (int64_t)c->grid_lin * m * kUfrag); PLAN_ENS(c->cholwork, (int64_t)((N + 31) / 32) * 1056 + N + 64);
         PLAN_ENS(c->vmask_dev, n * m); PLAN_ENS(c->idx_btot, (n + kIdxPts - 1) / kIdxPts + 1);
         PLAN_ENS(c->obs_ptr, n + 1); PLAN_ENS(c->obs_cam, nobs); PLAN_ENS(c->obs_uv, nobs); PLAN_ENS(c->pt_mask, n);
         PLAN_ENS(c->rot0, 4 * m); PLAN_ENS(c->camb[0], 16 * m); PLAN_ENS(c->camb[1], 16 * m); PLAN_ENS(c->cam0, 16 * m);
