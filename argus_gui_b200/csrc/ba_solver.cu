@@ -104,6 +104,38 @@ void *pinned_take()
 }
 void pinned_give(void *p) { std::lock_guard<std::mutex> lk(g_once_mutex); g_pinned_free.push_back(p); }
 
+// ... and small device arenas: cudaMalloc + cudaFree are a third of a one-shot call on a wand-sized problem (config 1).  A
+// destroyed context parks its arena here if it is small (its stream has been synchronised); an upload that needs no more takes it.
+constexpr size_t kArenaPoolMaxBytes = 32u << 20;
+constexpr size_t kArenaPoolSlots = 4;
+struct PooledArena { int device; char *base; size_t size; };
+std::vector<PooledArena> g_arena_pool;
+char *arena_take(int device, size_t need, size_t *got)
+{
+    if (need <= kArenaPoolMaxBytes) {
+        std::lock_guard<std::mutex> lk(g_once_mutex);
+        for (size_t i = 0; i < g_arena_pool.size(); ++i)
+            if (g_arena_pool[i].device == device && g_arena_pool[i].size >= need) {
+                char *b = g_arena_pool[i].base; *got = g_arena_pool[i].size;
+                g_arena_pool.erase(g_arena_pool.begin() + i);
+                return b;
+            }
+    }
+    char *b = nullptr;
+    if (cudaMalloc(&b, need) != cudaSuccess) return nullptr;
+    *got = need;
+    return b;
+}
+void arena_give(int device, char *base, size_t size)
+{
+    if (!base) return;
+    if (size <= kArenaPoolMaxBytes) {
+        std::lock_guard<std::mutex> lk(g_once_mutex);
+        if (g_arena_pool.size() < kArenaPoolSlots) { g_arena_pool.push_back({device, base, size}); return; }
+    }
+    cudaFree(base);
+}
+
 int g_default_device = 0;      // device of the one-shot calls (argus_set_default_device)
 
 }  // namespace
@@ -572,7 +604,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (auto &e : c->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int q = 0; q < kSnap; ++q) if (c->snap_ev[q]) cudaEventDestroy(c->snap_ev[q]);
-    if (c->arena.base) cudaFree(c->arena.base);
+    arena_give(c->device, c->arena.base, c->arena.size);
     if (c->h_snap) pinned_give(c->h_snap);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -654,7 +686,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     c->wand_n = 0; c->wand_grid = 0; c->wand_chunks = 0;       // pairs refer to the points of one upload
     const int mf = m - mcon, N = 16 * mf;
     c->npairs = mf * (mf + 1) / 2;
-    c->grid_pts128 = (int)std::min<int64_t>((n + 127) / 128, (int64_t)c->sms * 8); if (c->grid_pts128 < 1) c->grid_pts128 = 1;
+    c->grid_pts128 = (int)std::min<int64_t>((n + 127) / 128, (int64_t)c->sms * 4);   /* one wave: 4 CTAs of 128 threads x 120 registers per SM, one camera prologue each */ if (c->grid_pts128 < 1) c->grid_pts128 = 1;
     c->grid_pts256 = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sms * 8); if (c->grid_pts256 < 1) c->grid_pts256 = 1;
     // ---- plans: point tiles (<= 32 points; every point gets one of four classes, a class holds <= 64 observations per tile;
     //      the observation of rank r of a point sits in Z row 4 (first index inside the class + r) + class, see ba_schur_mma.cuh)
@@ -741,10 +773,11 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         cudaError_t pe = plan();
         const size_t need = ar.used + 256;
         if (pe == cudaSuccess && need > ar.size) {
-            if (ar.base) cudaFree(ar.base);
+            arena_give(c->device, ar.base, ar.size);
             ar.base = nullptr; ar.size = 0;
-            pe = cudaMalloc(&ar.base, need);
-            if (pe == cudaSuccess) ar.size = need;
+            size_t got = 0;
+            ar.base = arena_take(c->device, need, &got);
+            if (ar.base) ar.size = got; else pe = cudaErrorMemoryAllocation;
         }
         if (pe == cudaSuccess) { ar.measuring = false; ar.used = 0; pe = plan(); }
         g_arena = nullptr;
