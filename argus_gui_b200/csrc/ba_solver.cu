@@ -145,7 +145,7 @@ struct argus_ba_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sms = 148;
-    bool coop_ok = true;
+    bool coop_ok = true, cluster_ok = true;
     // comm
     int rank = 0, world = 1;
     argus_allreduce_fn allreduce = nullptr;
@@ -405,7 +405,7 @@ int enqueue_attempt_motstr(argus_ba_ctx *c, bool controller, double *dbout)
     }
     {
         ProfScope ps(c, P_CHOL);
-        if (N <= kClMaxN) {
+        if (c->cluster_ok && N <= kClMaxN) {
             // one thread-block cluster, hardware cluster barriers, the right-hand side carried through the factorisation
             k_chol_cluster<<<kClCtas, kClThreads, chol_cluster_smem(), s>>>(c->S.p, c->E.p, c->da_free.p, N, c->cholwork.p, c->flags.p + 1, c->flags.p + 2, done);
         } else if (c->coop_ok && N >= 192) {
@@ -578,6 +578,16 @@ int argus_ba_create(argus_ba_ctx **out, int device, void *stream)
             if (e != cudaSuccess) return fail("cudaFuncSetAttribute", e);
             g_attr_done |= 1ull << device;
         }
+    }
+    {   // can one cluster of kClCtas CTAs of the reduced-system solver be resident here (a partitioned GPU may say no)?
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kClCtas); cfg.blockDim = dim3(kClThreads); cfg.dynamicSmemBytes = chol_cluster_smem();
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = kClCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, (void *)k_chol_cluster, &cfg) != cudaSuccess) { cudaGetLastError(); ncl = 0; }
+        c->cluster_ok = ncl > 0;
     }
     *out = c;
     return ARGUS_OK;

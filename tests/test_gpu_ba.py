@@ -20,7 +20,10 @@ def test_p0_projection_golden(golden_ba):
 
 
 @pytest.mark.parametrize("cfg", [(4, 500, 3, 2, 3, 0, 0), (8, 2000, 6, 0, 0, 0, 0), (3, 300, 3, 5, 4, 0, 0), (6, 800, 4, 2, 0, 1, 0),
-                                 (5, 600, 4, 0, 3, 2, 25)])
+                                 (5, 600, 4, 0, 3, 2, 25),
+                                 # the reduced-system solvers by size: 32 unknowns (one diagonal block), 240 (a partial last block), 512 (the
+                                 # largest the thread-block-cluster kernel takes), 528 (the cooperative-grid kernel)
+                                 (2, 200, 2, 0, 0, 0, 0), (16, 1500, 9, 0, 0, 1, 0), (32, 1500, 10, 0, 0, 0, 0), (33, 1500, 10, 0, 0, 0, 0)])
 def test_p2_p3_normal_equations_and_step(cfg):
     """U, ea, V, eb, S, E and one step dp against the numpy restatement fed with the oracle's Jacobian."""
     m, n, views, nk, nd, mcon, ncon = cfg
