@@ -58,6 +58,10 @@ struct SchurPlan {
                                     //                            [nslots] = Z rows of the tile;
                                     //   then the entries: row of Z_ij | row of Z_ik << 8
     const int32_t *hit_ptr;         // [ntiles * G + 1]: start of every record in hit_blob, in 16-bit units (multiples of 8)
+    int *pace;                      // G == 2 only: [nchunk][8] tiles fetched so far by the two CTAs of a chunk (zeroed before the launch)
+                                    // or null.  They read the same Z tiles; kept within pace_slack tiles of each other, the
+                                    // second one finds them in L2
+    int pace_slack;
 };
 
 // ---- PTX helpers: mbarrier + bulk async copy (TMA, non-tensor form) ----
@@ -265,12 +269,32 @@ __device__ long long *g_schur_trace = nullptr;
 #else
 #define ARGUS_TRACE(slot_) do { } while (0)
 #endif
+constexpr int kPaceInts = 8;         // counters per chunk (G <= 8), one 32-byte row
+constexpr int kPaceSpins = 1 << 14;  // polls without success after which a CTA stops pacing itself (the groups of a chunk are co-resident
+                                     // whenever the GPU is ours alone - grid <= SMs, one CTA per SM - but nothing may depend on that)
 constexpr int kSchurUnroll = 1;      // groups of four hits per trip of the inner loop
 constexpr bool kSchurDiagPath = false;   // a separate 9-DMMA code path for the diagonal blocks (j == k): fewer DMMAs for 16 of 136 blocks, twice the code
 constexpr uint32_t kZBytes = 12u * (kTileRows + 1) * 32u;            // largest tile: 12 planes of 257 chunks
 __host__ __device__ constexpr uint32_t schur_ent_bytes(int nslots) { return (uint32_t)nslots * kTilePts * 2u; }
 __host__ __device__ constexpr uint32_t schur_tab_bytes(int nslots) { return ((uint32_t)nslots + 4u) * 4u; }        // table + the tile's row count, 16-byte multiple
 __host__ __device__ constexpr uint32_t schur_stage_bytes(int nslots) { return kZBytes + schur_tab_bytes(nslots) + schur_ent_bytes(nslots) + 16u + 256u; }
+
+// one pacing step of the copy-issuing lane.  Not inlined, and its state (the snapshot of the other CTA's counter, "still
+// pacing") lives in shared memory: the hot loop, which sits at the register limit, keeps nothing alive for it.
+__device__ __noinline__ void schur_pace_step(int *row, int grp, int it, int slack, int *s_pace /* [0..3] snapshot of the row, [4] pacing on */)
+{
+    if (!s_pace[4]) return;
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(row + grp), "r"(it) : "memory");
+    const int need = it - slack;
+    if (need > 1 && s_pace[grp ^ 1] < need) {            // rare: really ahead (the first snapshot is taken while tile 1 is fetched)
+        int v = 0;
+        for (int spins = 0; v < need; ++spins) {
+            if (spins >= kPaceSpins) { s_pace[4] = 0; break; }
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(row + (grp ^ 1)) : "memory");
+        }
+    }
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(s_pace)), "l"(row) : "memory");   // next snapshot (L2 only)
+}
 
 // DIAG (compile time): a code path of its own for the diagonal blocks; skip_hl (run time, warp uniform): in the common path,
 // leave out the (rows 8-15) x (columns 0-7) sub-tile, which a diagonal block gets from its transpose (k_assemble_mma)
@@ -345,6 +369,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(TilePlan tp, SchurPlan
     constexpr int kSlots = NW * NB;
     constexpr uint32_t kEnt = schur_ent_bytes(kSlots), kTab = schur_tab_bytes(kSlots), kStage = schur_stage_bytes(kSlots);
     __shared__ __align__(8) uint64_t mfull[2], mempty[2];
+    __shared__ __align__(16) int s_pace[8];            // pacing (G == 2): [0..3] snapshot of the chunk's counters, [4] still pacing
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g8 = lane >> 2, kk = lane & 3;
@@ -352,7 +377,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(TilePlan tp, SchurPlan
     const int ntl = (tp.ntiles > chunk) ? (tp.ntiles - chunk + sp.nchunk - 1) / sp.nchunk : 0;   // tiles of this chunk
     __shared__ __align__(16) int32_t s_meta[2][4];      // per tile: first Z row, first Z row of the next tile, record begin, record end
 
-    if (threadIdx.x == 0) { mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1); mbar_init(&mempty[0], NW); mbar_init(&mempty[1], NW); }
+    if (threadIdx.x == 0) { s_pace[0] = 0; s_pace[1] = 0; s_pace[4] = 1; mbar_init(&mfull[0], 1); mbar_init(&mfull[1], 1); mbar_init(&mempty[0], NW); mbar_init(&mempty[1], NW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -366,6 +391,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(TilePlan tp, SchurPlan
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 8u), "l"(sp.hit_ptr + (size_t)t * sp.G + grp) : "memory");
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 12u), "l"(sp.hit_ptr + (size_t)t * sp.G + grp + 1) : "memory");
     };
+    // pacing of the two CTAs of a chunk when G == 2 (they read the same Z tiles): each publishes the tile it is about to fetch and
+    // looks at a snapshot of the other's counter that an asynchronous copy brought into shared memory during the previous tile
+    // - nothing on the copy-issuing warp's critical path unless it really is more than pace_slack tiles ahead; then it waits (the
+    // launch ends with the slower CTA anyway) and the tile comes from DRAM once instead of twice
     auto produce = [&](int it) {
         if (warp == 0 && lane == 0) {
             const int b = it & 1;
@@ -373,6 +402,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(TilePlan tp, SchurPlan
             int4 mt;
             asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(mt.x), "=r"(mt.y), "=r"(mt.z), "=r"(mt.w) : "r"(smem_u32(&s_meta[b][0])) : "memory");
             if (it + 1 < ntl) fetch_meta(it + 1);
+            if (sp.pace != nullptr) schur_pace_step(sp.pace + (size_t)chunk * kPaceInts, grp, it, sp.pace_slack, s_pace);
             if (it >= 2) mbar_wait(&mempty[b], (uint32_t)(((it >> 1) - 1) & 1));
             const int t = chunk + it * sp.nchunk;
             const uint32_t zb = (uint32_t)(mt.y - mt.x + 1) * 384u, rb = (uint32_t)(mt.w - mt.z) * 2u;
@@ -437,6 +467,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k_schur_mma(TilePlan tp, SchurPlan
         if (lane == 0) mbar_arrive(&mempty[sb]);       // this warp is done with the stage
     }
 
+    if (sp.pace != nullptr && threadIdx.x == 0)      // nobody waits for a CTA that has fetched everything
+        asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(sp.pace + (size_t)chunk * kPaceInts + grp), "r"(0x7fffffff) : "memory");
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int pair = sp.blk_pair[((size_t)grp * NW + warp) * NB + b];

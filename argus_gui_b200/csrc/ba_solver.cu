@@ -172,6 +172,7 @@ struct argus_ba_ctx {
     // tile / MMA plan
     DevBuf<int32_t> tile_pt, tile_o, tile_r; DevBuf<uint16_t> blk_jk; DevBuf<int32_t> blk_pair; DevBuf<uint8_t> zsign, zs; DevBuf<double> Z;
     DevBuf<uint8_t> corder, pt_slot0, vmask_dev; DevBuf<int32_t> idx_btot; DevBuf<uint32_t> row_info; DevBuf<double2> row_uv;
+    DevBuf<int> schur_pace; int pace_slack = 0;
     DevBuf<uint16_t> hit_blob; DevBuf<int32_t> hit_ptr;     // static hit lists of the Schur kernel: one record per (tile, group)
     DevBuf<uint8_t> cam_fix; bool cam_fix_on = false; DevBuf<uint16_t> cstart;
     // wand pairs (extension, ba_wand.cuh); their buffers live outside the arena: argus_ba_set_wand comes after the upload
@@ -198,6 +199,8 @@ struct argus_ba_ctx {
     SchurPlan schur_plan() const {
         SchurPlan sp; sp.G = schur_G; sp.nchunk = schur_nchunk; sp.npairs = npairs; sp.nslots = schur_NW * schur_NB; sp.blk_jk = blk_jk.p;
         sp.blk_pair = blk_pair.p; sp.hit_blob = hit_blob.p; sp.hit_ptr = hit_ptr.p;
+        sp.pace = (pace_slack > 0 && schur_G == 2 && schur_nchunk * schur_G <= sms) ? schur_pace.p : nullptr;
+        sp.pace_slack = pace_slack;
         return sp;
     }
     LinTilePlan lin_plan() const { LinTilePlan lp; lp.corder = corder.p; lp.cstart = cstart.p; lp.row_info = row_info.p; lp.row_uv = row_uv.p; return lp; }
@@ -370,6 +373,7 @@ int enqueue_attempt_motstr(argus_ba_ctx *c, bool controller, double *dbout)
     {
         ProfScope ps(c, P_SCHUR);
         dim3 grid(c->schur_nchunk, c->schur_G);
+        if (c->schur_plan().pace) ARGUS_CUDA_CHECK(cudaMemsetAsync(c->schur_pace.p, 0, (size_t)c->schur_nchunk * kPaceInts * sizeof(int), s));
 #define SCHUR_LAUNCH(NB_, NW_) k_schur_mma<NB_, NW_><<<grid, (NW_) * 32, 2 * schur_stage_bytes((NB_) * (NW_)), s>>>(c->tile_plan(), c->schur_plan(), c->Z.p, \
                                                                                                       c->zs.p, c->Spart.p, done)
         switch (c->schur_NB * 100 + c->schur_NW) {
@@ -606,7 +610,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
                               &c->cam2, &c->scal, &c->respart, &c->Upart2, &c->cholwork, &c->Z};
     for (auto *b : bufs) b->release();
     c->corder.release(); c->row_info.release(); c->row_uv.release(); c->pt_slot0.release(); c->tile_r.release(); c->zs.release();
-    c->hit_blob.release(); c->hit_ptr.release(); c->cam_fix.release(); c->cstart.release(); c->vmask_dev.release();
+    c->hit_blob.release(); c->hit_ptr.release(); c->schur_pace.release(); c->cam_fix.release(); c->cstart.release(); c->vmask_dev.release();
     c->idx_btot.release(); c->flags.release(); c->tile_pt.release(); c->tile_o.release(); c->blk_jk.release(); c->blk_pair.release();
     c->zsign.release(); c->st.release();
     c->wand_ia.release(); c->wand_ib.release(); c->wand_of.release(); c->wand_len.release(); c->wand_rec.release(); c->wand_Q.release(); c->wand_part.release();
@@ -735,6 +739,11 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         int nch = c->sms / c->schur_G; if (nch < 1) nch = 1;
         if (nch > c->ntiles) nch = c->ntiles > 0 ? c->ntiles : 1;
         c->schur_nchunk = nch;
+        // tiles a group CTA may run ahead of the slowest group of its chunk: as many as half of the L2 holds over all chunks
+        int l2 = 0; cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, c->device);
+        const double tile_bytes = 384.0 * kTileRows;
+        int slack = (int)(0.5 * (double)l2 / ((double)nch * tile_bytes));
+        c->pace_slack = slack < 2 ? 0 : (slack > 64 ? 64 : slack);
     }
     // corder, cstart, row_info / row_uv and the hit lists are derived on the device (k_index_*, k_build_tile_index, k_hits_*)
     c->lin_smem = (((size_t)m * sizeof(CamConst) + 15) & ~(size_t)15) + (size_t)kTileRows * (kGa + kBs) * sizeof(double) +
@@ -768,7 +777,7 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         PLAN_ENS(c->ptsb[0], 3 * n); PLAN_ENS(c->ptsb[1], 3 * n); PLAN_ENS(c->pts0, 3 * n);
         PLAN_ENS(c->V, 6 * n); PLAN_ENS(c->eb, 3 * n); PLAN_ENS(c->vstate, 3 * n); PLAN_ENS(c->Vinv, 6 * n); PLAN_ENS(c->dbuf, 3 * n);
         PLAN_ENS(c->scpart, 4 * (c->grid_lin + kWandGridMax)); PLAN_ENS(c->red12, c->r1len + slen + 16 * m); PLAN_ENS(c->max2, 2);
-        PLAN_ENS(c->Spart, (int64_t)c->schur_nchunk * slen);
+        PLAN_ENS(c->Spart, (int64_t)c->schur_nchunk * slen); PLAN_ENS(c->schur_pace, (size_t)c->schur_nchunk * kPaceInts);
         PLAN_ENS(c->S, (int64_t)N * N); PLAN_ENS(c->E, N); PLAN_ENS(c->da_free, N); PLAN_ENS(c->da_full, 16 * m);
         PLAN_ENS(c->part3, 3 * (c->grid_pts128 + kWandGridMax)); PLAN_ENS(c->att3, 4); PLAN_ENS(c->cam2, 2); PLAN_ENS(c->scal, 8); PLAN_ENS(c->respart, c->grid_pts256 + kWandGridMax);
         PLAN_ENS(c->flags, 4); PLAN_ENS(c->st, 1);
