@@ -34,10 +34,11 @@ using namespace argus;
 
 namespace {
 
-enum ProfId { P_RESIDUAL = 0, P_LINEARIZE, P_LIN_REDUCE, P_SCHUR, P_SCHUR_REDUCE, P_ASSEMBLE, P_CHOL, P_BACKSUB, P_ALLREDUCE, P_CONTROL, P_COUNT };
+enum ProfId { P_RESIDUAL = 0, P_LINEARIZE, P_LIN_REDUCE, P_SCHUR, P_SCHUR_REDUCE, P_ASSEMBLE, P_CHOL, P_BACKSUB, P_ALLREDUCE, P_CONTROL, P_LIN_STATS, P_COUNT };
 const char *kProfNames[P_COUNT] = {"residual", "linearize", "lin_reduce", "schur", "schur_reduce", "assemble", "chol_solve", "backsub_eval",
-                                   "allreduce", "controller"};
+                                   "allreduce", "controller", "linearize_stats"};
 
+constexpr int kProfEvery = 4;            // ARGUS_BA_PROFILE with graphs: every fourth attempt carries the event-record nodes
 constexpr int kDepth = 2;               // damping attempts the host queues ahead of the one it has seen the outcome of
 constexpr int kSnap = kDepth + 2;       // ring of pinned LmState snapshots
 constexpr int kLogCap = 4096;           // verbose > 1: attempts remembered for the per-attempt report
@@ -75,12 +76,12 @@ template <typename T> struct DevBuf {
 
 // host-side helper: split [0, n) over host threads (counting the observations per point at upload is a pure host streaming
 // job); the thread count is divided by the number of ranks sharing the host
-void parallel_for(int64_t n, int world, const std::function<void(int64_t, int64_t)> &fn)
+void parallel_for(int64_t n, int world, const std::function<void(int64_t, int64_t)> &fn, int64_t grain = 65536)
 {
     unsigned hw = std::thread::hardware_concurrency();
     int cap = (int)std::min<unsigned>(hw ? hw : 4, 16) / std::max(1, world);
     if (cap < 1) cap = 1;
-    int T = (int)std::min<int64_t>(cap, (n + 65535) / 65536);
+    int T = (int)std::min<int64_t>(cap, (n + grain - 1) / grain);
     if (T <= 1) { fn(0, n); return; }
     std::vector<std::thread> th;
     for (int q = 0; q < T; ++q) th.emplace_back([&, q] { fn(n * q / T, n * (q + 1) / T); });
@@ -185,12 +186,16 @@ struct argus_ba_ctx {
     int grid_pts128 = 1, grid_pts256 = 1, npairs = 1;
     // damping attempt as a CUDA graph (captured at the first solve after an upload)
     bool use_graph = true;
+    cudaStream_t copy_stream = nullptr; cudaEvent_t copy_ev[2] = {nullptr, nullptr};     // upload: the large host arrays travel beside the index build
     cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphExec_t graph_exec_prof = nullptr;     // the same attempt with an event-record node on either side of every phase (ARGUS_BA_PROFILE)
+    bool capture_prof = false;
     int64_t graph_launches = 0, graph_allreduces = 0;
     // profile
     bool profiling = false, capturing = false;
     struct Ev { int id; cudaEvent_t a, b; };
     std::vector<Ev> evs;
+    std::vector<Ev> graph_evs;                     // events recorded by the nodes of graph_exec_prof: hold the times of its LAST replay
     std::vector<cudaEvent_t> ev_pool;
     double prof_ms[P_COUNT]; int64_t prof_n[P_COUNT];
     int64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0, n_allreduce = 0;
@@ -232,10 +237,13 @@ cudaEvent_t get_event(argus_ba_ctx *c)
 }
 struct ProfScope {
     argus_ba_ctx *c; int id; cudaEvent_t a = nullptr, b = nullptr; bool on;
-    ProfScope(argus_ba_ctx *c_, int id_) : c(c_), id(id_), on(c_->profiling && !c_->capturing) {
-        if (on) { a = get_event(c); b = get_event(c); cudaEventRecord(a, c->stream); }
+    ProfScope(argus_ba_ctx *c_, int id_) : c(c_), id(id_), on(c_->capturing ? c_->capture_prof : c_->profiling) {
+        if (on) { a = get_event(c); b = get_event(c); rec(a); }
     }
-    ~ProfScope() { if (on) { cudaEventRecord(b, c->stream); c->evs.push_back({id, a, b}); } }
+    ~ProfScope() { if (on) { rec(b); (c->capturing ? c->graph_evs : c->evs).push_back({id, a, b}); } }
+    // while capturing, cudaEventRecordExternal makes the call an event-record NODE of the graph (a plain record only expresses a
+    // dependency between captured streams)
+    void rec(cudaEvent_t e) { if (c->capturing) cudaEventRecordWithFlags(e, c->stream, cudaEventRecordExternal); else cudaEventRecord(e, c->stream); }
 };
 void prof_collect(argus_ba_ctx *c)
 {
@@ -252,6 +260,9 @@ void prof_collect(argus_ba_ctx *c)
 void drop_graph(argus_ba_ctx *c)
 {
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    if (c->graph_exec_prof) { cudaGraphExecDestroy(c->graph_exec_prof); c->graph_exec_prof = nullptr; }
+    for (auto &e : c->graph_evs) { c->ev_pool.push_back(e.a); c->ev_pool.push_back(e.b); }
+    c->graph_evs.clear();
 }
 
 // one collective step: every (buffer, count, op) of the list is reduced over the ranks, in place, on the solver's stream
@@ -303,7 +314,7 @@ int enqueue_lin(argus_ba_ctx *c, int mode)
 {
     const int m = c->m;
     {
-        ProfScope ps(c, P_LINEARIZE);
+        ProfScope ps(c, mode ? P_LINEARIZE : P_LIN_STATS);
 #define LIN_LAUNCH(MC_) k_lin_tile<MC_><<<c->grid_lin, 256, c->lin_smem, c->stream>>>(c->problem(), c->tile_plan(), c->lin_plan(), c->pbufs(), c->st.p, mode, c->lin_out())
         const int mc = (m - c->mcon + 7) / 8;
         if (mc <= 2) LIN_LAUNCH(2); else if (mc <= 4) LIN_LAUNCH(4); else LIN_LAUNCH(8);
@@ -484,20 +495,22 @@ int enqueue_attempt(argus_ba_ctx *c)
 }
 
 // capture one attempt into a graph; on any failure the solver simply keeps launching kernels directly
-void capture_attempt_graph(argus_ba_ctx *c)
+void capture_attempt_graph(argus_ba_ctx *c, bool prof)
 {
-    drop_graph(c);
+    cudaGraphExec_t &ge = prof ? c->graph_exec_prof : c->graph_exec;
+    if (ge) { cudaGraphExecDestroy(ge); ge = nullptr; }
+    if (prof) { for (auto &e : c->graph_evs) { c->ev_pool.push_back(e.a); c->ev_pool.push_back(e.b); } c->graph_evs.clear(); }
     const int64_t l0 = c->launches, a0 = c->n_allreduce;
     if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); c->use_graph = false; return; }
-    c->capturing = true;
+    c->capturing = true; c->capture_prof = prof;
     const int rc = enqueue_attempt(c);
-    c->capturing = false;
+    c->capturing = false; c->capture_prof = false;
     cudaGraph_t g = nullptr;
     const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
     c->graph_launches = c->launches - l0; c->graph_allreduces = c->n_allreduce - a0;
     c->launches = l0; c->n_allreduce = a0;
     if (rc != ARGUS_OK || e != cudaSuccess || !g) { if (g) cudaGraphDestroy(g); cudaGetLastError(); c->use_graph = false; return; }
-    if (cudaGraphInstantiate(&c->graph_exec, g, 0) != cudaSuccess) { cudaGetLastError(); c->graph_exec = nullptr; c->use_graph = false; }
+    if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) { cudaGetLastError(); ge = nullptr; c->use_graph = false; }
     cudaGraphDestroy(g);
 }
 
@@ -619,6 +632,7 @@ void argus_ba_destroy(argus_ba_ctx *c)
     for (auto &e : c->evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (int q = 0; q < kSnap; ++q) if (c->snap_ev[q]) cudaEventDestroy(c->snap_ev[q]);
     arena_give(c->device, c->arena.base, c->arena.size);
+    if (c->copy_stream) { cudaStreamDestroy(c->copy_stream); cudaEventDestroy(c->copy_ev[0]); cudaEventDestroy(c->copy_ev[1]); }
     if (c->h_snap) pinned_give(c->h_snap);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -709,22 +723,44 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     std::vector<uint8_t> slot0((size_t)n);
     int64_t nobs = 0, nrows = 0, hits_bound = 0;
     {
-        int64_t i = 0;
-        while (i < n) {
-            tiles.push_back((int32_t)i); tile_o.push_back((int32_t)nobs); tile_r.push_back((int32_t)nrows);
-            int fill[4] = {0, 0, 0, 0}, npts = 0, acc = 0;
-            while (i < n && npts < kTilePts) {
-                const int v = cnt[i];
-                int cl = 0;
-                for (int q = 1; q < 4; ++q) if (fill[q] < fill[cl]) cl = q;        // emptiest class, lowest id on ties
-                if (fill[cl] + v > kClassCap) break;
-                slot0[i] = (uint8_t)(4 * fill[cl] + cl);
-                fill[cl] += v; acc += v; ++npts; ++i;
-                hits_bound += (int64_t)v * (v + 1) / 2;
+        // the points are cut into segments of a FIXED length (so that the tiling, and with it every summation order, does not
+        // depend on how many host threads there are); the segments are planned in parallel, a tile never spans two of them
+        constexpr int64_t kSeg = 32768;
+        const int64_t nseg = (n + kSeg - 1) / kSeg;
+        struct SegPlan { std::vector<int32_t> first, obs, rows; int64_t hits = 0; };
+        std::vector<SegPlan> seg((size_t)nseg);
+        parallel_for(nseg, c->world, [&](int64_t lo, int64_t hi) {
+            for (int64_t sgi = lo; sgi < hi; ++sgi) {
+                SegPlan &sp = seg[(size_t)sgi];
+                const int64_t end = std::min(n, (sgi + 1) * kSeg);
+                int64_t i = sgi * kSeg;
+                while (i < end) {
+                    sp.first.push_back((int32_t)i);
+                    int fill[4] = {0, 0, 0, 0}, npts = 0, acc = 0;
+                    while (i < end && npts < kTilePts) {
+                        const int v = cnt[i];
+                        int cl = 0;
+                        for (int q = 1; q < 4; ++q) if (fill[q] < fill[cl]) cl = q;        // emptiest class, lowest id on ties
+                        if (fill[cl] + v > kClassCap) break;
+                        slot0[i] = (uint8_t)(4 * fill[cl] + cl);
+                        fill[cl] += v; acc += v; ++npts; ++i;
+                        sp.hits += (int64_t)v * (v + 1) / 2;
+                    }
+                    sp.obs.push_back(acc);
+                    sp.rows.push_back(4 * std::max(std::max(fill[0], fill[1]), std::max(fill[2], fill[3])));
+                }
             }
-            nobs += acc;
-            nrows += 4 * std::max(std::max(fill[0], fill[1]), std::max(fill[2], fill[3]));
-            if (nrows > 0x7fffffffLL) return ARGUS_E_ARG;
+        }, 1);
+        size_t nt = 0;
+        for (auto &sp : seg) nt += sp.first.size();
+        tiles.reserve(nt + 1); tile_o.reserve(nt + 1); tile_r.reserve(nt + 1);
+        for (auto &sp : seg) {
+            for (size_t t = 0; t < sp.first.size(); ++t) {
+                tiles.push_back(sp.first[t]); tile_o.push_back((int32_t)nobs); tile_r.push_back((int32_t)nrows);
+                nobs += sp.obs[t]; nrows += sp.rows[t];
+                if (nrows > 0x7fffffffLL || nobs > 0x7fffffffLL) return ARGUS_E_ARG;
+            }
+            hits_bound += sp.hits;
         }
         tiles.push_back((int32_t)n); tile_o.push_back((int32_t)nobs); tile_r.push_back((int32_t)nrows);
         c->ntiles = (int)tiles.size() - 1;
@@ -821,10 +857,22 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
     } else {
         ARGUS_CUDA_CHECK(cudaMemsetAsync(c->obs_ptr.p, 0, sizeof(int32_t), s));
     }
-    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_uv.p, x, nobs * sizeof(double2), cudaMemcpyHostToDevice, s));
+    // the two large host arrays (measurements, points: 368 of the 400 MB at config 4) travel on a second stream while the
+    // visibility index, the block assignment and the hit lists - which need neither - are built; k_build_tile_index waits for them
+    if (!c->copy_stream) {
+        ARGUS_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        ARGUS_CUDA_CHECK(cudaEventCreateWithFlags(&c->copy_ev[0], cudaEventDisableTiming));
+        ARGUS_CUDA_CHECK(cudaEventCreateWithFlags(&c->copy_ev[1], cudaEventDisableTiming));
+    }
+    // (the small copies first: one copy engine serves both streams in issue order, and the solver's stream is synchronised for
+    // the hit histogram long before the large ones are through)
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->rot0.p, rot0, 4 * m * sizeof(double), cudaMemcpyHostToDevice, s));
     ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->cam0.p, p, 16 * m * sizeof(double), cudaMemcpyHostToDevice, s));
-    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pts0.p, p + 16 * m, 3 * n * sizeof(double), cudaMemcpyHostToDevice, s));
+    ARGUS_CUDA_CHECK(cudaEventRecord(c->copy_ev[0], s));                       // (earlier work on the solver's stream may still use the buffers)
+    ARGUS_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->copy_ev[0], 0));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->obs_uv.p, x, nobs * sizeof(double2), cudaMemcpyHostToDevice, c->copy_stream));
+    ARGUS_CUDA_CHECK(cudaMemcpyAsync(c->pts0.p, p + 16 * m, 3 * n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    ARGUS_CUDA_CHECK(cudaEventRecord(c->copy_ev[1], c->copy_stream));
     {
         // Every warp of the Schur kernel keeps its blocks for the whole launch and the warps of a CTA advance tile by tile
         // together (two shared-memory stages), so the slowest warp sets the pace: deal the blocks by weight.  Weight = hits of
@@ -908,8 +956,6 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         ARGUS_CUDA_CHECK(cudaMemsetAsync(c->row_info.p, 0xFF, (size_t)nrows * sizeof(uint32_t), s));
         ARGUS_CUDA_CHECK(cudaMemsetAsync(c->row_uv.p, 0, (size_t)nrows * sizeof(double2), s));
         ARGUS_CUDA_CHECK(cudaMemsetAsync(c->zs.p, 0, (size_t)c->ntiles * 256, s));
-        k_build_tile_index<<<c->ntiles, 256, 0, s>>>(m, c->tile_pt.p, c->tile_o.p, c->tile_r.p, c->obs_ptr.p, c->obs_cam.p, c->obs_uv.p, c->pt_slot0.p,
-                                                     c->corder.p, c->cstart.p, c->row_info.p, c->row_uv.p);
         if (c->mode == kModeMotStr) {
             const int G = c->schur_G, nslots = c->schur_NW * c->schur_NB, ntg = c->ntiles * G;
             k_hits_count<<<c->ntiles, 256, (size_t)G * sizeof(int), s>>>(c->ntiles, G, nslots, c->tile_pt.p, ncon, c->pt_mask.p, c->pt_slot0.p,
@@ -917,9 +963,15 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
             k_index_scan<<<1, 1024, 0, s>>>(ntg, c->hit_ptr.p);
             k_hits_fill<<<c->ntiles, 256, (size_t)G * nslots * sizeof(int), s>>>(c->ntiles, G, nslots, c->tile_pt.p, ncon, c->pt_mask.p,
                                                                                c->pt_slot0.p, c->blk_jk.p, c->tile_r.p, c->hit_ptr.p, c->hit_blob.p);
-            // the padding chunks of Z travel to shared memory with every tile: keep them defined
-            ARGUS_CUDA_CHECK(cudaMemsetAsync(c->Z.p, 0, (size_t)48 * (nrows + c->ntiles) * sizeof(double), s));
+            // Z itself needs no initialisation: the lineariser writes every row that holds an observation before the Schur
+            // kernel runs, the hit lists name only such rows, and the unused rows and the padding chunk of every plane travel to
+            // shared memory without ever being read from there
         }
+    }
+    ARGUS_CUDA_CHECK(cudaStreamWaitEvent(s, c->copy_ev[1], 0));               // measurements and points have arrived
+    if (n > 0 && c->ntiles > 0) {
+        k_build_tile_index<<<c->ntiles, 256, 0, s>>>(m, c->tile_pt.p, c->tile_o.p, c->tile_r.p, c->obs_ptr.p, c->obs_cam.p, c->obs_uv.p, c->pt_slot0.p,
+                                                     c->corder.p, c->cstart.p, c->row_info.p, c->row_uv.p);
         ARGUS_CUDA_CHECK(cudaGetLastError());
     }
     ARGUS_CUDA_CHECK(cudaStreamSynchronize(s));      // host staging vectors go out of scope
@@ -1136,20 +1188,29 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
     // damping attempts: queued kDepth ahead of the last one whose outcome has been seen.  Attempt q is queued only after
     // attempt q - kDepth - 1 is known not to have ended the loop - a rule every rank follows identically, so that all ranks
     // queue the same number of (collective-carrying) attempts; attempts queued behind the end of the loop return at once.
-    const bool graph = c->use_graph && !c->profiling && (c->world == 1 || c->nccl != nullptr);
-    if (graph && !c->graph_exec) capture_attempt_graph(c);
-    int queued = 0, confirmed = 0;
+    // ARGUS_BA_PROFILE: every kProfEvery-th attempt is replayed from a second graph that has an event-record node on either side
+    // of every phase.  Before such a replay the host waits for the outcome of everything queued so far, so that it is a real
+    // attempt (not one queued behind the end of the loop) and its events - the ones that can be read after the solve - hold the
+    // times of real work; the other attempts run as always.
+    const bool graph = c->use_graph && (c->world == 1 || c->nccl != nullptr);
+    if (graph && !c->graph_exec) capture_attempt_graph(c, false);
+    const bool prof_graph = c->profiling && graph && c->graph_exec;
+    if (prof_graph && !c->graph_exec_prof) capture_attempt_graph(c, true);
+    int queued = 0, confirmed = 0, last_prof = -1;
     bool done = false;
-    std::vector<size_t> ev_mark;          // profiling: first event of each attempt (attempts queued behind the end are dropped)
+    std::vector<size_t> ev_mark;          // profiling without graphs: first event of each attempt (attempts queued behind the end are dropped)
     while (!done) {
-        while (queued - confirmed > kDepth) {
+        const bool prof_this = prof_graph && c->graph_exec_prof && (queued % kProfEvery == kProfEvery - 1);
+        const int depth = prof_this ? 0 : kDepth;
+        while (queued - confirmed > depth) {
             ARGUS_CUDA_CHECK(cudaEventSynchronize(c->snap_ev[confirmed % kSnap]));
             if (c->h_snap[confirmed % kSnap].done) { done = true; break; }
             ++confirmed;
         }
         if (done) break;
         if (graph && c->graph_exec) {
-            ARGUS_CUDA_CHECK(cudaGraphLaunch(c->graph_exec, s));
+            ARGUS_CUDA_CHECK(cudaGraphLaunch(prof_this ? c->graph_exec_prof : c->graph_exec, s));
+            if (prof_this) last_prof = queued;
             c->launches += c->graph_launches; c->n_allreduce += c->graph_allreduces;
         } else {
             if (c->profiling) ev_mark.push_back(c->evs.size());
@@ -1170,6 +1231,11 @@ int argus_ba_solve(argus_ba_ctx *c, int itmax, int verbose, const double opts[5]
             c->evs.resize(ev_mark[confirmed + 1]);
         }
         prof_collect(c);
+        if (prof_graph && last_prof >= 0)                      // per-phase times of the last profiled attempt (one sample per phase and solve)
+            for (auto &e : c->graph_evs) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) { c->prof_ms[e.id] += ms; c->prof_n[e.id] += 1; } else cudaGetLastError();
+            }
     }
 
     const double nvis = gc[0];

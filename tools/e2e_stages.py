@@ -1,0 +1,20 @@
+"""Where the time of a one-shot call goes (create / upload / solve / download / destroy through the resident API), per workload."""
+import sys, time; sys.path.insert(0, '/root/repo')
+import numpy as np, torch
+import bench
+from argus_gui_b200 import ba
+for wl in sys.argv[1:] or ["c4r8", "c4"]:
+    s, p0, rot0, (m, n, views, nk, nd) = bench.make_scene(wl, 0)
+    hp = torch.from_numpy(p0.copy()).pin_memory().numpy(); hx = torch.from_numpy(np.ascontiguousarray(s["x"])).pin_memory().numpy()
+    hv = torch.from_numpy(np.ascontiguousarray(s["vmask"]).view(np.int8)).pin_memory().numpy()
+    best = None
+    for rep in range(4):
+        t = [time.perf_counter()]
+        B = ba.BundleAdjuster(device=0); t.append(time.perf_counter())
+        B.upload(hv, hp, rot0, hx, nk, nd); t.append(time.perf_counter())
+        B.solve(itmax=10, opts=bench.OPTS_FIXED_WORK); t.append(time.perf_counter())
+        B.download(out=hp.copy()); t.append(time.perf_counter())
+        B.close(); t.append(time.perf_counter())
+        st = [1e3 * (b - a) for a, b in zip(t, t[1:])]
+        best = st if best is None else [min(a, b) for a, b in zip(best, st)]
+    print("%s (%d observations): create %.2f upload %.2f solve %.2f download %.2f close %.2f ms" % ((wl, s["nobs"]) + tuple(best)))

@@ -18,5 +18,5 @@ for w in (0.0, 1000.0):
         B.reset(); ret, info = B.solve(itmax=10, opts=bench.OPTS_FIXED_WORK)
     e1.record(); e1.synchronize()
     B.reset(); B.solve(itmax=10, opts=bench.OPTS_FIXED_WORK, profile=True)
-    print("weight", w, "ms/iter %.3f" % (e0.elapsed_time(e1) / 30), {k: round(v[0] / 10, 4) for k, v in B.profile().items() if v[1]})
+    print("weight", w, "ms/iter %.3f" % (e0.elapsed_time(e1) / 30), {k: round(v[0] / v[1], 4) for k, v in B.profile().items() if v[1]})
 B.close()
