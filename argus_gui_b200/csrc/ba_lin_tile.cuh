@@ -175,6 +175,14 @@ __device__ __forceinline__ void st_global_v4(double *p, double a, double b, doub
     asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
+#ifdef ARGUS_LIN_TRACE
+// debug builds only (tools/lin_trace.py): clock64 stamps per (CTA < 2, tile of the CTA < 64, warp, phase boundary)
+__device__ long long *g_lin_trace = nullptr;
+#define LIN_TRACE(slot_) do { if (g_lin_trace && blockIdx.x < 2 && lane == 0 && ltile < 64) \
+    g_lin_trace[(((size_t)blockIdx.x * 64 + ltile) * 8 + warp) * 10 + (slot_)] = clock64(); } while (0)
+#else
+#define LIN_TRACE(slot_) do { } while (0)
+#endif
 template <int MC>
 __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem pb, TilePlan tp, LinTilePlan lp, ParamBufs pbuf,
                                                   const LmState *__restrict__ st, int mode, LinTileOut out)
@@ -214,7 +222,14 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
         nx_p0 = tp.tile_pt[blockIdx.x]; nx_p1 = tp.tile_pt[blockIdx.x + 1]; nx_o0 = tp.tile_o[blockIdx.x]; nx_o1 = tp.tile_o[blockIdx.x + 1];
         nx_r0 = tp.tile_r[blockIdx.x]; nx_r1 = tp.tile_r[blockIdx.x + 1];
     }
+#ifdef ARGUS_LIN_TRACE
+    int ltile = -1;
+#endif
     for (int tile = blockIdx.x; tile < tp.ntiles; tile += gridDim.x) {
+#ifdef ARGUS_LIN_TRACE
+        ++ltile;
+#endif
+        LIN_TRACE(0);
         const int p0 = nx_p0, npts = nx_p1 - nx_p0;
         const int o0 = nx_o0, nobs_t = nx_o1 - nx_o0;
         const int r0 = nx_r0, nrows_t = nx_r1 - nx_r0;
@@ -235,6 +250,7 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
         if (tid < npts) { const int64_t i = p0 + tid; s_M[3 * tid] = pts[3 * i]; s_M[3 * tid + 1] = pts[3 * i + 1]; s_M[3 * tid + 2] = pts[3 * i + 2]; }
         if (tid <= pb.m) s_cst[tid] = lp.cstart[(size_t)tile * (pb.m + 1) + tid];
         __syncthreads();
+        LIN_TRACE(1);
 
         // ---- P1: one thread per observation ----
         if (act) {
@@ -278,7 +294,9 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
             if (tid >= 32 && tid < 40 && (tid - 32) * 16 < 3 * np + 15) prefetch_l2(pts + 3 * (int64_t)nx_p0 + (tid - 32) * 16);
             if (tid == 64) { prefetch_l2(pb.obs_ptr + nx_p0); prefetch_l2(pb.obs_ptr + nx_p0 + 31); prefetch_l2(lp.cstart + (size_t)ntile * (pb.m + 1)); }
         }
+        LIN_TRACE(2);
         __syncthreads();
+        LIN_TRACE(3);
 
         // ---- P2: 8 threads per point ----
         {
@@ -352,7 +370,9 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                 }
             }
         }
+        LIN_TRACE(4);
         __syncthreads();
+        LIN_TRACE(5);
 
         // ---- P3: per observation: e' and Z ----
         if (mode != 0) out.zs[(size_t)tile * 256 + tid] = act ? (uint8_t)(int)Ps[my_lp * kPs + 9] : (uint8_t)0;
@@ -390,7 +410,9 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                 st_global_v4(zp + 2 * zpl, zz[8], zz[9], zz[10], zz[11]);
             }
         }
+        LIN_TRACE(6);
         __syncthreads();
+        LIN_TRACE(7);
 
         // ---- P4: Gram per camera on the tensor pipe (the cameras a warp owns advance together: independent DMMA chains) ----
         {
@@ -427,7 +449,9 @@ __global__ void __launch_bounds__(256, (MC <= 4) ? 2 : 1) k_lin_tile(BaProblem p
                 }
             }
         }
+        LIN_TRACE(8);
         __syncthreads();
+        LIN_TRACE(9);
     }
 
     {   // per-CTA Gram fragments; cameras nobody owns (fixed ones) are written as zeros

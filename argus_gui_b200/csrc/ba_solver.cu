@@ -534,6 +534,9 @@ int global_counts(argus_ba_ctx *c, double out[3])
 
 extern "C" {
 
+#ifdef ARGUS_LIN_TRACE
+int argus_debug_set_lin_trace(long long *dev_ptr) { return cudaMemcpyToSymbol(g_lin_trace, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? 0 : -1; }
+#endif
 #ifdef ARGUS_SCHUR_TRACE
 int argus_debug_set_schur_trace(long long *dev_ptr) { return cudaMemcpyToSymbol(g_schur_trace, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? 0 : -1; }
 #endif
