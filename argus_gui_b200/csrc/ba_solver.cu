@@ -778,10 +778,12 @@ int argus_ba_upload(argus_ba_ctx *c, int64_t n, int64_t ncon, int m, int mcon, c
         int nch = c->sms / c->schur_G; if (nch < 1) nch = 1;
         if (nch > c->ntiles) nch = c->ntiles > 0 ? c->ntiles : 1;
         c->schur_nchunk = nch;
-        // tiles a group CTA may run ahead of the slowest group of its chunk: as many as half of the L2 holds over all chunks
+        // tiles a group CTA may run ahead of the slowest group of its chunk: as many as a QUARTER of the L2 holds over all chunks
+        // (measured: with half of it - 9 tiles at config 4 - the second CTA misses again; the L2 is two partitions and lines
+        // read from the far one are held twice)
         int l2 = 0; cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, c->device);
         const double tile_bytes = 384.0 * kTileRows;
-        int slack = (int)(0.5 * (double)l2 / ((double)nch * tile_bytes));
+        int slack = (int)(0.25 * (double)l2 / ((double)nch * tile_bytes));
         c->pace_slack = slack < 2 ? 0 : (slack > 64 ? 64 : slack);
     }
     // corder, cstart, row_info / row_uv and the hit lists are derived on the device (k_index_*, k_build_tile_index, k_hits_*)
