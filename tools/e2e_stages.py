@@ -18,3 +18,9 @@ for wl in sys.argv[1:] or ["c4r8", "c4"]:
         st = [1e3 * (b - a) for a, b in zip(t, t[1:])]
         best = st if best is None else [min(a, b) for a, b in zip(best, st)]
     print("%s (%d observations): create %.2f upload %.2f solve %.2f download %.2f close %.2f ms" % ((wl, s["nobs"]) + tuple(best)))
+    one = []
+    for rep in range(5):
+        t0 = time.perf_counter()
+        ba.solve_motstr(hv, hp, rot0, hx, nk, nd, itmax=10, opts=bench.OPTS_FIXED_WORK, inplace=True)
+        one.append(1e3 * (time.perf_counter() - t0))
+    print("   one-shot argus_ba_motstr_kdrts, 5 calls: " + " ".join("%.1f" % v for v in one) + " ms")
