@@ -568,25 +568,36 @@ def main():
         sampler = ClockSampler(local); sampler.start()
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        # N = 1: the per-phase CUDA events are taken INSIDE the timed region (event-record nodes in every fourth attempt's graph;
+        # the cost is below 0.1 %).  N > 1: the host wait in front of such an attempt lets the ranks drift apart before a
+        # collective (measured: 7 % at 2 GPUs), so the timed region is the product path as it is and the per-phase events come
+        # from a second pass of the same steps right after it.
         prof = {}
+        prof_in_timed = world == 1
+
+        def run_steps(profile):
+            last = None
+            for _ in range(args.steps):
+                B.reset(); ret_, info_ = B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK, profile=profile)
+                assert ret_ == ITERS_PER_STEP and int(info_[5]) == ITERS_PER_STEP, (ret_, info_)
+                if profile:
+                    for kname, (ms, cnt) in B.profile().items():
+                        a = prof.setdefault(kname, [0.0, 0]); a[0] += ms; a[1] += cnt
+                last = info_
+            return last
         e0.record(stream)
-        for _ in range(args.steps):
-            B.reset(); ret, info = B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK, profile=True)
-            assert ret == ITERS_PER_STEP and int(info[5]) == ITERS_PER_STEP, (ret, info)
-            for kname, (ms, cnt) in B.profile().items():
-                a = prof.setdefault(kname, [0.0, 0]); a[0] += ms; a[1] += cnt
+        info = run_steps(prof_in_timed)
         e1.record(stream)
         barrier()
         clocks = sampler.stop()
         ms_total = e0.elapsed_time(e1)
         c1 = B.counters()
-        # the same steps replayed as CUDA graphs (no per-kernel events): what a resident user gets
+        # second pass of the same steps: N = 1 without the event nodes and with attempts queued two ahead throughout; N > 1 with them
         barrier()
         g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
-        B.reset(); B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+        B.reset(); B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK, profile=not prof_in_timed)
         g0.record(stream)
-        for _ in range(args.steps):
-            B.reset(); ret, info_g = B.solve(itmax=ITERS_PER_STEP, opts=OPTS_FIXED_WORK)
+        run_steps(not prof_in_timed)
         g1.record(stream)
         barrier()
         ms_graph = g0.elapsed_time(g1)
@@ -657,6 +668,7 @@ def main():
     except Exception:
         pass
     rl["ms_per_launch"] = dom_ms
+    rl["events_from"] = "the timed region (event-record nodes in every fourth attempt's graph)" if world == 1 else "a second pass of the same steps right after the timed region"
     rl["share_of_kernel_time"] = kern[dom][0] / sum_ms
     t_iter = ms_total * 1e-3 / (ITERS_PER_STEP * args.steps)
     flops_iter_job = counts["flops_iter"] * (1 if strong else world)
@@ -664,7 +676,7 @@ def main():
     rl["iteration"] = {"ms": t_iter * 1e3, "fp64_frac": flops_iter_job / t_iter / 1e12 / (dmma_peak * world),
                        "hbm_frac": bytes_iter_job / t_iter / 1e9 / (hbm_peak * world),
                        "algorithmic_gflop": flops_iter_job / 1e9, "algorithmic_gbyte": bytes_iter_job / 1e9,
-                       "ms_graph_replay": ms_graph / (ITERS_PER_STEP * args.steps)}
+                       ("ms_graph_replay" if world == 1 else "ms_profiled_pass"): ms_graph / (ITERS_PER_STEP * args.steps)}
     # one sample per phase and step: event-record nodes inside the captured attempt hold the times of the step's last attempt
     rl["kernels_ms_per_iteration"] = {k_: (v[0] / v[1] if v[1] else 0.0) for k_, v in sorted(prof.items()) if k_ not in ("residual", "linearize_stats")}
     rl["once_per_solve_ms"] = {k_: v[0] / v[1] for k_, v in sorted(prof.items()) if v[1] and k_ in ("residual", "linearize_stats")}
@@ -718,9 +730,12 @@ def main():
                            "final_cost": final_cost},
                 "convergence": conv,
                 "lm_iters_per_sec": ITERS_PER_STEP * args.steps / (ms_total * 1e-3),
-                "graph_replay": {"value": total_obs * ITERS_PER_STEP * args.steps / (ms_graph * 1e-3), "unit": "obs*iters/s",
-                                 "note": "same steps without the event-record nodes and with attempts queued two ahead (the timed region waits for "
-                                         "every attempt's outcome so that the per-phase events it reads are those of a real attempt)"},
+                ("graph_replay" if world == 1 else "profiled_pass"):
+                    {"value": total_obs * ITERS_PER_STEP * args.steps / (ms_graph * 1e-3), "unit": "obs*iters/s",
+                     "note": ("same steps without the event-record nodes (the timed region carries them in every fourth attempt and waits for the "
+                              "outcome of the attempts before it)") if world == 1 else
+                             ("same steps with event-record nodes in every fourth attempt: the source of roofline.kernels_ms_per_iteration at "
+                              "N > 1, where the timed region runs without them")},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(c1["launches"] - c0["launches"]),
                 "allreduces": int(c1["allreduces"] - c0["allreduces"]), "roofline": rl, "cpu_baseline": cpu, "blockdiag": bd_res, "pair_init": pair_res,
                 "configs": extras, "dlt": dlt_res}
