@@ -59,7 +59,11 @@ extern "C" {
                                      not restored (SBA/sba_levmar.c:1339-1353 is #if 0) and V's diagonal holds the
                                      inverse's diagonal (SBA/sba_lapack.c:1118-1121).  Without it the diagonals are
                                      restored (textbook LM). */
-#define ARGUS_BA_PROFILE       2  /* record per-kernel CUDA-event times (argus_ba_get_profile)             */
+#define ARGUS_BA_PROFILE       2  /* record per-phase CUDA-event times (argus_ba_get_profile): every fourth damping
+                                     attempt is replayed from a graph with an event-record node on either side of every
+                                     phase, after the host has seen the outcome of the attempts before it; the profile
+                                     holds ONE sample per phase and solve (the last such attempt), plus the once-per-solve
+                                     phases (initial cost, statistics-only linearisation)                              */
 
 typedef struct argus_ba_ctx argus_ba_ctx;
 
@@ -143,8 +147,8 @@ int  argus_ba_solve(argus_ba_ctx *ctx, int itmax, int verbose, const double opts
 int  argus_ba_download(argus_ba_ctx *ctx, double *p);
 int64_t argus_ba_num_observations(const argus_ba_ctx *ctx);
 
-/* profile of the last solve: names[i] (static strings), total ms and launch count per kernel; returns the
- * number of entries written (<= cap). */
+/* profile of the last solve (ARGUS_BA_PROFILE): names[i] (static strings), summed ms and number of samples per phase;
+ * returns the number of entries written (<= cap). */
 int  argus_ba_get_profile(argus_ba_ctx *ctx, const char **names, double *ms, int64_t *launches, int cap);
 
 /* counters since creation: out = {kernel launches, all-reduce calls, host->device bytes, device->host bytes} */
