@@ -8,7 +8,7 @@ for wl in sys.argv[1:] or ["c4r8", "c4"]:
     hp = torch.from_numpy(p0.copy()).pin_memory().numpy(); hx = torch.from_numpy(np.ascontiguousarray(s["x"])).pin_memory().numpy()
     hv = torch.from_numpy(np.ascontiguousarray(s["vmask"]).view(np.int8)).pin_memory().numpy()
     best = None
-    for rep in range(4):
+    for rep in range(2):
         t = [time.perf_counter()]
         B = ba.BundleAdjuster(device=0); t.append(time.perf_counter())
         B.upload(hv, hp, rot0, hx, nk, nd); t.append(time.perf_counter())
@@ -19,8 +19,8 @@ for wl in sys.argv[1:] or ["c4r8", "c4"]:
         best = st if best is None else [min(a, b) for a, b in zip(best, st)]
     print("%s (%d observations): create %.2f upload %.2f solve %.2f download %.2f close %.2f ms" % ((wl, s["nobs"]) + tuple(best)))
     one = []
-    for rep in range(5):
+    for rep in range(12):
         t0 = time.perf_counter()
         ba.solve_motstr(hv, hp, rot0, hx, nk, nd, itmax=10, opts=bench.OPTS_FIXED_WORK, inplace=True)
         one.append(1e3 * (time.perf_counter() - t0))
-    print("   one-shot argus_ba_motstr_kdrts, 5 calls: " + " ".join("%.1f" % v for v in one) + " ms")
+    print("   one-shot argus_ba_motstr_kdrts, 12 calls: " + " ".join("%.1f" % v for v in one) + " ms")
